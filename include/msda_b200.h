@@ -1,0 +1,134 @@
+/*
+ * msda_b200.h -- C ABI of the B200-native (sm_100a) multi-scale deformable
+ * attention library, libmsda_b200.so.
+ *
+ * This is the drop-in boundary for the one hot path of
+ * HI-ComputerVision/uni-encoder-code that this repository replaces: the two
+ * functions its pybind11 module `MultiScaleDeformableAttention` exports
+ * (reference: model/modeling/pixel_decoder/ops/src/vision.cpp:18-21, dispatch in
+ * ops/src/ms_deform_attn.h:25-66, host wrappers in
+ * ops/src/cuda/ms_deform_attn_cuda.cu:25-85 and :88-158).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer
+ *     (the reference requires CUDA tensors: ms_deform_attn_cuda.cu:39-43);
+ *   - all tensors contiguous, row-major (ms_deform_attn_cuda.cu:33-37):
+ *       value          [batch, spatial_size, num_heads, channels]
+ *       spatial_shapes [num_levels, 2]  int64 (H_l, W_l), on the device
+ *       level_start    [num_levels]     int64,            on the device
+ *       sampling_loc   [batch, num_query, num_heads, num_levels, num_point, 2]
+ *                      normalised (x, y), x first (ms_deform_im2col_cuda.cuh:286-287)
+ *       attn_weight    [batch, num_query, num_heads, num_levels, num_point]
+ *       output / grad_output [batch, num_query, num_heads * channels]
+ *   - `stream` is a cudaStream_t passed as void* (the reference launches on the
+ *     caller's current stream, ms_deform_attn_cuda.cu:70,140); the library never
+ *     synchronises the device, allocates or frees, and keeps no mutable state
+ *     that affects results: calls are re-entrant and CUDA-graph capturable;
+ *   - one launch covers the whole batch with 64-bit base offsets; the
+ *     reference's im2col_step chunk loop (ms_deform_attn_cuda.cu:55-80) is a
+ *     host-side concern handled (validated, then ignored) by the Python shim;
+ *   - return value: 0 on success, a negative MSDA_ERR_* for argument errors, a
+ *     positive cudaError_t if the launch failed (the reference only printf()s
+ *     launch errors, ms_deform_im2col_cuda.cuh:953-957; we report them).
+ */
+#ifndef MSDA_B200_H_
+#define MSDA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSDA_B200_ABI_VERSION 1
+
+enum {
+    MSDA_OK = 0,
+    MSDA_ERR_NULL_POINTER = -1,   /* a required pointer is NULL                      */
+    MSDA_ERR_BAD_SHAPE = -2,      /* a size is <= 0 or exceeds a supported bound     */
+    MSDA_ERR_UNSUPPORTED = -3,    /* e.g. num_levels > MSDA_MAX_LEVELS               */
+    MSDA_ERR_BAD_OPTION = -4      /* msda_b200_set_option: unknown name / bad value  */
+};
+
+#define MSDA_MAX_LEVELS 16        /* level table kept in shared memory               */
+
+/* Library / ABI identification. */
+int msda_b200_abi_version(void);
+/* Human-readable text for a code returned by any function here. */
+const char *msda_b200_error_string(int code);
+/* Number of kernel launches issued through this library since load (all
+ * streams); bench.py reports the delta over its timed region as gpu_launches. */
+long long msda_b200_launch_count(void);
+
+/*
+ * Forward.  Replaces ms_deform_attn_cuda_forward (ms_deform_attn_cuda.cu:25-85)
+ * + ms_deformable_im2col_cuda (ms_deform_im2col_cuda.cuh:928-959) + the kernel
+ * ms_deformable_im2col_gpu_kernel (cuh:242-304).
+ * `output` is fully overwritten (no zero-fill needed; cf. at::zeros at cu:59).
+ */
+int msda_b200_forward_f32(const float *value, const int64_t *spatial_shapes,
+                          const int64_t *level_start, const float *sampling_loc,
+                          const float *attn_weight, int batch, int spatial_size,
+                          int num_heads, int channels, int num_levels, int num_query,
+                          int num_point, float *output, void *stream);
+int msda_b200_forward_f64(const double *value, const int64_t *spatial_shapes,
+                          const int64_t *level_start, const double *sampling_loc,
+                          const double *attn_weight, int batch, int spatial_size,
+                          int num_heads, int channels, int num_levels, int num_query,
+                          int num_point, double *output, void *stream);
+
+/*
+ * Backward.  Replaces ms_deform_attn_cuda_backward (ms_deform_attn_cuda.cu:88-158)
+ * + ms_deformable_col2im_cuda (cuh:961-1331) + the seven col2im kernels
+ * (cuh:306-925).
+ * `grad_value` MUST be zero on entry (it is accumulated with reductions, like
+ * the reference's at::zeros_like at cu:126); `grad_sampling_loc` and
+ * `grad_attn_weight` are fully overwritten (no zero-fill needed, cf. cu:127-128).
+ */
+int msda_b200_backward_f32(const float *grad_output, const float *value,
+                           const int64_t *spatial_shapes, const int64_t *level_start,
+                           const float *sampling_loc, const float *attn_weight,
+                           int batch, int spatial_size, int num_heads, int channels,
+                           int num_levels, int num_query, int num_point,
+                           float *grad_value, float *grad_sampling_loc,
+                           float *grad_attn_weight, void *stream);
+int msda_b200_backward_f64(const double *grad_output, const double *value,
+                           const int64_t *spatial_shapes, const int64_t *level_start,
+                           const double *sampling_loc, const double *attn_weight,
+                           int batch, int spatial_size, int num_heads, int channels,
+                           int num_levels, int num_query, int num_point,
+                           double *grad_value, double *grad_sampling_loc,
+                           double *grad_attn_weight, void *stream);
+
+/*
+ * Integer known-answer hook (no counterpart in the reference; it exposes the
+ * integer work of cuh:43-58, 279-293 so tests can pin it bit-exactly).
+ * For every (n, q, m, l, p), in sampling_loc order:
+ *   idx[4*s+0] = point valid (cuh:293)   idx[4*s+1] = h_low   idx[4*s+2] = w_low
+ *   idx[4*s+3] = corner mask, bit k set <=> corner k contributes
+ *                (k = 0:(h_low,w_low) 1:(h_low,w_high) 2:(h_high,w_low) 3:(h_high,w_high))
+ *   off[4*s+k] = flat element offset (channel 0) of corner k in the whole value
+ *                tensor, or -1 if the corner does not contribute.
+ * Uses the same device function as the forward/backward fp32 kernels.
+ */
+int msda_b200_debug_indices_f32(const int64_t *spatial_shapes, const int64_t *level_start,
+                                const float *sampling_loc, int batch, int spatial_size,
+                                int num_heads, int channels, int num_levels, int num_query,
+                                int num_point, int32_t *idx, int64_t *off, void *stream);
+
+/*
+ * Tuning knobs for tools/sweep.py and the profiles; they select between
+ * kernel variants that all produce the same results (forward: bit-identical;
+ * backward: identical up to the order of the grad_value reductions).  Defaults
+ * are what the shipped path uses.  Not thread-safe against concurrent launches.
+ *   "fwd_variant"  0 = auto, other values select a specific forward kernel
+ *   "bwd_variant"  0 = auto, other values select a specific backward kernel
+ *   "tile_order"   0 = auto, 1 = linear query order, 2 = spatial tiles
+ */
+int msda_b200_set_option(const char *name, int value);
+int msda_b200_get_option(const char *name, int *value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSDA_B200_H_ */

@@ -1,0 +1,112 @@
+"""Generate tests/golden/*.npz by running the REFERENCE's own CPU path.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+It imports ``ms_deform_attn_core_pytorch`` from
+/root/reference/model/modeling/pixel_decoder/ops/functions/ms_deform_attn_func.py (by file
+path, so ``model/__init__.py`` and its detectron2 import never run), evaluates it in
+fp64 on fp32-representable seeded inputs, takes the three gradients with autograd, and
+stores inputs + outputs.  The committed fixtures are what pins oracle/ (and through it
+the CUDA path) to the reference; nothing on the GPU box reads /root/reference.
+
+Cases cover SURVEY.md section 8(c): model-like and uniform locations, all points out of
+bounds, exact borders / pixel centres / half-pixel borders, single level / single point,
+D in {4, 8, 16, 32, 64}, odd and non-square levels such as (12, 39), Lq != S.
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF_FUNC = "/root/reference/model/modeling/pixel_decoder/ops/functions/ms_deform_attn_func.py"
+
+sys.path.insert(0, ROOT)
+from __graft_entry__ import load_package  # noqa: E402
+
+
+def load_reference():
+    spec = importlib.util.spec_from_file_location("ref_ms_deform_attn_func", REF_FUNC)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.ms_deform_attn_core_pytorch
+
+
+def border_locations(levels, batch, heads, points, Lq):
+    """Locations exactly at 0, 1, -1/W, 1+1/W, pixel centres, and the half-pixel borders."""
+    L = len(levels)
+    loc = torch.zeros(batch, Lq, heads, L, points, 2)
+    for l, (H, W) in enumerate(levels):
+        xs = [0.0, 1.0, -1.0 / W, 1.0 + 1.0 / W, 0.5 / W, (W - 0.5) / W, 0.25 / W, (W - 0.25) / W,
+              1.5 / W, 0.5, -0.49 / W, 1.0 + 0.49 / W]
+        ys = [0.0, 1.0, -1.0 / H, 1.0 + 1.0 / H, 0.5 / H, (H - 0.5) / H, 0.25 / H, (H - 0.25) / H,
+              1.5 / H, 0.5, -0.49 / H, 1.0 + 0.49 / H]
+        k = 0
+        for q in range(Lq):
+            for m in range(heads):
+                for p in range(points):
+                    loc[:, q, m, l, p, 0] = xs[k % len(xs)]
+                    loc[:, q, m, l, p, 1] = ys[(k // len(xs) + k) % len(ys)]
+                    k += 1
+    return loc
+
+
+def cases(syn):
+    out = {}
+    pyr = [(2, 3), (4, 6), (8, 12)]
+    out["model_d32"] = syn.make_inputs(pyr, batch=1, mode="model", seed=1)
+    out["model_d32_b2_m2"] = syn.make_inputs(pyr, batch=2, heads=2, mode="model", seed=8)
+    out["uniform_d32"] = syn.make_inputs(pyr, batch=1, num_query=16, mode="uniform", seed=2)
+    out["kitti_like_odd"] = syn.make_inputs([(2, 3), (3, 5), (6, 13)], batch=1, heads=2, mode="model", seed=3)
+    for D in (4, 8, 16, 64):
+        out[f"uniform_d{D}"] = syn.make_inputs([(5, 7), (9, 4)], batch=2, heads=2, channels=D,
+                                               points=2, num_query=19, mode="uniform", seed=10 + D)
+    out["single_level_point"] = syn.make_inputs([(7, 9)], batch=1, heads=3, channels=32, points=1,
+                                                num_query=23, mode="uniform", seed=4)
+    out["four_levels"] = syn.make_inputs([(1, 2), (2, 3), (4, 6), (8, 12)], batch=1, heads=2,
+                                         mode="model", seed=5)
+    # every point out of bounds -> output and gradients exactly zero
+    oob = syn.make_inputs(pyr, batch=1, heads=2, num_query=11, mode="uniform", seed=6)
+    oob["sampling_locations"] = oob["sampling_locations"] + 3.0
+    out["all_oob"] = oob
+    # exact borders / centres / half-pixel borders (forward is continuous there; gradients wrt
+    # location are not, so only forward, grad_value and grad_attn_weight are pinned)
+    b = syn.make_inputs(pyr, batch=1, heads=2, num_query=29, mode="uniform", seed=7)
+    b["sampling_locations"] = border_locations(pyr, 1, 2, 4, 29)
+    out["borders"] = b
+    return out
+
+
+def main():
+    core = load_reference()
+    syn = load_package().synthetic if os.path.exists(
+        os.path.join(ROOT, "uni-encoder-code_b200", "lib", "libmsda_b200.so")) else None
+    if syn is None:
+        raise SystemExit("build the package first (python __graft_entry__.py)")
+    for name, inp in cases(syn).items():
+        v = inp["value"].double().requires_grad_(True)
+        loc = inp["sampling_locations"].double().requires_grad_(True)
+        w = inp["attention_weights"].double().requires_grad_(True)
+        out = core(v, inp["spatial_shapes"], loc, w)
+        out.backward(inp["grad_output"].double())
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(
+            path,
+            value=inp["value"].numpy(), spatial_shapes=inp["spatial_shapes"].numpy(),
+            level_start_index=inp["level_start_index"].numpy(),
+            sampling_locations=inp["sampling_locations"].numpy(),
+            attention_weights=inp["attention_weights"].numpy(),
+            grad_output=inp["grad_output"].numpy(),
+            ref_output=out.detach().numpy(), ref_grad_value=v.grad.numpy(),
+            ref_grad_sampling_loc=loc.grad.numpy(), ref_grad_attn_weight=w.grad.numpy(),
+            loc_grad_pinned=np.array(name != "borders"))
+        print(f"{name}: out {tuple(out.shape)} -> {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,326 @@
+"""GPU parity tests: the sm_100a kernels, called through the C ABI / drop-in shim, against
+(1) the committed golden vectors of the reference's own CPU path, (2) the CPU oracle on fresh
+seeded inputs, (3) size-independent properties at BASELINE.json's full sizes.
+
+Tolerances (BASELINE.json north_star): integer work bit-exact; fp32 forward max abs error
+<= 1e-5 against the fp64 oracle with value ~ N(0,1); gradients max|g - g_ref| / max|g_ref|
+<= 1e-4 per tensor on non-integer sampling coordinates.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import FWD_ABS_TOL, GOLDEN_NAMES, GRAD_REL_TOL, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def to_dev(inp, dtype=None):
+    out = {}
+    for k, v in inp.items():
+        t = torch.as_tensor(v)
+        if dtype is not None and t.is_floating_point():
+            t = t.to(dtype)
+        out[k] = t.to(DEV).contiguous()
+    return out
+
+
+def run_fwd_bwd(pkg, d):
+    args = (d["value"], d["spatial_shapes"], d["level_start_index"], d["sampling_locations"],
+            d["attention_weights"])
+    out = pkg.ms_deform_attn_forward(*args, 128)
+    gv, gl, gw = pkg.ms_deform_attn_backward(*args, d["grad_output"], 128)
+    torch.cuda.synchronize()
+    return out, gv, gl, gw
+
+
+def check_against(out, gv, gl, gw, ref_out, ref_gv, ref_gl, ref_gw, loc_grad=True, tag=""):
+    err = np.abs(out.double().cpu().numpy() - ref_out).max()
+    assert err <= FWD_ABS_TOL, f"{tag} forward max abs err {err}"
+    assert rel_err(gv.cpu().numpy(), np.reshape(ref_gv, gv.shape)) <= GRAD_REL_TOL, f"{tag} grad_value"
+    assert rel_err(gw.cpu().numpy(), ref_gw) <= GRAD_REL_TOL, f"{tag} grad_attn_weight"
+    if loc_grad:
+        assert rel_err(gl.cpu().numpy(), ref_gl) <= GRAD_REL_TOL, f"{tag} grad_sampling_loc"
+
+
+# ---------------------------------------------------------------- golden vectors
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_fp32_kernels_match_reference_golden(pkg, name):
+    g = load_golden(name)
+    pinned = bool(g.pop("loc_grad_pinned"))
+    d = to_dev({k: v for k, v in g.items() if not k.startswith("ref_")})
+    out, gv, gl, gw = run_fwd_bwd(pkg, d)
+    check_against(out, gv, gl, gw, g["ref_output"], g["ref_grad_value"], g["ref_grad_sampling_loc"],
+                  g["ref_grad_attn_weight"], loc_grad=pinned, tag=name)
+    if name == "all_oob":   # every point outside: exact zeros (cuh:293, cuh:370-372)
+        for t in (out, gv, gl, gw):
+            assert not t.any().item()
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_fp64_kernels_match_reference_golden(pkg, name):
+    g = load_golden(name)
+    pinned = bool(g.pop("loc_grad_pinned"))
+    d = to_dev({k: v for k, v in g.items() if not k.startswith("ref_")}, dtype=torch.float64)
+    out, gv, gl, gw = run_fwd_bwd(pkg, d)
+    assert np.abs(out.cpu().numpy() - g["ref_output"]).max() <= 1e-11
+    assert rel_err(gv.cpu().numpy(), g["ref_grad_value"]) <= 1e-11
+    assert rel_err(gw.cpu().numpy(), g["ref_grad_attn_weight"]) <= 1e-11
+    if pinned:
+        assert rel_err(gl.cpu().numpy(), g["ref_grad_sampling_loc"]) <= 1e-10
+
+
+# ---------------------------------------------------------------- oracle on fresh inputs
+CASES = [
+    # levels, batch, heads, channels, points, num_query, mode
+    ([(16, 32), (32, 64), (64, 128)], 2, 8, 32, 4, None, "model"),     # 512x1024 crop pyramid
+    ([(12, 39), (24, 78), (48, 156)], 1, 8, 32, 4, None, "model"),     # KITTI 384x1248 pyramid
+    ([(16, 32), (32, 64), (64, 128)], 1, 8, 32, 4, 777, "uniform"),    # decoder-style Lq != S
+    ([(9, 13), (17, 5)], 3, 4, 32, 2, None, "uniform"),                # LP = 4, odd sizes
+    ([(7, 9), (5, 3), (4, 4), (2, 2)], 2, 2, 32, 4, None, "uniform"),  # LP = 16
+    ([(6, 7), (3, 4)], 2, 3, 32, 3, None, "uniform"),                  # LP = 6 -> generic kernel
+    ([(6, 7), (3, 4)], 2, 2, 16, 4, 33, "uniform"),                    # D = 16 -> generic kernel
+    ([(6, 7)], 1, 2, 48, 4, 21, "uniform"),                            # D not a power of two
+]
+
+
+@pytest.mark.parametrize("levels,batch,heads,channels,points,nq,mode", CASES)
+def test_kernels_match_oracle(pkg, oracle, levels, batch, heads, channels, points, nq, mode):
+    inp = pkg.synthetic.make_inputs(levels, batch, heads, channels, points, num_query=nq, mode=mode,
+                                    seed=42)
+    out, gv, gl, gw = run_fwd_bwd(pkg, to_dev(inp))
+    a = (inp["value"], inp["spatial_shapes"], inp["level_start_index"], inp["sampling_locations"],
+         inp["attention_weights"])
+    ref_out = oracle.forward(*a)
+    rgv, rgl, rgw = oracle.backward(inp["grad_output"], *a)
+    check_against(out, gv, gl, gw, ref_out, rgv, rgl, rgw, tag=str(levels))
+
+
+@pytest.mark.parametrize("fwd_variant,bwd_variant,tile_order", [
+    (1, 1, 0), (2, 2, 0), (3, 3, 0), (4, 4, 0), (2, 2, 1), (63, 63, 0)])
+def test_kernel_variants_agree(pkg, oracle, fwd_variant, bwd_variant, tile_order):
+    """Every tile shape / query order / the generic kernel computes the same function."""
+    inp = pkg.synthetic.make_inputs([(5, 11), (10, 22), (20, 44)], 2, mode="model", seed=3)
+    a = (inp["value"], inp["spatial_shapes"], inp["level_start_index"], inp["sampling_locations"],
+         inp["attention_weights"])
+    ref_out = oracle.forward(*a)
+    rgv, rgl, rgw = oracle.backward(inp["grad_output"], *a)
+    try:
+        pkg.set_option("fwd_variant", fwd_variant)
+        pkg.set_option("bwd_variant", bwd_variant)
+        pkg.set_option("tile_order", tile_order)
+        out, gv, gl, gw = run_fwd_bwd(pkg, to_dev(inp))
+    finally:
+        for k in ("fwd_variant", "bwd_variant", "tile_order"):
+            pkg.set_option(k, 0)
+    check_against(out, gv, gl, gw, ref_out, rgv, rgl, rgw, tag=f"variant {fwd_variant}")
+
+
+# ---------------------------------------------------------------- integer work, bit-exact
+@pytest.mark.parametrize("mode,seed", [("model", 0), ("uniform", 1)])
+def test_integer_work_bit_exact(pkg, oracle, mode, seed):
+    levels = [(16, 32), (32, 64), (64, 128)]
+    inp = pkg.synthetic.make_inputs(levels, 2, mode=mode, seed=seed, with_grad_output=False)
+    d = to_dev(inp)
+    idx, off = pkg.debug_indices(inp["value"].shape, d["spatial_shapes"], d["level_start_index"],
+                                 d["sampling_locations"])
+    ridx, roff = oracle.indices(inp["spatial_shapes"], inp["level_start_index"],
+                                inp["sampling_locations"], tuple(inp["value"].shape), dtype=np.float32)
+    assert np.array_equal(idx.cpu().numpy(), ridx)
+    assert np.array_equal(off.cpu().numpy(), roff)
+    assert (ridx[..., 0] == 0).any() or mode == "model"   # uniform mode exercises invalid points
+
+
+def test_integer_work_at_exact_lattice_points(pkg, oracle):
+    """Pixel centres, borders and +-1 px outside: floor() and the validity tests at their edges."""
+    levels = [(4, 8), (12, 39)]
+    shapes, lsi = pkg.synthetic.level_tensors(levels)
+    xs, ys = [], []
+    for H, W in levels:
+        xs.append(torch.tensor([(i - 2) * 0.5 / W for i in range(2 * W + 8)]))
+        ys.append(torch.tensor([(i - 2) * 0.5 / H for i in range(2 * H + 8)]))
+    Lq = max(max(len(x), len(y)) for x, y in zip(xs, ys))
+    loc = torch.zeros(1, Lq, 2, 2, 3, 2)
+    for l in range(2):
+        for q in range(Lq):
+            loc[0, q, :, l, :, 0] = xs[l][q % len(xs[l])]
+            loc[0, q, :, l, :, 1] = ys[l][(q * 3) % len(ys[l])]
+    S = sum(h * w for h, w in levels)
+    idx, off = pkg.debug_indices((1, S, 2, 32), shapes.to(DEV), lsi.to(DEV), loc.to(DEV))
+    ridx, roff = oracle.indices(shapes, lsi, loc, (1, S, 2, 32), dtype=np.float32)
+    assert np.array_equal(idx.cpu().numpy(), ridx)
+    assert np.array_equal(off.cpu().numpy(), roff)
+
+
+# ---------------------------------------------------------------- full-size properties
+def _full(pkg, name, mode="model", batch=None):
+    return pkg.synthetic.make_workload_inputs(name, mode=mode, seed=1, device=DEV, batch=batch)
+
+
+def test_full_size_config1_forward_vs_oracle(pkg, oracle):
+    """BASELINE configs[0]: single forward at the 1024x2048 pixel-decoder shape, batch 1."""
+    inp = pkg.synthetic.make_workload_inputs("cityscapes_1024x2048_b1", seed=0)
+    d = to_dev(inp)
+    out = pkg.ms_deform_attn_forward(d["value"], d["spatial_shapes"], d["level_start_index"],
+                                     d["sampling_locations"], d["attention_weights"], 128)
+    ref = oracle.forward(inp["value"], inp["spatial_shapes"], inp["level_start_index"],
+                         inp["sampling_locations"], inp["attention_weights"])
+    assert np.abs(out.double().cpu().numpy() - ref).max() <= FWD_ABS_TOL
+
+
+def test_full_size_config2_gradients_vs_oracle(pkg, oracle):
+    """BASELINE configs[1]: forward+backward at the 512x1024 crop, batch 8, fp32 gradient check."""
+    inp = pkg.synthetic.make_workload_inputs("cityscapes_512x1024_b8", seed=1)
+    out, gv, gl, gw = run_fwd_bwd(pkg, to_dev(inp))
+    a = (inp["value"], inp["spatial_shapes"], inp["level_start_index"], inp["sampling_locations"],
+         inp["attention_weights"])
+    ref_out = oracle.forward(*a)
+    rgv, rgl, rgw = oracle.backward(inp["grad_output"], *a)
+    check_against(out, gv, gl, gw, ref_out, rgv, rgl, rgw, tag="config2")
+
+
+@pytest.mark.parametrize("name", ["cityscapes_1024x2048_b8", "kitti_384x1248_b16"])
+def test_full_size_properties(pkg, name):
+    """Linearity in value / weights, adjointness <out, g> == <value, grad_value>, batch independence."""
+    d = _full(pkg, name)
+    args = (d["spatial_shapes"], d["level_start_index"], d["sampling_locations"])
+    f = lambda v, w: pkg.ms_deform_attn_forward(v, *args, w, 128)
+    out = f(d["value"], d["attention_weights"])
+    # determinism of the forward
+    assert torch.equal(out, f(d["value"], d["attention_weights"]))
+    # homogeneity (exact: scaling by 2 commutes with fp32 rounding)
+    assert torch.equal(f(d["value"] * 2, d["attention_weights"]), out * 2)
+    assert torch.equal(f(d["value"], d["attention_weights"] * 0.5), out * 0.5)
+    # additivity in value
+    v2 = torch.randn_like(d["value"])
+    lhs = f(d["value"] + v2, d["attention_weights"])
+    rhs = out + f(v2, d["attention_weights"])
+    assert (lhs - rhs).abs().max().item() <= 2e-5
+    # adjoint: forward is linear in value, so <f(v), g> == <v, grad_value(g)>
+    gv, gl, gw = pkg.ms_deform_attn_backward(d["value"], *args, d["attention_weights"],
+                                             d["grad_output"], 128)
+    lhs = (out.double() * d["grad_output"].double()).sum()
+    rhs = (d["value"].double() * gv.double()).sum()
+    assert abs((lhs - rhs).item()) <= 1e-5 * max(1.0, abs(lhs.item())) + 1e-2
+    # ... and linear in the weights: <f, g> == <w, grad_w>
+    rhs_w = (d["attention_weights"].double() * gw.double()).sum()
+    assert abs((lhs - rhs_w).item()) <= 1e-5 * max(1.0, abs(lhs.item())) + 1e-2
+    # batch independence: image 0 alone gives the same rows (the path shards by image)
+    n0 = {k: (v[:1].contiguous() if v.dim() > 2 else v) for k, v in d.items()}
+    out0 = pkg.ms_deform_attn_forward(n0["value"], *args[:2], n0["sampling_locations"],
+                                      n0["attention_weights"], 128)
+    assert torch.equal(out0[0], out[0])
+    assert torch.isfinite(gl).all() and torch.isfinite(gw).all()
+
+
+def test_grad_loc_matches_finite_differences_fp64(pkg):
+    """Independent of any oracle: central differences of the fp64 forward."""
+    inp = pkg.synthetic.make_inputs([(5, 6), (9, 11)], 1, heads=2, channels=8, points=2,
+                                    num_query=7, mode="uniform", seed=9, dtype=torch.float64)
+    d = to_dev(inp)
+    args = (d["spatial_shapes"], d["level_start_index"])
+    _, gl, gw = pkg.ms_deform_attn_backward(d["value"], *args, d["sampling_locations"],
+                                            d["attention_weights"], d["grad_output"], 128)
+    loc = d["sampling_locations"]
+    eps = 1e-6
+    flat = loc.view(-1)
+    num = torch.zeros_like(flat)
+    for i in range(0, flat.numel(), 7):
+        lp, lm = flat.clone(), flat.clone()
+        lp[i] += eps
+        lm[i] -= eps
+        fp = pkg.ms_deform_attn_forward(d["value"], *args, lp.view_as(loc), d["attention_weights"], 128)
+        fm = pkg.ms_deform_attn_forward(d["value"], *args, lm.view_as(loc), d["attention_weights"], 128)
+        num[i] = ((fp - fm) * d["grad_output"]).sum() / (2 * eps)
+    sel = torch.arange(0, flat.numel(), 7, device=DEV)
+    assert (num[sel] - gl.view(-1)[sel]).abs().max().item() <= 1e-5 * max(1.0, gl.abs().max().item())
+
+
+# ---------------------------------------------------------------- boundary behaviour on the GPU
+def test_error_behaviour_matches_reference(pkg):
+    inp = pkg.synthetic.make_inputs([(4, 6), (8, 12)], 4, heads=2, points=2, num_query=9, mode="uniform")
+    d = to_dev(inp)
+    a = [d["value"], d["spatial_shapes"], d["level_start_index"], d["sampling_locations"],
+         d["attention_weights"]]
+    # non-contiguous value (ms_deform_attn_cuda.cu:33)
+    bad = list(a)
+    bad[0] = d["value"].transpose(2, 3).contiguous().transpose(2, 3)
+    with pytest.raises(RuntimeError, match="value tensor has to be contiguous"):
+        pkg.ms_deform_attn_forward(*bad, 128)
+    # a CPU tensor next to CUDA ones (cu:40)
+    bad = list(a)
+    bad[1] = bad[1].cpu()
+    with pytest.raises(RuntimeError, match="spatial_shapes must be a CUDA tensor"):
+        pkg.ms_deform_attn_forward(*bad, 128)
+    # batch not divisible by min(batch, im2col_step) (cu:55-57)
+    with pytest.raises(RuntimeError, match="must divide im2col_step"):
+        pkg.ms_deform_attn_forward(*a, 3)
+    # half precision is not dispatched (cu:69)
+    with pytest.raises(RuntimeError, match="not implemented for"):
+        pkg.ms_deform_attn_forward(a[0].half(), a[1], a[2], a[3].half(), a[4].half(), 128)
+    # non-contiguous grad_output (cu:103)
+    go = d["grad_output"].transpose(0, 1).contiguous().transpose(0, 1)
+    with pytest.raises(RuntimeError, match="grad_output tensor has to be contiguous"):
+        pkg.ms_deform_attn_backward(*a, go, 128)
+    # im2col_step that divides the batch is accepted and changes nothing
+    o1 = pkg.ms_deform_attn_forward(*a, 2)
+    o2 = pkg.ms_deform_attn_forward(*a, 128)
+    assert torch.equal(o1, o2)
+
+
+def test_dropin_module_and_autograd_function(pkg, oracle):
+    """`import MultiScaleDeformableAttention as MSDA` + the reference-style autograd function."""
+    pkg.install_dropin()
+    import MultiScaleDeformableAttention as MSDA
+    inp = pkg.synthetic.make_inputs([(6, 10), (12, 20), (24, 40)], 2, mode="model", seed=11)
+    d = to_dev(inp)
+    v = d["value"].clone().requires_grad_(True)
+    loc = d["sampling_locations"].clone().requires_grad_(True)
+    w = d["attention_weights"].clone().requires_grad_(True)
+    out = pkg.MSDeformAttnFunction.apply(v, d["spatial_shapes"], d["level_start_index"], loc, w, 128)
+    assert out.shape == (2, v.shape[1], 256)
+    out.backward(d["grad_output"])
+    direct = MSDA.ms_deform_attn_forward(d["value"], d["spatial_shapes"], d["level_start_index"],
+                                         d["sampling_locations"], d["attention_weights"], 128)
+    assert torch.equal(direct, out.detach())
+    a = (inp["value"], inp["spatial_shapes"], inp["level_start_index"], inp["sampling_locations"],
+         inp["attention_weights"])
+    rgv, rgl, rgw = oracle.backward(inp["grad_output"], *a)
+    check_against(out.detach(), v.grad, loc.grad, w.grad, oracle.forward(*a), rgv, rgl, rgw, tag="autograd")
+
+
+def test_non_default_stream_and_cuda_graph(pkg):
+    """No device-wide sync, no allocation, no host reads of device data inside the library:
+    the launches are capturable and follow the caller's current stream."""
+    inp = pkg.synthetic.make_inputs([(8, 16), (16, 32), (32, 64)], 2, mode="model", seed=5)
+    d = to_dev(inp)
+    a = (d["value"], d["spatial_shapes"], d["level_start_index"], d["sampling_locations"],
+         d["attention_weights"])
+    ref = pkg.ms_deform_attn_forward(*a, 128)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            warm = pkg.ms_deform_attn_forward(*a, 128)
+            pkg.ms_deform_attn_backward(*a, d["grad_output"], 128)
+    torch.cuda.current_stream().wait_stream(s)
+    assert torch.equal(warm, ref)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        gout = pkg.ms_deform_attn_forward(*a, 128)
+        ggrads = pkg.ms_deform_attn_backward(*a, d["grad_output"], 128)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(gout, ref)
+    eager = pkg.ms_deform_attn_backward(*a, d["grad_output"], 128)
+    assert torch.equal(ggrads[1], eager[1]) and torch.equal(ggrads[2], eager[2])
+    assert rel_err(ggrads[0].cpu().numpy(), eager[0].cpu().numpy()) <= 1e-5
+
+
+def test_launches_are_counted(pkg):
+    inp = pkg.synthetic.make_inputs([(4, 6), (8, 12)], 1, heads=2, points=2, mode="uniform")
+    d = to_dev(inp)
+    n0 = pkg.launch_count()
+    run_fwd_bwd(pkg, d)
+    assert pkg.launch_count() - n0 == 2

@@ -1,0 +1,187 @@
+// msda_api.cu -- the extern "C" boundary declared in include/msda_b200.h.
+//
+// Host-side counterpart of the reference's ms_deform_attn_cuda_forward/backward
+// (ms_deform_attn_cuda.cu:25-85, 88-158): argument validation and kernel choice.
+// Tensor-level checks (contiguity, device, dtype, im2col_step divisibility) live in
+// the Python shim because they need tensor metadata; this layer sees raw pointers.
+#include <atomic>
+#include <cstring>
+
+#include "../../include/msda_b200.h"
+#include "msda_common.cuh"
+
+namespace msda {
+
+// implemented in the kernel translation units
+cudaError_t launch_fwd_d32(const float *, const int64_t *, const int64_t *, const float *,
+                           const float *, const Dims &, float *, cudaStream_t, bool *handled);
+cudaError_t launch_bwd_d32(const float *, const float *, const int64_t *, const int64_t *,
+                           const float *, const float *, const Dims &, float *, float *, float *,
+                           cudaStream_t, bool *handled);
+template <typename T>
+cudaError_t launch_fwd_generic(const T *, const int64_t *, const int64_t *, const T *, const T *,
+                               const Dims &, T *, cudaStream_t);
+template <typename T>
+cudaError_t launch_bwd_generic(const T *, const T *, const int64_t *, const int64_t *, const T *,
+                               const T *, const Dims &, T *, T *, T *, cudaStream_t);
+cudaError_t launch_debug_indices(const int64_t *, const int64_t *, const float *, const Dims &,
+                                 int32_t *, int64_t *, cudaStream_t);
+
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_options[OPT_COUNT];   // zero-initialised: 0 == auto
+
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+int option_value(int which) { return g_options[which].load(std::memory_order_relaxed); }
+
+int sm_count() {
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int v = cached[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0)
+            v = 148;
+        cached[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
+static int check_dims(const Dims &d) {
+    if (d.N <= 0 || d.S <= 0 || d.M <= 0 || d.D <= 0 || d.L <= 0 || d.Lq <= 0 || d.P <= 0)
+        return MSDA_ERR_BAD_SHAPE;
+    if (d.L > MSDA_MAX_LEVELS) return MSDA_ERR_UNSUPPORTED;
+    return MSDA_OK;
+}
+
+static int option_index(const char *name) {
+    if (!name) return -1;
+    if (!strcmp(name, "fwd_variant")) return OPT_FWD_VARIANT;
+    if (!strcmp(name, "bwd_variant")) return OPT_BWD_VARIANT;
+    if (!strcmp(name, "tile_order")) return OPT_TILE_ORDER;
+    if (!strcmp(name, "ctas_per_sm")) return OPT_CTAS_PER_SM;
+    return -1;
+}
+
+}  // namespace msda
+
+using namespace msda;
+
+extern "C" {
+
+int msda_b200_abi_version(void) { return MSDA_B200_ABI_VERSION; }
+
+const char *msda_b200_error_string(int code) {
+    switch (code) {
+        case MSDA_OK: return "success";
+        case MSDA_ERR_NULL_POINTER: return "msda_b200: a required pointer is NULL";
+        case MSDA_ERR_BAD_SHAPE: return "msda_b200: a tensor size is zero or negative";
+        case MSDA_ERR_UNSUPPORTED: return "msda_b200: unsupported configuration (num_levels > 16)";
+        case MSDA_ERR_BAD_OPTION: return "msda_b200: unknown option name or value out of range";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "msda_b200: unknown error code";
+}
+
+long long msda_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int msda_b200_set_option(const char *name, int value) {
+    const int i = option_index(name);
+    if (i < 0 || value < 0 || value > 64) return MSDA_ERR_BAD_OPTION;
+    g_options[i].store(value, std::memory_order_relaxed);
+    return MSDA_OK;
+}
+
+int msda_b200_get_option(const char *name, int *value) {
+    const int i = option_index(name);
+    if (i < 0 || !value) return MSDA_ERR_BAD_OPTION;
+    *value = g_options[i].load(std::memory_order_relaxed);
+    return MSDA_OK;
+}
+
+int msda_b200_forward_f32(const float *value, const int64_t *spatial_shapes,
+                          const int64_t *level_start, const float *sampling_loc,
+                          const float *attn_weight, int batch, int spatial_size, int num_heads,
+                          int channels, int num_levels, int num_query, int num_point, float *output,
+                          void *stream) {
+    if (!value || !spatial_shapes || !level_start || !sampling_loc || !attn_weight || !output)
+        return MSDA_ERR_NULL_POINTER;
+    const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+    if (int rc = check_dims(d)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    bool handled = false;
+    cudaError_t e = cudaSuccess;
+    if (option_value(OPT_FWD_VARIANT) != 63)   // 63 forces the generic kernel (tests)
+        e = launch_fwd_d32(value, spatial_shapes, level_start, sampling_loc, attn_weight, d, output, st,
+                           &handled);
+    if (e == cudaSuccess && !handled)
+        e = launch_fwd_generic<float>(value, spatial_shapes, level_start, sampling_loc, attn_weight, d,
+                                      output, st);
+    return (int)e;
+}
+
+int msda_b200_forward_f64(const double *value, const int64_t *spatial_shapes,
+                          const int64_t *level_start, const double *sampling_loc,
+                          const double *attn_weight, int batch, int spatial_size, int num_heads,
+                          int channels, int num_levels, int num_query, int num_point,
+                          double *output, void *stream) {
+    if (!value || !spatial_shapes || !level_start || !sampling_loc || !attn_weight || !output)
+        return MSDA_ERR_NULL_POINTER;
+    const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+    if (int rc = check_dims(d)) return rc;
+    return (int)launch_fwd_generic<double>(value, spatial_shapes, level_start, sampling_loc,
+                                           attn_weight, d, output, (cudaStream_t)stream);
+}
+
+int msda_b200_backward_f32(const float *grad_output, const float *value,
+                           const int64_t *spatial_shapes, const int64_t *level_start,
+                           const float *sampling_loc, const float *attn_weight, int batch,
+                           int spatial_size, int num_heads, int channels, int num_levels,
+                           int num_query, int num_point, float *grad_value,
+                           float *grad_sampling_loc, float *grad_attn_weight, void *stream) {
+    if (!grad_output || !value || !spatial_shapes || !level_start || !sampling_loc || !attn_weight ||
+        !grad_value || !grad_sampling_loc || !grad_attn_weight)
+        return MSDA_ERR_NULL_POINTER;
+    const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+    if (int rc = check_dims(d)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    bool handled = false;
+    cudaError_t e = cudaSuccess;
+    if (option_value(OPT_BWD_VARIANT) != 63)
+        e = launch_bwd_d32(grad_output, value, spatial_shapes, level_start, sampling_loc, attn_weight,
+                           d, grad_value, grad_sampling_loc, grad_attn_weight, st, &handled);
+    if (e == cudaSuccess && !handled)
+        e = launch_bwd_generic<float>(grad_output, value, spatial_shapes, level_start, sampling_loc,
+                                      attn_weight, d, grad_value, grad_sampling_loc,
+                                      grad_attn_weight, st);
+    return (int)e;
+}
+
+int msda_b200_backward_f64(const double *grad_output, const double *value,
+                           const int64_t *spatial_shapes, const int64_t *level_start,
+                           const double *sampling_loc, const double *attn_weight, int batch,
+                           int spatial_size, int num_heads, int channels, int num_levels,
+                           int num_query, int num_point, double *grad_value,
+                           double *grad_sampling_loc, double *grad_attn_weight, void *stream) {
+    if (!grad_output || !value || !spatial_shapes || !level_start || !sampling_loc || !attn_weight ||
+        !grad_value || !grad_sampling_loc || !grad_attn_weight)
+        return MSDA_ERR_NULL_POINTER;
+    const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+    if (int rc = check_dims(d)) return rc;
+    return (int)launch_bwd_generic<double>(grad_output, value, spatial_shapes, level_start,
+                                           sampling_loc, attn_weight, d, grad_value,
+                                           grad_sampling_loc, grad_attn_weight, (cudaStream_t)stream);
+}
+
+int msda_b200_debug_indices_f32(const int64_t *spatial_shapes, const int64_t *level_start,
+                                const float *sampling_loc, int batch, int spatial_size,
+                                int num_heads, int channels, int num_levels, int num_query,
+                                int num_point, int32_t *idx, int64_t *off, void *stream) {
+    if (!spatial_shapes || !level_start || !sampling_loc || !idx || !off) return MSDA_ERR_NULL_POINTER;
+    const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+    if (int rc = check_dims(d)) return rc;
+    return (int)launch_debug_indices(spatial_shapes, level_start, sampling_loc, d, idx, off,
+                                     (cudaStream_t)stream);
+}
+
+}  // extern "C"

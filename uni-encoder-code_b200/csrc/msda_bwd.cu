@@ -1,0 +1,265 @@
+// msda_bwd.cu -- backward MSDA kernel for sm_100a, 32 fp32 channels per head.
+//
+// Replaces the reference's col2im kernel that is hit at D = 32,
+// ms_deformable_col2im_gpu_kernel_shm_blocksize_aware_reduce_v1<T,32>
+// (ms_deform_im2col_cuda.cuh:306-408) and its bilinear helper (cuh:92-164):
+// there every (query, head) is a 32-thread block that, per sampling point, issues
+// 128 scalar atomicAdds, writes 3 partials per thread to shared memory and lets
+// thread 0 add them up serially between two __syncthreads.
+//
+// Design (same work decomposition and phase 1 as msda_fwd.cu):
+//   * lane = corner*8 + chunk.  Per sampling point a lane loads 16 bytes of its
+//     corner's value row, forms the partial dot product with its 4 grad_output
+//     channels (d) and adds weight*grad_output to grad_value with ONE 128-bit
+//     vector reduction (red.global.add.v4.f32) -- 4 warp-level REDG per point
+//     row instead of 128 scalar ones, no shared-memory atomics (fp32 shared atomics
+//     are CAS loops on sm_100a);
+//   * grad_sampling_loc and grad_attn_weight are linear in the four per-corner dot
+//     products D_k = sum_c v_k[c]*g[c].  The L*P partials d are kept in registers
+//     and summed over the 8 lanes of each corner group with a reduce-scatter
+//     (11 shuffles for 12 points), multiplied by the per-corner coefficients, and
+//     summed over the 4 corner groups with a second reduce-scatter (5 shuffles):
+//     16 shuffles and no barrier per (query, head) instead of 24 barriers and a
+//     serial 32-term sum per point.  The summation order is fixed, so these two
+//     outputs are deterministic; only grad_value depends on reduction order.
+#include "msda_common.cuh"
+
+namespace msda {
+
+template <int LP, int WARPS, int TILE_W>
+struct BwdCfg {
+    static constexpr int kQPW = 8;
+    static constexpr int kGroup = WARPS * kQPW;
+    static constexpr int kTileH = kGroup / TILE_W;
+    static constexpr int kRounds = (kQPW * LP + 31) / 32;
+    static constexpr int kRecPerWarp = kRounds * 32;
+    // per record: 4 x {offset, weight} (32 B) + {lh, lw, aw*W, aw*H} (16 B)
+    static constexpr size_t kSmem = (size_t)WARPS * kRecPerWarp * (4 * sizeof(uint2) + sizeof(float4));
+    // sizes along the two reduce-scatters
+    static constexpr int kN1 = (LP + 1) / 2, kN2 = (kN1 + 1) / 2, kN3 = (kN2 + 1) / 2;  // per-lane D count
+    static constexpr int kT0 = 3 * kN3, kT1 = (kT0 + 1) / 2, kT2 = (kT1 + 1) / 2;
+};
+
+template <int LP, int WARPS, int TILE_W, bool VEC_RED>
+__global__ void __launch_bounds__(WARPS * 32)
+msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict__ value,
+                    const int64_t *__restrict__ shapes, const int64_t *__restrict__ lstart,
+                    const float *__restrict__ loc, const float *__restrict__ attw, const Dims d,
+                    const int want_spatial, float *__restrict__ grad_value,
+                    float *__restrict__ grad_loc, float *__restrict__ grad_attw) {
+    using Cfg = BwdCfg<LP, WARPS, TILE_W>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ LevelTable lt;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int corner = lane >> 3, chunk = lane & 7;
+    uint2 *rec = reinterpret_cast<uint2 *>(smem_raw) + (size_t)warp * Cfg::kRecPerWarp * 4;
+    float4 *aux = reinterpret_cast<float4 *>(smem_raw + (size_t)WARPS * Cfg::kRecPerWarp * 4 * sizeof(uint2)) +
+                  (size_t)warp * Cfg::kRecPerWarp;
+
+    fill_level_table(lt, shapes, lstart, d.L, d.P, d.S, d.Lq, Cfg::kGroup, Cfg::kTileH, TILE_W,
+                     want_spatial);
+    __syncthreads();
+
+    const int M = d.M;
+    const long long items = (long long)d.N * M * lt.groups;
+    const uint32_t pix_stride = (uint32_t)M * 8u;
+
+    // which of the L*P points this lane finalises after the first reduce-scatter
+    // (lane bits 2,1,0 = chunk bits): index unwinding, see rs_step()
+    const bool b2 = chunk & 4, b1 = chunk & 2, b0 = chunk & 1;
+    const bool c1 = corner & 2, c0 = corner & 1;
+
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const int m = (int)(item % M);
+        const long long rest = item / M;
+        const int g = (int)(rest % lt.groups);
+        const long long n = rest / lt.groups;
+        int q0, cnt;
+        warp_queries(lt, d.L, g, warp, Cfg::kGroup, Cfg::kTileH, TILE_W, d.Lq, q0, cnt);
+
+        // ---- phase 1: records ----
+#pragma unroll
+        for (int r = 0; r < Cfg::kRounds; ++r) {
+            const int s = r * 32 + lane;
+            const int qi = s / LP, sp = s - qi * LP;
+            if (qi < cnt) {
+                const long long row = ((n * d.Lq + q0 + qi) * M + m) * (long long)LP + sp;
+                const float2 xy = ldg_stream_f2(reinterpret_cast<const float2 *>(loc) + row);
+                const float aw = ldg_stream_f1(attw + row);
+                const int l = lt.level_of[sp];
+                const int H = lt.H[l], W = lt.W[l];
+                const Geom<float> gm = decompose(xy.x, xy.y, H, W);
+                const float hh = 1.f - gm.lh, hw = 1.f - gm.lw;
+                const uint32_t base = ((uint32_t)lt.start[l] + (uint32_t)gm.h_low * (uint32_t)W +
+                                       (uint32_t)gm.w_low) * pix_stride + (uint32_t)m * 8u;
+                const uint32_t row_stride = (uint32_t)W * pix_stride;
+                uint4 lo, hi;
+                lo.x = (gm.cmask & 1) ? base : kNoCorner;
+                lo.y = __float_as_uint((gm.cmask & 1) ? (hh * hw) * aw : 0.f);
+                lo.z = (gm.cmask & 2) ? base + pix_stride : kNoCorner;
+                lo.w = __float_as_uint((gm.cmask & 2) ? (hh * gm.lw) * aw : 0.f);
+                hi.x = (gm.cmask & 4) ? base + row_stride : kNoCorner;
+                hi.y = __float_as_uint((gm.cmask & 4) ? (gm.lh * hw) * aw : 0.f);
+                hi.z = (gm.cmask & 8) ? base + row_stride + pix_stride : kNoCorner;
+                hi.w = __float_as_uint((gm.cmask & 8) ? (gm.lh * gm.lw) * aw : 0.f);
+                uint4 *dst = reinterpret_cast<uint4 *>(rec + (size_t)s * 4);
+                dst[0] = lo;
+                dst[1] = hi;
+                // invalid point: every D_k is 0 (no corner is read), so any finite
+                // coefficients give the reference's zero gradients (cuh:370-372)
+                aux[s] = gm.valid ? make_float4(gm.lh, gm.lw, aw * (float)W, aw * (float)H)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        __syncwarp();
+
+        // ---- phase 2 ----
+        const long long img = n * (long long)d.S * M * 8 + chunk;
+        const float4 *vb = reinterpret_cast<const float4 *>(value) + img;
+        float4 *gvb = reinterpret_cast<float4 *>(grad_value) + img;
+        for (int qi = 0; qi < cnt; ++qi) {
+            const long long qrow = (n * d.Lq + q0 + qi) * M + m;
+            const float4 go = ldg_stream_f4(reinterpret_cast<const float4 *>(grad_out) + qrow * 8 + chunk);
+            const uint2 *rq = rec + (size_t)qi * LP * 4 + corner;
+            float dpart[LP];
+#pragma unroll
+            for (int sp = 0; sp < LP; ++sp) {
+                const uint2 e = rq[sp * 4];
+                float dot = 0.f;
+                if (e.x != kNoCorner) {
+                    const float4 v = ldg_keep_f4(vb + e.x);
+                    const float w = __uint_as_float(e.y);
+                    dot = fmaf(v.w, go.w, fmaf(v.z, go.z, fmaf(v.y, go.y, v.x * go.x)));
+                    const float4 gv = make_float4(w * go.x, w * go.y, w * go.z, w * go.w);
+                    if (VEC_RED) {
+                        red_add_f4(gvb + e.x, gv);
+                    } else {
+                        float *p = reinterpret_cast<float *>(gvb + e.x);
+                        atomicAdd(p + 0, gv.x);
+                        atomicAdd(p + 1, gv.y);
+                        atomicAdd(p + 2, gv.z);
+                        atomicAdd(p + 3, gv.w);
+                    }
+                }
+                dpart[sp] = dot;
+            }
+            // D_k for this lane's corner: sum over the 8 chunk lanes (lane bits 2,1,0)
+            float r1[Cfg::kN1], r2[Cfg::kN2], r3[Cfg::kN3];
+            rs_step<LP>(dpart, r1, b2, 4);
+            rs_step<Cfg::kN1>(r1, r2, b1, 2);
+            rs_step<Cfg::kN2>(r2, r3, b0, 1);
+            // coefficient of D_corner in (d/dx, d/dy, d/dweight) of each finalised point
+            float t0[Cfg::kT0];
+#pragma unroll
+            for (int j = 0; j < Cfg::kN3; ++j) {
+                const int i2 = j + (b0 ? Cfg::kN3 : 0);          // index before step 3
+                const int i1 = i2 + (b1 ? Cfg::kN2 : 0);         // index before step 2
+                const int sp = i1 + (b2 ? Cfg::kN1 : 0);         // index before step 1 = point
+                const bool live = (i2 < Cfg::kN2) && (i1 < Cfg::kN1) && (sp < LP);
+                float cx = 0.f, cy = 0.f, ca = 0.f;
+                if (live) {
+                    const float4 a = aux[qi * LP + sp];
+                    const float lh = a.x, lw = a.y, hh = 1.f - a.x, hw = 1.f - a.y;
+                    const float fh = c1 ? lh : hh;               // factor along h of this corner's weight
+                    const float fw = c0 ? lw : hw;               // factor along w
+                    ca = fh * fw;                                // d val / d weight part (cuh:161)
+                    cx = (c0 ? fh : -fh) * a.z;                  // W * aw * d w_k / d w  (cuh:128-156,162)
+                    cy = (c1 ? fw : -fw) * a.w;                  // H * aw * d w_k / d h  (cuh:128-156,163)
+                }
+                t0[3 * j + 0] = cx * r3[j];
+                t0[3 * j + 1] = cy * r3[j];
+                t0[3 * j + 2] = ca * r3[j];
+            }
+            // sum over the 4 corner groups (lane bits 4,3)
+            float t1[Cfg::kT1], t2[Cfg::kT2];
+            rs_step<Cfg::kT0>(t0, t1, c1, 16);
+            rs_step<Cfg::kT1>(t1, t2, c0, 8);
+#pragma unroll
+            for (int i = 0; i < Cfg::kT2; ++i) {
+                const int u1 = i + (c0 ? Cfg::kT2 : 0);
+                const int u0 = u1 + (c1 ? Cfg::kT1 : 0);
+                if (u1 < Cfg::kT1 && u0 < Cfg::kT0) {
+                    const int j = u0 / 3, comp = u0 - 3 * j;
+                    const int i2 = j + (b0 ? Cfg::kN3 : 0);
+                    const int i1 = i2 + (b1 ? Cfg::kN2 : 0);
+                    const int sp = i1 + (b2 ? Cfg::kN1 : 0);
+                    if (i2 < Cfg::kN2 && i1 < Cfg::kN1 && sp < LP) {
+                        const long long sidx = qrow * LP + sp;
+                        if (comp == 2) stg_stream_f1(grad_attw + sidx, t2[i]);
+                        else stg_stream_f1(grad_loc + 2 * sidx + comp, t2[i]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+template <int LP, int WARPS, int TILE_W, bool VEC_RED>
+static cudaError_t launch_bwd_cfg(const float *grad_out, const float *value, const int64_t *shapes,
+                                  const int64_t *lstart, const float *loc, const float *attw,
+                                  const Dims &d, float *grad_value, float *grad_loc,
+                                  float *grad_attw, cudaStream_t stream) {
+    using Cfg = BwdCfg<LP, WARPS, TILE_W>;
+    auto kern = msda_bwd_d32_kernel<LP, WARPS, TILE_W, VEC_RED>;
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)Cfg::kSmem);
+        if (e != cudaSuccess) return e;
+        int nb = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, WARPS * 32, Cfg::kSmem);
+        if (e != cudaSuccess) return e;
+        ctas_per_sm = nb > 0 ? nb : 1;
+    }
+    int per_sm = ctas_per_sm;
+    const int cap = option_value(OPT_CTAS_PER_SM);
+    if (cap > 0 && cap < per_sm) per_sm = cap;
+    long long blocks = (long long)sm_count() * per_sm;
+    const long long items_ub = (long long)d.N * d.M * d.Lq;
+    if (blocks > items_ub) blocks = items_ub;
+    if (blocks < 1) blocks = 1;
+    const int want_spatial = option_value(OPT_TILE_ORDER) != 1;
+    kern<<<(unsigned)blocks, WARPS * 32, Cfg::kSmem, stream>>>(grad_out, value, shapes, lstart, loc,
+                                                              attw, d, want_spatial, grad_value,
+                                                              grad_loc, grad_attw);
+    note_launch();
+    return cudaGetLastError();
+}
+
+template <int LP>
+static cudaError_t launch_bwd_lp(const float *grad_out, const float *value, const int64_t *shapes,
+                                 const int64_t *lstart, const float *loc, const float *attw,
+                                 const Dims &d, float *gv, float *gl, float *gw, cudaStream_t st) {
+    switch (option_value(OPT_BWD_VARIANT)) {
+        case 1: return launch_bwd_cfg<LP, 8, 8, true>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, st);
+        case 3: return launch_bwd_cfg<LP, 16, 16, false>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, st);
+        case 4: return launch_bwd_cfg<LP, 16, 8, true>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, st);
+        case 2:
+        default: return launch_bwd_cfg<LP, 16, 16, true>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, st);
+    }
+}
+
+cudaError_t launch_bwd_d32(const float *grad_out, const float *value, const int64_t *shapes,
+                           const int64_t *lstart, const float *loc, const float *attw, const Dims &d,
+                           float *gv, float *gl, float *gw, cudaStream_t stream, bool *handled) {
+    *handled = true;
+    const int LP = d.L * d.P;
+    if (d.D != 32 || (long long)d.S * d.M * 8 >= 0x7fffffffLL) {
+        *handled = false;
+        return cudaSuccess;
+    }
+    switch (LP) {
+        case 4: return launch_bwd_lp<4>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, stream);
+        case 8: return launch_bwd_lp<8>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, stream);
+        case 12: return launch_bwd_lp<12>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, stream);
+        case 16: return launch_bwd_lp<16>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, stream);
+        default: *handled = false; return cudaSuccess;
+    }
+}
+
+}  // namespace msda

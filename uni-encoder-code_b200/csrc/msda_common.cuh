@@ -1,0 +1,218 @@
+// msda_common.cuh -- shared device code for the sm_100a multi-scale deformable
+// attention (MSDA) kernels.
+//
+// Nothing here is derived from the reference's CUDA sources; the arithmetic that
+// must agree with them is cited by file:line (relative to
+// /root/reference/model/modeling/pixel_decoder/ops/src/cuda/) next to the code.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace msda {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+constexpr int kMaxLevels = 16;           // == MSDA_MAX_LEVELS in include/msda_b200.h
+constexpr int kMaxSamples = 64;          // L*P bound for the shared sample->level table
+constexpr uint32_t kNoCorner = 0xffffffffu;  // record marker: corner outside the level
+
+// ---------------------------------------------------------------------------
+// exact-rounding helpers: one rounding per operation, never contracted to FMA
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ int floor_to_int(float a) { return __float2int_rd(a); }
+__device__ __forceinline__ int floor_to_int(double a) { return __double2int_rd(a); }
+
+// ---------------------------------------------------------------------------
+// Geometry of one sampling point.  This single function carries all the integer
+// work that the parity tests pin bit-exactly (through msda_b200_debug_indices_f32):
+//   pixel coordinate  x = loc_x*W - 0.5, y = loc_y*H - 0.5  as a rounded product
+//                     followed by a rounded difference          (cuh:290-291)
+//   point valid       y > -1 && x > -1 && y < H && x < W         (cuh:293)
+//   h_low, w_low      floor                                      (cuh:43-44)
+//   lh, lw            fractional parts                           (cuh:48-49)
+//   corner k valid    0 <= h <= H-1 && 0 <= w <= W-1             (cuh:60-83)
+//     k = 0:(h_low,w_low) 1:(h_low,w_high) 2:(h_high,w_low) 3:(h_high,w_high)
+// ---------------------------------------------------------------------------
+template <typename T>
+struct Geom {
+    int valid;
+    int h_low, w_low;
+    int cmask;
+    T lh, lw;
+};
+
+template <typename T>
+__device__ __forceinline__ Geom<T> decompose(T loc_x, T loc_y, int H, int W) {
+    Geom<T> g;
+    const T h_im = sub_rn(mul_rn(loc_y, (T)H), (T)0.5);
+    const T w_im = sub_rn(mul_rn(loc_x, (T)W), (T)0.5);
+    g.valid = (h_im > (T)-1) && (w_im > (T)-1) && (h_im < (T)H) && (w_im < (T)W);
+    g.h_low = floor_to_int(h_im);   // cvt.rmi saturates; NaN -> 0, and then valid == 0
+    g.w_low = floor_to_int(w_im);
+    g.lh = sub_rn(h_im, (T)g.h_low);
+    g.lw = sub_rn(w_im, (T)g.w_low);
+    int mask = 0;
+    if (g.valid) {
+        const bool h0 = g.h_low >= 0, h1 = g.h_low + 1 <= H - 1;
+        const bool w0 = g.w_low >= 0, w1 = g.w_low + 1 <= W - 1;
+        mask = (h0 && w0 ? 1 : 0) | (h0 && w1 ? 2 : 0) | (h1 && w0 ? 4 : 0) | (h1 && w1 ? 8 : 0);
+    }
+    g.cmask = mask;
+    return g;
+}
+
+// ---------------------------------------------------------------------------
+// Level table kept in shared memory by every kernel: the int64 device tensors
+// spatial_shapes / level_start_index are read once per CTA instead of once per
+// thread per level (the reference re-reads them inside its level loop, cuh:279-282).
+// ---------------------------------------------------------------------------
+struct LevelTable {
+    int H[kMaxLevels];
+    int W[kMaxLevels];
+    int start[kMaxLevels];            // first pixel of the level inside one image
+    int tiles_x[kMaxLevels];          // query tiles per row (spatial order only)
+    int tile_begin[kMaxLevels + 1];   // prefix sum of tiles per level
+    unsigned char level_of[kMaxSamples];  // sample index (l*P+p) -> l
+    int spatial;                      // 1: queries are walked as 2-D tiles of the levels
+    int groups;                       // query groups per (image, head)
+};
+
+// Fill the table.  Must be followed by __syncthreads().  `group` = queries per
+// work item; tiles are tile_h x tile_w with tile_h*tile_w == group.
+__device__ __forceinline__ void fill_level_table(LevelTable &lt, const int64_t *shapes,
+                                                 const int64_t *lstart, int L, int P, int S,
+                                                 int Lq, int group, int tile_h, int tile_w,
+                                                 int want_spatial) {
+    if (threadIdx.x == 0) {
+        long long pix = 0;
+        int tiles = 0;
+        bool layout_ok = true;
+        for (int l = 0; l < L; ++l) {
+            const int H = (int)shapes[2 * l], W = (int)shapes[2 * l + 1];
+            const long long st = lstart[l];
+            lt.H[l] = H;
+            lt.W[l] = W;
+            lt.start[l] = (int)st;
+            layout_ok = layout_ok && (st == pix) && H > 0 && W > 0;
+            pix += (long long)H * W;
+            lt.tiles_x[l] = (W + tile_w - 1) / tile_w;
+            lt.tile_begin[l] = tiles;
+            tiles += lt.tiles_x[l] * ((H + tile_h - 1) / tile_h);
+        }
+        lt.tile_begin[L] = tiles;
+        // Spatial tiling only permutes the order in which queries are visited; it is
+        // chosen when the queries are laid out like the value pixels (encoder
+        // self-attention, msdeformattn.py:152-166), otherwise groups of consecutive
+        // queries are used.  Either way every query is visited exactly once.
+        const bool spatial = want_spatial && layout_ok && pix == (long long)S && Lq == S;
+        lt.spatial = spatial ? 1 : 0;
+        lt.groups = spatial ? tiles : (Lq + group - 1) / group;
+    }
+    for (int s = threadIdx.x; s < L * P && s < kMaxSamples; s += blockDim.x)
+        lt.level_of[s] = (unsigned char)(s / P);
+}
+
+// First query and number of consecutive queries (0..8) handled by `warp` in
+// query group `g` of an (image, head).
+__device__ __forceinline__ void warp_queries(const LevelTable &lt, int L, int g, int warp,
+                                             int group, int tile_h, int tile_w, int Lq,
+                                             int &q0, int &cnt) {
+    if (lt.spatial) {
+        int l = 0;
+        while (l + 1 < L && g >= lt.tile_begin[l + 1]) ++l;
+        const int t = g - lt.tile_begin[l];
+        const int ty = t / lt.tiles_x[l], tx = t - ty * lt.tiles_x[l];
+        const int per_row = tile_w >> 3;
+        const int y = ty * tile_h + warp / per_row;
+        const int x = tx * tile_w + (warp % per_row) * 8;
+        const int W = lt.W[l];
+        cnt = (y < lt.H[l]) ? min(max(W - x, 0), 8) : 0;
+        q0 = lt.start[l] + y * W + x;
+    } else {
+        q0 = g * group + warp * 8;
+        cnt = min(max(Lq - q0, 0), 8);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// cache-hinted global accesses
+// ---------------------------------------------------------------------------
+// value rows are re-used by neighbouring queries: keep them in L1 (default .ca)
+__device__ __forceinline__ float4 ldg_keep_f4(const float4 *p) {
+    float4 r;
+    asm("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+// streamed once: do not allocate in L1
+__device__ __forceinline__ float4 ldg_stream_f4(const float4 *p) {
+    float4 r;
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float2 ldg_stream_f2(const float2 *p) {
+    float2 r;
+    asm("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];"
+                 : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ldg_stream_f1(const float *p) {
+    float r;
+    asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream_f1(float *p, float v) {
+    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void stg_stream_f2(float2 *p, float2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y)
+                 : "memory");
+}
+// 128-bit vector reduction into global memory (sm_90+): one instruction adds four
+// consecutive floats (SASS: REDG.E.ADD.F32x4).
+__device__ __forceinline__ void red_add_f4(float4 *p, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// Warp reduce-scatter: n per-lane values are summed across the two lanes that
+// differ in one lane-id bit; each lane keeps ceil(n/2) of the sums.  Repeating it
+// over k bits sums across 2^k lanes with ~n shuffles in total instead of n*k.
+// After a step, element i of a lane whose bit is `upper` holds the sum for input
+// index i + upper*ceil(n/2) (absent if that is >= n).
+// ---------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void rs_step(const float (&in)[N], float (&out)[(N + 1) / 2],
+                                        bool upper, int lane_xor) {
+    constexpr int H = (N + 1) / 2;
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        const float lo = in[i];
+        const float hi = (i + H < N) ? in[i + H] : 0.f;
+        const float keep = upper ? hi : lo;
+        const float send = upper ? lo : hi;
+        out[i] = keep + __shfl_xor_sync(kFullMask, send, lane_xor);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// launch bookkeeping shared by the translation units
+// ---------------------------------------------------------------------------
+struct Dims {
+    int N, S, M, D, L, Lq, P;
+};
+
+void note_launch();                   // increments the library launch counter
+int sm_count();                       // SMs of the current device (cached)
+int option_value(int which);          // tuning knobs, see msda_api.cu
+enum { OPT_FWD_VARIANT = 0, OPT_BWD_VARIANT = 1, OPT_TILE_ORDER = 2, OPT_CTAS_PER_SM = 3,
+       OPT_COUNT = 4 };
+
+}  // namespace msda

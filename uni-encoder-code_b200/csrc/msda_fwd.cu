@@ -1,0 +1,202 @@
+// msda_fwd.cu -- forward MSDA kernel for sm_100a, specialised for 32 fp32
+// channels per head (the pixel-decoder shape: d_model 256 / 8 heads).
+//
+// Replaces the reference's ms_deformable_im2col_gpu_kernel
+// (ms_deform_im2col_cuda.cuh:242-304), which runs one thread per output element
+// and recomputes every sampling point's geometry in all 32 lanes.
+//
+// Design (see DESIGN.md "forward kernel"):
+//   * persistent CTAs walk work items = (image n, head m, group of 8*WARPS queries);
+//     when the queries are laid out like the value pixels (encoder self-attention)
+//     a group is a 2-D tile of one level, so neighbouring queries' bilinear
+//     footprints overlap in L1;
+//   * each warp owns 8 consecutive queries of the item.  Phase 1: the 8*L*P
+//     sampling points are spread over the lanes (one point per lane per round):
+//     load (x, y, weight), run decompose() once per point and write a 32-byte
+//     record {offset, bilinear*attention weight} x 4 corners to shared memory;
+//   * phase 2, per query: lane = corner*8 + chunk.  Each lane reads its corner's
+//     record (one 8-byte shared load, broadcast over 8 lanes), fetches 16 bytes of
+//     that corner's 128-byte value row (one LDG.128; a warp instruction covers the
+//     four corner rows of a point) and accumulates 4 channels;
+//   * the four corner groups are summed with a 3-shuffle reduce-scatter that leaves
+//     one output channel per lane: the store is a single coalesced 128-byte line.
+#include "msda_common.cuh"
+
+namespace msda {
+
+template <int LP, int WARPS, int TILE_W>
+struct FwdCfg {
+    static constexpr int kQPW = 8;                        // queries per warp per item
+    static constexpr int kGroup = WARPS * kQPW;           // queries per item
+    static constexpr int kTileH = kGroup / TILE_W;
+    static constexpr int kRounds = (kQPW * LP + 31) / 32; // phase-1 rounds
+    static constexpr int kRecPerWarp = kRounds * 32;      // records, padded to full rounds
+    static constexpr size_t kSmem = (size_t)WARPS * kRecPerWarp * 4 * sizeof(uint2);
+    static_assert(TILE_W % 8 == 0 && kGroup % TILE_W == 0, "tile shape");
+};
+
+template <int LP, int WARPS, int TILE_W>
+__global__ void __launch_bounds__(WARPS * 32)
+msda_fwd_d32_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes,
+                    const int64_t *__restrict__ lstart, const float *__restrict__ loc,
+                    const float *__restrict__ attw, const Dims d, const int want_spatial,
+                    float *__restrict__ out) {
+    using Cfg = FwdCfg<LP, WARPS, TILE_W>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ LevelTable lt;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int corner = lane >> 3, chunk = lane & 7;
+    uint2 *rec = reinterpret_cast<uint2 *>(smem_raw) + (size_t)warp * Cfg::kRecPerWarp * 4;
+
+    fill_level_table(lt, shapes, lstart, d.L, d.P, d.S, d.Lq, Cfg::kGroup, Cfg::kTileH, TILE_W,
+                     want_spatial);
+    __syncthreads();
+
+    const int M = d.M;
+    const long long items = (long long)d.N * M * lt.groups;
+    const uint32_t pix_stride = (uint32_t)M * 8u;          // float4 units per pixel
+
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const int m = (int)(item % M);
+        const long long rest = item / M;
+        const int g = (int)(rest % lt.groups);
+        const long long n = rest / lt.groups;
+        int q0, cnt;
+        warp_queries(lt, d.L, g, warp, Cfg::kGroup, Cfg::kTileH, TILE_W, d.Lq, q0, cnt);
+
+        // ---- phase 1: one sampling point per lane per round -> records ----
+#pragma unroll
+        for (int r = 0; r < Cfg::kRounds; ++r) {
+            const int s = r * 32 + lane;
+            const int qi = s / LP, sp = s - qi * LP;
+            if (qi < cnt) {
+                const long long row = ((n * d.Lq + q0 + qi) * M + m) * (long long)LP + sp;
+                const float2 xy = ldg_stream_f2(reinterpret_cast<const float2 *>(loc) + row);
+                const float aw = ldg_stream_f1(attw + row);
+                const int l = lt.level_of[sp];
+                const int H = lt.H[l], W = lt.W[l];
+                const Geom<float> gm = decompose(xy.x, xy.y, H, W);
+                const float hh = 1.f - gm.lh, hw = 1.f - gm.lw;
+                // offset (float4 units inside image n) of pixel (h_low, w_low), head m
+                // (modular uint32 arithmetic: h_low / w_low may be -1; contributing corners
+                // always land on a true offset < 2^31, checked on the host)
+                const uint32_t base = ((uint32_t)lt.start[l] + (uint32_t)gm.h_low * (uint32_t)W +
+                                       (uint32_t)gm.w_low) * pix_stride + (uint32_t)m * 8u;
+                const uint32_t row_stride = (uint32_t)W * pix_stride;
+                uint4 lo, hi;   // {off0, w0, off1, w1}, {off2, w2, off3, w3}
+                lo.x = (gm.cmask & 1) ? base : kNoCorner;
+                lo.y = __float_as_uint((gm.cmask & 1) ? (hh * hw) * aw : 0.f);
+                lo.z = (gm.cmask & 2) ? base + pix_stride : kNoCorner;
+                lo.w = __float_as_uint((gm.cmask & 2) ? (hh * gm.lw) * aw : 0.f);
+                hi.x = (gm.cmask & 4) ? base + row_stride : kNoCorner;
+                hi.y = __float_as_uint((gm.cmask & 4) ? (gm.lh * hw) * aw : 0.f);
+                hi.z = (gm.cmask & 8) ? base + row_stride + pix_stride : kNoCorner;
+                hi.w = __float_as_uint((gm.cmask & 8) ? (gm.lh * gm.lw) * aw : 0.f);
+                uint4 *dst = reinterpret_cast<uint4 *>(rec + (size_t)s * 4);
+                dst[0] = lo;
+                dst[1] = hi;
+            }
+        }
+        __syncwarp();
+
+        // ---- phase 2: gather + weighted reduction, one query at a time ----
+        const float4 *vb = reinterpret_cast<const float4 *>(value) + n * (long long)d.S * M * 8 + chunk;
+        for (int qi = 0; qi < cnt; ++qi) {
+            const uint2 *rq = rec + (size_t)qi * LP * 4 + corner;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int sp = 0; sp < LP; ++sp) {
+                const uint2 e = rq[sp * 4];
+                if (e.x != kNoCorner) {
+                    const float4 v = ldg_keep_f4(vb + e.x);
+                    const float w = __uint_as_float(e.y);
+                    acc.x = fmaf(w, v.x, acc.x);
+                    acc.y = fmaf(w, v.y, acc.y);
+                    acc.z = fmaf(w, v.z, acc.z);
+                    acc.w = fmaf(w, v.w, acc.w);
+                }
+            }
+            // sum the 4 corner groups (lane bits 3 and 4); lane ends with channel 4*chunk+corner
+            const bool up16 = lane & 16, up8 = lane & 8;
+            float a0 = up16 ? acc.z : acc.x, a1 = up16 ? acc.w : acc.y;
+            const float s0 = up16 ? acc.x : acc.z, s1 = up16 ? acc.y : acc.w;
+            a0 += __shfl_xor_sync(kFullMask, s0, 16);
+            a1 += __shfl_xor_sync(kFullMask, s1, 16);
+            const float keep = up8 ? a1 : a0, send = up8 ? a0 : a1;
+            const float res = keep + __shfl_xor_sync(kFullMask, send, 8);
+            float *o = out + ((n * d.Lq + q0 + qi) * M + m) * 32LL + chunk * 4 + corner;
+            stg_stream_f1(o, res);
+        }
+        __syncwarp();   // records are overwritten by the next item
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+template <int LP, int WARPS, int TILE_W>
+static cudaError_t launch_fwd_cfg(const float *value, const int64_t *shapes, const int64_t *lstart,
+                                  const float *loc, const float *attw, const Dims &d,
+                                  float *out, cudaStream_t stream) {
+    using Cfg = FwdCfg<LP, WARPS, TILE_W>;
+    auto kern = msda_fwd_d32_kernel<LP, WARPS, TILE_W>;
+    static int ctas_per_sm = 0;   // immutable after first use
+    if (ctas_per_sm == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)Cfg::kSmem);
+        if (e != cudaSuccess) return e;
+        int nb = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, WARPS * 32, Cfg::kSmem);
+        if (e != cudaSuccess) return e;
+        ctas_per_sm = nb > 0 ? nb : 1;
+    }
+    int per_sm = ctas_per_sm;
+    const int cap = option_value(OPT_CTAS_PER_SM);
+    if (cap > 0 && cap < per_sm) per_sm = cap;
+    // every group holds at least one query, so items <= N*M*Lq
+    long long blocks = (long long)sm_count() * per_sm;
+    const long long items_ub = (long long)d.N * d.M * d.Lq;
+    if (blocks > items_ub) blocks = items_ub;
+    if (blocks < 1) blocks = 1;
+    const int want_spatial = option_value(OPT_TILE_ORDER) != 1;
+    kern<<<(unsigned)blocks, WARPS * 32, Cfg::kSmem, stream>>>(value, shapes, lstart, loc, attw, d,
+                                                              want_spatial, out);
+    note_launch();
+    return cudaGetLastError();
+}
+
+template <int LP>
+static cudaError_t launch_fwd_lp(const float *value, const int64_t *shapes, const int64_t *lstart,
+                                 const float *loc, const float *attw, const Dims &d, float *out,
+                                 cudaStream_t stream) {
+    switch (option_value(OPT_FWD_VARIANT)) {
+        case 1: return launch_fwd_cfg<LP, 8, 8>(value, shapes, lstart, loc, attw, d, out, stream);
+        case 3: return launch_fwd_cfg<LP, 32, 16>(value, shapes, lstart, loc, attw, d, out, stream);
+        case 4: return launch_fwd_cfg<LP, 16, 8>(value, shapes, lstart, loc, attw, d, out, stream);
+        case 2:
+        default: return launch_fwd_cfg<LP, 16, 16>(value, shapes, lstart, loc, attw, d, out, stream);
+    }
+}
+
+// Returns cudaErrorInvalidConfiguration-free status; `handled` tells the caller
+// whether this specialised path took the problem (otherwise use the generic kernel).
+cudaError_t launch_fwd_d32(const float *value, const int64_t *shapes, const int64_t *lstart,
+                           const float *loc, const float *attw, const Dims &d, float *out,
+                           cudaStream_t stream, bool *handled) {
+    *handled = true;
+    const int LP = d.L * d.P;
+    if (d.D != 32 || (long long)d.S * d.M * 8 >= 0x7fffffffLL) {
+        *handled = false;
+        return cudaSuccess;
+    }
+    switch (LP) {
+        case 4: return launch_fwd_lp<4>(value, shapes, lstart, loc, attw, d, out, stream);
+        case 8: return launch_fwd_lp<8>(value, shapes, lstart, loc, attw, d, out, stream);
+        case 12: return launch_fwd_lp<12>(value, shapes, lstart, loc, attw, d, out, stream);
+        case 16: return launch_fwd_lp<16>(value, shapes, lstart, loc, attw, d, out, stream);
+        default: *handled = false; return cudaSuccess;
+    }
+}
+
+}  // namespace msda

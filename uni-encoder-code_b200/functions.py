@@ -1,0 +1,34 @@
+"""Autograd wrapper with the reference's interface:
+``MSDeformAttnFunction.apply(value, spatial_shapes, level_start_index, sampling_locations,
+attention_weights, im2col_step)`` (ops/functions/ms_deform_attn_func.py:35-52).
+
+The reference's own ``MSDeformAttnFunction`` also runs unchanged on top of
+``dropin/MultiScaleDeformableAttention.py``; this mirror exists so that code on a box
+without the reference checkout (the GPU box, bench.py) has the same entry point.
+"""
+from __future__ import annotations
+
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import ops
+
+
+class MSDeformAttnFunction(Function):
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                attention_weights, im2col_step):
+        ctx.im2col_step = im2col_step
+        output = ops.ms_deform_attn_forward(value, value_spatial_shapes, value_level_start_index,
+                                            sampling_locations, attention_weights, im2col_step)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index,
+                              sampling_locations, attention_weights)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, lsi, loc, w = ctx.saved_tensors
+        grad_value, grad_loc, grad_w = ops.ms_deform_attn_backward(
+            value, shapes, lsi, loc, w, grad_output, ctx.im2col_step)
+        return grad_value, None, None, grad_loc, grad_w, None

@@ -1,0 +1,121 @@
+"""Host side of the drop-in boundary: the two functions the reference's pybind11 module
+``MultiScaleDeformableAttention`` exports (ops/src/vision.cpp:18-21), re-implemented as
+thin Python over the C ABI (include/msda_b200.h).
+
+Argument meaning, order, return types and error behaviour follow the reference's
+dispatch + host wrappers (ops/src/ms_deform_attn.h:25-66,
+ops/src/cuda/ms_deform_attn_cuda.cu:25-85 and :88-158):
+
+* a non-CUDA ``value`` raises ``RuntimeError("Not implemented on the CPU")``
+  (ms_deform_attn.h:43,65) -- there is no CPU path here either;
+* every tensor must be contiguous and on a CUDA device (cu:33-43, :98-110);
+* ``im2col_step_ = min(batch, im2col_step)`` must divide ``batch`` (cu:55-57, :122-124).
+  It is validated for error parity and otherwise ignored: one launch covers the batch;
+* dtype float32 or float64 (AT_DISPATCH_FLOATING_TYPES, cu:69,139); the shape tensors
+  are int64 on the device (``.data<int64_t>()``, cu:72-73);
+* outputs are allocated here with torch's caching allocator on the current stream
+  (the reference allocates with ``value.options()``, cu:59, :126-128); the C side never
+  allocates, frees or synchronises.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+_FWD = {torch.float32: _lib.lib.msda_b200_forward_f32, torch.float64: _lib.lib.msda_b200_forward_f64}
+_BWD = {torch.float32: _lib.lib.msda_b200_backward_f32, torch.float64: _lib.lib.msda_b200_backward_f64}
+
+
+def _check_common(named, im2col_step, opname):
+    value = named[0][1]
+    if not isinstance(value, torch.Tensor) or not value.is_cuda:
+        raise RuntimeError("Not implemented on the CPU")                     # ms_deform_attn.h:43,65
+    for name, t in named:
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name} tensor has to be contiguous")        # cu:33-37
+    for name, t in named:
+        if not t.is_cuda:
+            raise RuntimeError(f"{name} must be a CUDA tensor")              # cu:39-43
+        if t.device != value.device:
+            raise RuntimeError(f"{name} is on {t.device}, value is on {value.device}")
+    if value.dtype not in _FWD:
+        raise RuntimeError(f'"{opname}" not implemented for \'{value.dtype}\'')   # cu:69,139
+    _, shapes, lsi, loc, w = (t for _, t in named[:5])
+    for name, t in named[1:3]:
+        if t.dtype != torch.int64:
+            raise RuntimeError(f"expected scalar type Long but found {t.dtype} for {name}")
+    for name, t in named[3:]:
+        if t.dtype != value.dtype:
+            raise RuntimeError(f"expected scalar type {value.dtype} but found {t.dtype} for {name}")
+    if value.dim() != 4 or loc.dim() != 6 or shapes.dim() != 2 or shapes.size(1) != 2:
+        raise RuntimeError("value must be [N,S,M,D], sampling_loc [N,Lq,M,L,P,2], spatial_shapes [L,2]")
+    N, S, M, D = value.shape
+    L = shapes.size(0)
+    Lq, P = loc.size(1), loc.size(4)
+    if tuple(loc.shape) != (N, Lq, M, L, P, 2) or w.numel() != N * Lq * M * L * P or lsi.numel() != L:
+        raise RuntimeError(
+            f"inconsistent shapes: value {tuple(value.shape)}, spatial_shapes {tuple(shapes.shape)}, "
+            f"level_start_index {tuple(lsi.shape)}, sampling_loc {tuple(loc.shape)}, "
+            f"attn_weight {tuple(w.shape)}")
+    step = min(N, int(im2col_step))
+    if step <= 0 or N % step != 0:
+        raise RuntimeError(f"batch({N}) must divide im2col_step({step})")     # cu:57, :124
+    return N, S, M, D, L, Lq, P
+
+
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                           im2col_step):
+    """-> output [N, Lq, M*D]  (vision.cpp:19; ms_deform_attn_cuda.cu:25-85)."""
+    named = [("value", value), ("spatial_shapes", spatial_shapes),
+             ("level_start_index", level_start_index), ("sampling_loc", sampling_loc),
+             ("attn_weight", attn_weight)]
+    N, S, M, D, L, Lq, P = _check_common(named, im2col_step, "ms_deform_attn_forward_cuda")
+    with torch.cuda.device(value.device):
+        output = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+        rc = _FWD[value.dtype](
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+            sampling_loc.data_ptr(), attn_weight.data_ptr(), N, S, M, D, L, Lq, P,
+            output.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "ms_deform_attn_forward")
+    return output
+
+
+def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                            grad_output, im2col_step):
+    """-> [grad_value, grad_sampling_loc, grad_attn_weight]  (vision.cpp:20; cu:88-158)."""
+    named = [("value", value), ("spatial_shapes", spatial_shapes),
+             ("level_start_index", level_start_index), ("sampling_loc", sampling_loc),
+             ("attn_weight", attn_weight), ("grad_output", grad_output)]
+    N, S, M, D, L, Lq, P = _check_common(named, im2col_step, "ms_deform_attn_backward_cuda")
+    if grad_output.numel() != N * Lq * M * D:
+        raise RuntimeError(f"grad_output has {grad_output.numel()} elements, expected {N * Lq * M * D}")
+    with torch.cuda.device(value.device):
+        grad_value = torch.zeros_like(value)            # accumulated by reductions (cu:126)
+        grad_loc = torch.empty_like(sampling_loc)       # fully overwritten (cf. cu:127)
+        grad_w = torch.empty_like(attn_weight)          # fully overwritten (cf. cu:128)
+        rc = _BWD[value.dtype](
+            grad_output.data_ptr(), value.data_ptr(), spatial_shapes.data_ptr(),
+            level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
+            N, S, M, D, L, Lq, P, grad_value.data_ptr(), grad_loc.data_ptr(), grad_w.data_ptr(),
+            torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "ms_deform_attn_backward")
+    return [grad_value, grad_loc, grad_w]
+
+
+def debug_indices(value_shape, spatial_shapes, level_start_index, sampling_loc):
+    """Integer known-answer hook (msda_b200_debug_indices_f32): (idx int32 [...,4], off int64 [...,4])."""
+    N, S, M, D = (int(x) for x in value_shape)
+    if not sampling_loc.is_cuda or sampling_loc.dtype != torch.float32 or not sampling_loc.is_contiguous():
+        raise RuntimeError("sampling_loc must be a contiguous float32 CUDA tensor")
+    L = spatial_shapes.size(0)
+    Lq, P = sampling_loc.size(1), sampling_loc.size(4)
+    with torch.cuda.device(sampling_loc.device):
+        idx = torch.empty(tuple(sampling_loc.shape[:-1]) + (4,), dtype=torch.int32, device=sampling_loc.device)
+        off = torch.empty(tuple(sampling_loc.shape[:-1]) + (4,), dtype=torch.int64, device=sampling_loc.device)
+        rc = _lib.lib.msda_b200_debug_indices_f32(
+            spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_loc.data_ptr(),
+            N, S, M, D, L, Lq, P, idx.data_ptr(), off.data_ptr(),
+            torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "debug_indices")
+    return idx, off
