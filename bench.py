@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- MSDeformAttn forward+backward throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--mode model|uniform]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference's CPU path on the host cores
+
+A "step" is one forward + one backward pass of the MSDA hot path over one synthetic batch
+(default workload: BASELINE configs[1], the 512x1024 Cityscapes crop pyramid, batch 8 per GPU,
+fp32).  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+
+Timing: per-step CUDA events on the launching stream; an untimed 512 MiB L2 flush between steps;
+W >= 3 warm-up steps; max over ranks; SM clocks / throttle reasons sampled through NVML during
+the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "msda_fwd_bwd_queries_per_s"
+UNIT = "queries/s"
+DEFAULT_WORKLOAD = "cityscapes_512x1024_b8"
+NOMINAL_HBM_GBS = 8000.0          # north_star's "~8 TB/s"
+FALLBACK_HBM_GBS = 6650.0         # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=50)
+    p.add_argument("--warmup", type=int, default=10)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    p.add_argument("--mode", default="model", choices=["model", "uniform"])
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--cpu-sample-batch", type=int, default=2)
+    return p.parse_args()
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- CPU arms
+def cpu_reference_run(workload_name, mode, sample_batch, steps, warmup):
+    """The reference's CPU path for this op is ms_deform_attn_core_pytorch
+    (ops/functions/ms_deform_attn_func.py:55-75) + autograd.  It is Python and cannot travel to
+    the GPU box, so the timed code is its restatement oracle.core_grid_sample (kind "port"),
+    pinned to the reference by tests/golden.  Each step is forward+backward on `sample_batch`
+    images of the workload's shape, with every host thread torch can use."""
+    import torch
+    from __graft_entry__ import load_oracle, load_package
+    oracle = load_oracle()
+    syn = load_package().synthetic
+    torch.set_num_threads(os.cpu_count() or 1)
+    w = syn.WORKLOADS[workload_name]
+    inp = syn.make_inputs(w.levels, sample_batch, w.heads, w.channels, w.points, mode=mode, seed=0)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        oracle.core_grid_sample_grads(inp["value"], inp["spatial_shapes"], inp["sampling_locations"],
+                                      inp["attention_weights"], inp["grad_output"])
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    q = sample_batch * w.spatial_size
+    mean = sum(times) / len(times)
+    return {"value": q / mean, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "host_cpus": os.cpu_count(),
+            "sample": f"fwd+bwd of oracle.core_grid_sample (restated ms_deform_attn_core_pytorch, fp32) "
+                      f"on {sample_batch} image(s) of {workload_name} = {q} queries/step, "
+                      f"{len(times)} timed steps after {warmup} warm-up",
+            "ms_per_step": mean * 1e3}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # ~0.6 s per step on 8 cores: honour K and W up to a cap that keeps the run within minutes
+    steps = max(1, min(args.steps, 100))
+    warmup = max(1, min(args.warmup, 10))
+    base = cpu_reference_run(args.workload, args.mode, args.cpu_sample_batch, steps, warmup)
+    from __graft_entry__ import load_package
+    w = load_package().synthetic.WORKLOADS[args.workload]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT,
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": base["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{args.workload} fwd+bwd (BASELINE.json configs[1])",
+                   "levels": [list(x) for x in w.levels], "batch_per_gpu": w.batch,
+                   "loc_mode": args.mode,
+                   "note": "CPU arm: bounded sample per step, see cpu_baseline.sample"},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_package
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    pkg = load_package()
+    lib = pkg._lib.lib
+    syn = pkg.synthetic
+    w = syn.WORKLOADS[args.workload]
+    # batch sharding: every rank owns its own images; weak scaling, no data-path collective
+    host = syn.make_inputs(w.levels, w.batch, w.heads, w.channels, w.points, mode=args.mode,
+                           seed=1000 + rank)
+    d = {k: v.to(dev) for k, v in host.items()}
+    N, S, M, D = d["value"].shape
+    L, Lq, P = len(w.levels), S, w.points
+    out = torch.empty(N, Lq, M * D, device=dev)
+    gv = torch.empty_like(d["value"])
+    gl = torch.empty_like(d["sampling_locations"])
+    gw = torch.empty_like(d["attention_weights"])
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+    dims = (N, S, M, D, L, Lq, P)
+    ptr = {k: v.data_ptr() for k, v in d.items()}
+
+    def fwd():
+        pkg._lib.check(lib.msda_b200_forward_f32(
+            ptr["value"], ptr["spatial_shapes"], ptr["level_start_index"], ptr["sampling_locations"],
+            ptr["attention_weights"], *dims, out.data_ptr(), sp), "forward")
+
+    def bwd():
+        pkg._lib.check(lib.msda_b200_backward_f32(
+            ptr["grad_output"], ptr["value"], ptr["spatial_shapes"], ptr["level_start_index"],
+            ptr["sampling_locations"], ptr["attention_weights"], *dims, gv.data_ptr(), gl.data_ptr(),
+            gw.data_ptr(), sp), "backward")
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    marks = [[ev() for _ in range(4)] for _ in range(args.steps)]
+
+    def step(m=None):
+        flush.zero_()                       # untimed: evict inputs/outputs from the 126 MB L2
+        if m: m[0].record(stream)
+        fwd()
+        if m: m[1].record(stream)
+        gv.zero_()                          # grad_value is accumulated with reductions
+        if m: m[2].record(stream)
+        bwd()
+        if m: m[3].record(stream)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n0 = pkg.launch_count()
+    with ClockSampler(local_rank) as clocks:
+        t_wall0 = time.perf_counter()
+        for i in range(args.steps):
+            step(marks[i])
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter() - t_wall0
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches = pkg.launch_count() - n0
+
+    step_ms = [m[0].elapsed_time(m[3]) for m in marks]
+    fwd_ms = [m[0].elapsed_time(m[1]) for m in marks]
+    zero_ms = [m[1].elapsed_time(m[2]) for m in marks]
+    bwd_ms = [m[2].elapsed_time(m[3]) for m in marks]
+    total_ms = sum(step_ms)
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    queries_rank = N * Lq
+    ms_per_step = total_ms / args.steps
+    value = world * queries_rank / (ms_per_step * 1e-3)
+
+    # ---- end to end through the plugin API with host buffers (rank-local, then max over ranks)
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(pkg, host, dev, world, max(3, min(args.steps, 10)), dist if world > 1 else None)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    bwd_mean = statistics.mean(bwd_ms)
+    fwd_mean = statistics.mean(fwd_ms)
+    bwd_bytes = queries_rank * syn.BWD_BYTES_PER_QUERY
+    fwd_bytes = queries_rank * syn.FWD_BYTES_PER_QUERY
+    achieved = bwd_bytes / (bwd_mean * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": f"{args.workload} fwd+bwd (BASELINE.json configs[1])",
+            "levels": [list(x) for x in w.levels], "batch_per_gpu": N, "heads": M, "channels": D,
+            "points": P, "queries_per_step_per_gpu": queries_rank, "loc_mode": args.mode,
+            "l2": "512 MiB memset between steps (untimed); step working set 640 MB > 126 MB L2",
+            "step": "forward kernel + grad_value memset + backward kernel, inputs resident in HBM",
+            "sharding": "batch (independent images per rank), no data-path collective",
+        },
+        "roofline": {
+            "bound": "hbm", "kernel": "msda_bwd_d32_kernel", "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": bwd_bytes, "ms_per_launch": bwd_mean,
+            "frac_of_nominal_8TBs": achieved / NOMINAL_HBM_GBS,
+        },
+        "kernels": {
+            "forward": {"ms": fwd_mean, "algorithmic_GBs": fwd_bytes / (fwd_mean * 1e-3) / 1e9,
+                        "frac": fwd_bytes / (fwd_mean * 1e-3) / 1e9 / peak},
+            "grad_value_memset": {"ms": statistics.mean(zero_ms)},
+            "backward": {"ms": bwd_mean, "algorithmic_GBs": achieved, "frac": achieved / peak},
+            "fwd_bwd": {"algorithmic_GBs": (fwd_bytes + bwd_bytes) / (ms_per_step * 1e-3) / 1e9,
+                        "frac": (fwd_bytes + bwd_bytes) / (ms_per_step * 1e-3) / 1e9 / peak},
+        },
+        "gpu_launches": launches,
+        "clocks": clocks.summary(),
+        "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu_baseline:
+        base = cpu_reference_run(args.workload, args.mode, args.cpu_sample_batch, 3, 1)
+        line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(pkg, host, dev, world, steps, dist):
+    """Same metric through the public plugin call (MSDeformAttnFunction.apply + autograd backward)
+    with HOST buffers: every step copies the inputs from pinned host memory to the device and the
+    four results back to pinned host memory, all inside the timed region."""
+    import torch
+    pin = {k: v.pin_memory() for k, v in host.items()}
+    res_host = None
+    stream = torch.cuda.current_stream()
+    h2d = sum(v.numel() * v.element_size() for v in pin.values())
+    d2h = 0
+
+    def one():
+        nonlocal res_host, d2h
+        d = {k: v.to(dev, non_blocking=True) for k, v in pin.items()}
+        value = d["value"].requires_grad_(True)
+        loc = d["sampling_locations"].requires_grad_(True)
+        wts = d["attention_weights"].requires_grad_(True)
+        out = pkg.MSDeformAttnFunction.apply(value, d["spatial_shapes"], d["level_start_index"],
+                                             loc, wts, 128)
+        out.backward(d["grad_output"])
+        results = (out.detach(), value.grad, loc.grad, wts.grad)
+        if res_host is None:
+            res_host = [torch.empty(r.shape, dtype=r.dtype, pin_memory=True) for r in results]
+            d2h = sum(r.numel() * r.element_size() for r in results)
+        for h, r in zip(res_host, results):
+            h.copy_(r, non_blocking=True)
+
+    for _ in range(3):
+        one()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        one()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    q = host["value"].shape[0] * host["sampling_locations"].shape[1]
+    return {"value": world * q * steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "ms_per_step": ms / steps, "steps": steps,
+            "api": "MSDeformAttnFunction.apply + .backward, pinned host <-> device copies per step"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -123,7 +123,9 @@ int msda_b200_debug_indices_f32(const int64_t *spatial_shapes, const int64_t *le
  * are what the shipped path uses.  Not thread-safe against concurrent launches.
  *   "fwd_variant"  0 = auto, other values select a specific forward kernel
  *   "bwd_variant"  0 = auto, other values select a specific backward kernel
- *   "tile_order"   0 = auto, 1 = linear query order, 2 = spatial tiles
+ *   "tile_order"   0 = auto (2-D tiles when the queries are laid out like the value pixels),
+ *                  1 = groups of consecutive queries
+ *   "ctas_per_sm"  0 = occupancy limit, k > 0 caps the persistent grid at k CTAs per SM
  */
 int msda_b200_set_option(const char *name, int value);
 int msda_b200_get_option(const char *name, int *value);

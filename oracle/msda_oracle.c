@@ -40,19 +40,43 @@
 #include <string.h>
 
 #define MSDA_ORACLE_BODY
+/* REAL: type of value / weights / accumulation.  GEO: type the sampling-point
+ * geometry (pixel coordinate, floor, fractions) is computed in.
+ *   f32     = (float,  float)   the reference CUDA kernel's fp32 arithmetic
+ *   f64     = (double, double)  the float golden
+ *   f64g32  = (double, float)   fp32 geometry exactly as the reference kernel computes
+ *             it (its `loc*W - 0.5` is rounded to fp32, cuh:290-291), everything after
+ *             that in fp64: "the reference fp32 kernel with exact accumulation".  This
+ *             is what an fp32 implementation can be held to 1e-5 against on level
+ *             sizes that are not powers of two, where the fp32 product loc*W is
+ *             inexact and the reference's own fp32 paths sit ~1.7e-5 from fp64. */
 #define REAL float
+#define GEO float
 #define SUFFIX(name) name##_f32
 #define FLOOR floorf
 #include "msda_oracle.c"
 #undef REAL
+#undef GEO
 #undef SUFFIX
 #undef FLOOR
 
 #define REAL double
+#define GEO double
 #define SUFFIX(name) name##_f64
 #define FLOOR floor
 #include "msda_oracle.c"
 #undef REAL
+#undef GEO
+#undef SUFFIX
+#undef FLOOR
+
+#define REAL double
+#define GEO float
+#define SUFFIX(name) name##_f64g32
+#define FLOOR floorf
+#include "msda_oracle.c"
+#undef REAL
+#undef GEO
 #undef SUFFIX
 #undef FLOOR
 
@@ -72,19 +96,20 @@ typedef struct {
 } SUFFIX(point_t);
 
 static inline SUFFIX(point_t)
-SUFFIX(decompose)(REAL loc_x, REAL loc_y, int H, int W)
+SUFFIX(decompose)(REAL loc_x_, REAL loc_y_, int H, int W)
 {
     SUFFIX(point_t) pt;
+    const GEO loc_x = (GEO)loc_x_, loc_y = (GEO)loc_y_;
     /* two roundings each: product, then difference (cuh:290-291) */
-    volatile REAL hm = loc_y * (REAL)H;
-    volatile REAL wm = loc_x * (REAL)W;
-    const REAL h_im = hm - (REAL)0.5;
-    const REAL w_im = wm - (REAL)0.5;
+    volatile GEO hm = loc_y * (GEO)H;
+    volatile GEO wm = loc_x * (GEO)W;
+    const GEO h_im = hm - (GEO)0.5;
+    const GEO w_im = wm - (GEO)0.5;
     pt.valid = (h_im > -1 && w_im > -1 && h_im < H && w_im < W);
     pt.h_low = (int)FLOOR(h_im);
     pt.w_low = (int)FLOOR(w_im);
-    pt.lh = h_im - (REAL)pt.h_low;
-    pt.lw = w_im - (REAL)pt.w_low;
+    pt.lh = (REAL)(h_im - (GEO)pt.h_low);
+    pt.lw = (REAL)(w_im - (GEO)pt.w_low);
     const int h_high = pt.h_low + 1, w_high = pt.w_low + 1;
     pt.cmask = 0;
     if (pt.valid) {

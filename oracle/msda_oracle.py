@@ -72,8 +72,11 @@ def _dims(value, shapes, loc):
     return [ctypes.c_int(int(x)) for x in (N, S, M, D, L, Lq, P)]
 
 
-def _suffix(dtype):
-    return {np.float32: "f32", np.float64: "f64"}[np.dtype(dtype).type]
+def _suffix(dtype, geometry=None):
+    base = {np.float32: "f32", np.float64: "f64"}[np.dtype(dtype).type]
+    if geometry is not None and np.dtype(geometry) == np.float32 and base == "f64":
+        return "f64g32"     # fp32 sampling-point geometry, fp64 accumulation
+    return base
 
 
 def indices(shapes, level_start, loc, value_shape, dtype=np.float32):
@@ -97,20 +100,24 @@ def indices(shapes, level_start, loc, value_shape, dtype=np.float32):
     return idx, off
 
 
-def forward(value, shapes, level_start, loc, weight, dtype=np.float64):
-    """out [N, Lq, M*D]; arithmetic in ``dtype`` (fp64 on fp32 inputs is the golden)."""
+def forward(value, shapes, level_start, loc, weight, dtype=np.float64, geometry=None):
+    """out [N, Lq, M*D]; arithmetic in ``dtype`` (fp64 on fp32 inputs is the golden).
+
+    ``geometry=np.float32`` with ``dtype=np.float64`` computes the sampling-point geometry
+    (pixel coordinate, floor, fractions) in fp32 exactly like the reference kernel
+    (cuh:290-291, 43-50) and everything after it in fp64."""
     lib = _load()
     value, loc, weight = _np(value, dtype), _np(loc, dtype), _np(weight, dtype)
     shapes, level_start = _np(shapes, np.int64), _np(level_start, np.int64)
     dims = _dims(value, shapes, loc)
     N, S, M, D = value.shape
     out = np.empty((N, loc.shape[1], M * D), dtype)
-    getattr(lib, "msda_oracle_forward_" + _suffix(dtype))(
+    getattr(lib, "msda_oracle_forward_" + _suffix(dtype, geometry))(
         _ptr(value), _ptr(shapes), _ptr(level_start), _ptr(loc), _ptr(weight), *dims, _ptr(out))
     return out
 
 
-def backward(grad_out, value, shapes, level_start, loc, weight, dtype=np.float64):
+def backward(grad_out, value, shapes, level_start, loc, weight, dtype=np.float64, geometry=None):
     """(grad_value, grad_sampling_loc, grad_attn_weight), shapes as their primals."""
     lib = _load()
     value, loc, weight = _np(value, dtype), _np(loc, dtype), _np(weight, dtype)
@@ -120,7 +127,7 @@ def backward(grad_out, value, shapes, level_start, loc, weight, dtype=np.float64
     gv = np.zeros_like(value)
     gl = np.empty_like(loc)
     gw = np.empty_like(weight)
-    getattr(lib, "msda_oracle_backward_" + _suffix(dtype))(
+    getattr(lib, "msda_oracle_backward_" + _suffix(dtype, geometry))(
         _ptr(grad_out), _ptr(value), _ptr(shapes), _ptr(level_start), _ptr(loc), _ptr(weight),
         *dims, _ptr(gv), _ptr(gl), _ptr(gw))
     return gv, gl, gw

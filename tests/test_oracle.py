@@ -112,3 +112,22 @@ def test_oracle_linearity_and_zero_weight(oracle, pkg):
     assert np.allclose(o2, 2 * o1, rtol=0, atol=1e-12)
     o0 = oracle.forward(inp["value"], *a, 0 * inp["attention_weights"])
     assert not o0.any()
+
+
+def test_fp32_geometry_mode(oracle, pkg):
+    """geometry=float32: on power-of-two levels the fp32 product loc*W is exact (only `- 0.5` can
+    round, and only for coordinates in (-0.5, 0)), so it reproduces pure fp64 to ~1e-7; elsewhere it
+    agrees with the all-fp32 restatement to accumulation rounding."""
+    inp = pkg.synthetic.make_inputs([(4, 8), (8, 16), (16, 32)], 1, heads=2, mode="model", seed=3)
+    a = (inp["value"], inp["spatial_shapes"], inp["level_start_index"], inp["sampling_locations"],
+         inp["attention_weights"])
+    assert np.abs(oracle.forward(*a) - oracle.forward(*a, geometry=np.float32)).max() <= 1e-6
+    for x, y in zip(oracle.backward(inp["grad_output"], *a),
+                    oracle.backward(inp["grad_output"], *a, geometry=np.float32)):
+        assert rel_err(y, x) <= 1e-6
+    inp = pkg.synthetic.make_inputs([(12, 39), (24, 78)], 1, heads=2, mode="model", seed=4)
+    a = (inp["value"], inp["spatial_shapes"], inp["level_start_index"], inp["sampling_locations"],
+         inp["attention_weights"])
+    mixed = oracle.forward(*a, geometry=np.float32)
+    assert np.abs(oracle.forward(*a, dtype=np.float32) - mixed).max() <= 2e-6
+    assert np.abs(oracle.forward(*a) - mixed).max() <= 1e-4

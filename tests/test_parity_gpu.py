@@ -85,27 +85,50 @@ CASES = [
 ]
 
 
+def _pow2(levels):
+    return all((h & (h - 1)) == 0 and (w & (w - 1)) == 0 for h, w in levels)
+
+
+def oracle_refs(oracle, inp, geometry=np.float32):
+    """fp64 oracle outputs.  geometry=float32 (default) evaluates the sampling-point geometry in
+    fp32 exactly as the reference kernel does (`loc*W - 0.5` rounded to fp32, cuh:290-291) and
+    everything after it in fp64.  When a level size is not a power of two the fp32 product loc*W is
+    inexact: the reference's own fp32 paths then sit ~1.7e-5 from a pure-fp64 evaluation and a few
+    points per million land in a different bilinear cell (floor is discontinuous), so a pure-fp64
+    oracle cannot be matched to 1e-5 / 1e-4 by ANY fp32 implementation of the reference formula."""
+    a = (inp["value"], inp["spatial_shapes"], inp["level_start_index"], inp["sampling_locations"],
+         inp["attention_weights"])
+    return (oracle.forward(*a, geometry=geometry),) + tuple(
+        oracle.backward(inp["grad_output"], *a, geometry=geometry))
+
+
 @pytest.mark.parametrize("levels,batch,heads,channels,points,nq,mode", CASES)
 def test_kernels_match_oracle(pkg, oracle, levels, batch, heads, channels, points, nq, mode):
     inp = pkg.synthetic.make_inputs(levels, batch, heads, channels, points, num_query=nq, mode=mode,
                                     seed=42)
     out, gv, gl, gw = run_fwd_bwd(pkg, to_dev(inp))
+    check_against(out, gv, gl, gw, *oracle_refs(oracle, inp), tag=str(levels))
     a = (inp["value"], inp["spatial_shapes"], inp["level_start_index"], inp["sampling_locations"],
          inp["attention_weights"])
-    ref_out = oracle.forward(*a)
-    rgv, rgl, rgw = oracle.backward(inp["grad_output"], *a)
-    check_against(out, gv, gl, gw, ref_out, rgv, rgl, rgw, tag=str(levels))
+    pure = oracle.forward(*a)
+    mine = np.abs(out.double().cpu().numpy() - pure).max()
+    if _pow2(levels):
+        # power-of-two level sizes: the fp32 coordinate arithmetic is exact, so the pure fp64
+        # evaluation is held to the same tolerances
+        check_against(out, gv, gl, gw, pure, *oracle.backward(inp["grad_output"], *a), tag="pure fp64")
+    else:
+        # otherwise we may not be further from pure fp64 than the reference's own fp32 arithmetic
+        ref32 = np.abs(oracle.forward(*a, dtype=np.float32).astype(np.float64) - pure).max()
+        assert mine <= 1.25 * ref32 + 1e-6, (mine, ref32)
 
 
 @pytest.mark.parametrize("fwd_variant,bwd_variant,tile_order", [
-    (1, 1, 0), (2, 2, 0), (3, 3, 0), (4, 4, 0), (2, 2, 1), (63, 63, 0)])
+    (1, 1, 0), (2, 2, 0), (3, 3, 0), (4, 4, 0), (2, 2, 1), (5, 1, 0), (6, 2, 0), (7, 2, 1), (8, 4, 0),
+    (63, 63, 0)])
 def test_kernel_variants_agree(pkg, oracle, fwd_variant, bwd_variant, tile_order):
     """Every tile shape / query order / the generic kernel computes the same function."""
     inp = pkg.synthetic.make_inputs([(5, 11), (10, 22), (20, 44)], 2, mode="model", seed=3)
-    a = (inp["value"], inp["spatial_shapes"], inp["level_start_index"], inp["sampling_locations"],
-         inp["attention_weights"])
-    ref_out = oracle.forward(*a)
-    rgv, rgl, rgw = oracle.backward(inp["grad_output"], *a)
+    refs = oracle_refs(oracle, inp)
     try:
         pkg.set_option("fwd_variant", fwd_variant)
         pkg.set_option("bwd_variant", bwd_variant)
@@ -114,7 +137,7 @@ def test_kernel_variants_agree(pkg, oracle, fwd_variant, bwd_variant, tile_order
     finally:
         for k in ("fwd_variant", "bwd_variant", "tile_order"):
             pkg.set_option(k, 0)
-    check_against(out, gv, gl, gw, ref_out, rgv, rgl, rgw, tag=f"variant {fwd_variant}")
+    check_against(out, gv, gl, gw, *refs, tag=f"variant {fwd_variant}")
 
 
 # ---------------------------------------------------------------- integer work, bit-exact
@@ -164,6 +187,7 @@ def test_full_size_config1_forward_vs_oracle(pkg, oracle):
     d = to_dev(inp)
     out = pkg.ms_deform_attn_forward(d["value"], d["spatial_shapes"], d["level_start_index"],
                                      d["sampling_locations"], d["attention_weights"], 128)
+    # 1024x2048 pyramid: power-of-two level sizes -> pure fp64 evaluation is the reference
     ref = oracle.forward(inp["value"], inp["spatial_shapes"], inp["level_start_index"],
                          inp["sampling_locations"], inp["attention_weights"])
     assert np.abs(out.double().cpu().numpy() - ref).max() <= FWD_ABS_TOL
@@ -175,7 +199,7 @@ def test_full_size_config2_gradients_vs_oracle(pkg, oracle):
     out, gv, gl, gw = run_fwd_bwd(pkg, to_dev(inp))
     a = (inp["value"], inp["spatial_shapes"], inp["level_start_index"], inp["sampling_locations"],
          inp["attention_weights"])
-    ref_out = oracle.forward(*a)
+    ref_out = oracle.forward(*a)                      # pure fp64 (power-of-two pyramid)
     rgv, rgl, rgw = oracle.backward(inp["grad_output"], *a)
     check_against(out, gv, gl, gw, ref_out, rgv, rgl, rgw, tag="config2")
 
@@ -284,10 +308,7 @@ def test_dropin_module_and_autograd_function(pkg, oracle):
     direct = MSDA.ms_deform_attn_forward(d["value"], d["spatial_shapes"], d["level_start_index"],
                                          d["sampling_locations"], d["attention_weights"], 128)
     assert torch.equal(direct, out.detach())
-    a = (inp["value"], inp["spatial_shapes"], inp["level_start_index"], inp["sampling_locations"],
-         inp["attention_weights"])
-    rgv, rgl, rgw = oracle.backward(inp["grad_output"], *a)
-    check_against(out.detach(), v.grad, loc.grad, w.grad, oracle.forward(*a), rgv, rgl, rgw, tag="autograd")
+    check_against(out.detach(), v.grad, loc.grad, w.grad, *oracle_refs(oracle, inp), tag="autograd")
 
 
 def test_non_default_stream_and_cuda_graph(pkg):

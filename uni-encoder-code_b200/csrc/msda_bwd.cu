@@ -90,19 +90,9 @@ msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict_
                 const int l = lt.level_of[sp];
                 const int H = lt.H[l], W = lt.W[l];
                 const Geom<float> gm = decompose(xy.x, xy.y, H, W);
-                const float hh = 1.f - gm.lh, hw = 1.f - gm.lw;
-                const uint32_t base = ((uint32_t)lt.start[l] + (uint32_t)gm.h_low * (uint32_t)W +
-                                       (uint32_t)gm.w_low) * pix_stride + (uint32_t)m * 8u;
-                const uint32_t row_stride = (uint32_t)W * pix_stride;
                 uint4 lo, hi;
-                lo.x = (gm.cmask & 1) ? base : kNoCorner;
-                lo.y = __float_as_uint((gm.cmask & 1) ? (hh * hw) * aw : 0.f);
-                lo.z = (gm.cmask & 2) ? base + pix_stride : kNoCorner;
-                lo.w = __float_as_uint((gm.cmask & 2) ? (hh * gm.lw) * aw : 0.f);
-                hi.x = (gm.cmask & 4) ? base + row_stride : kNoCorner;
-                hi.y = __float_as_uint((gm.cmask & 4) ? (gm.lh * hw) * aw : 0.f);
-                hi.z = (gm.cmask & 8) ? base + row_stride + pix_stride : kNoCorner;
-                hi.w = __float_as_uint((gm.cmask & 8) ? (gm.lh * gm.lw) * aw : 0.f);
+                make_record<false>(gm, aw, (uint32_t)lt.start[l], (uint32_t)W, pix_stride,
+                                   (uint32_t)m * 8u, lo, hi);
                 uint4 *dst = reinterpret_cast<uint4 *>(rec + (size_t)s * 4);
                 dst[0] = lo;
                 dst[1] = hi;
@@ -128,14 +118,14 @@ msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict_
                 const uint2 e = rq[sp * 4];
                 float dot = 0.f;
                 if (e.x != kNoCorner) {
-                    const float4 v = ldg_keep_f4(vb + e.x);
+                    const float4 v = ldg_keep_f4(at_off16(vb, e.x));
                     const float w = __uint_as_float(e.y);
                     dot = fmaf(v.w, go.w, fmaf(v.z, go.z, fmaf(v.y, go.y, v.x * go.x)));
                     const float4 gv = make_float4(w * go.x, w * go.y, w * go.z, w * go.w);
                     if (VEC_RED) {
-                        red_add_f4(gvb + e.x, gv);
+                        red_add_f4(at_off16(gvb, e.x), gv);
                     } else {
-                        float *p = reinterpret_cast<float *>(gvb + e.x);
+                        float *p = reinterpret_cast<float *>(at_off16(gvb, e.x));
                         atomicAdd(p + 0, gv.x);
                         atomicAdd(p + 1, gv.y);
                         atomicAdd(p + 2, gv.z);

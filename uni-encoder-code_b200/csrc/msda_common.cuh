@@ -139,6 +139,68 @@ __device__ __forceinline__ void warp_queries(const LevelTable &lt, int L, int g,
 }
 
 // ---------------------------------------------------------------------------
+// Per-point record shared by the 32-channel kernels: for each of the 4 bilinear
+// corners {offset, weight}, offset in float4 units from the start of image n
+// (pixel, head m, channel 0), weight = bilinear corner weight * attention weight.
+//   ALIAS == false: a corner outside the level gets {kNoCorner, 0}.
+//   ALIAS == true : a corner outside the level of an otherwise valid point gets
+//                   the offset of an in-range corner of the SAME point with weight
+//                   0, so a warp can test one flag per point instead of four; the
+//                   aliased row is one the point reads anyway.  (0 * v == 0 unless v
+//                   is Inf/NaN, in which case the same row already poisons the
+//                   output through its own, non-aliased use or is weighted by an
+//                   exact 0 in the reference too.)  A point that fails the range
+//                   test (cuh:293) gets kNoCorner in all four slots either way.
+// ---------------------------------------------------------------------------
+template <bool ALIAS>
+__device__ __forceinline__ void make_record(const Geom<float> &gm, float aw, uint32_t level_start,
+                                            uint32_t W, uint32_t pix_stride, uint32_t head_off,
+                                            uint4 &lo, uint4 &hi) {
+    const float hh = 1.f - gm.lh, hw = 1.f - gm.lw;
+    // modular uint32 arithmetic: h_low / w_low may be -1; contributing corners always land on
+    // a true offset < 2^31 (checked on the host)
+    const uint32_t base = (level_start + (uint32_t)gm.h_low * W + (uint32_t)gm.w_low) * pix_stride + head_off;
+    const uint32_t row_stride = W * pix_stride;
+    uint32_t off[4] = {base, base + pix_stride, base + row_stride, base + row_stride + pix_stride};
+    float w[4] = {(hh * hw) * aw, (hh * gm.lw) * aw, (gm.lh * hw) * aw, (gm.lh * gm.lw) * aw};
+    const int cm = gm.cmask;
+    if (ALIAS) {
+        // which axis of each corner is out of range (only meaningful when cm != 0)
+        const int w_low_bad = !(cm & 0x5), w_high_bad = !(cm & 0xA);   // columns: corners {0,2} / {1,3}
+        const int h_low_bad = !(cm & 0x3), h_high_bad = !(cm & 0xC);   // rows:    corners {0,1} / {2,3}
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!(cm >> k & 1)) {
+                const int flip = (((k & 1) ? w_high_bad : w_low_bad) ? 1 : 0) |
+                                 (((k & 2) ? h_high_bad : h_low_bad) ? 2 : 0);
+                const int src = k ^ flip;
+                off[k] = cm ? (src == 0 ? off[0] : src == 1 ? off[1] : src == 2 ? off[2] : off[3]) : kNoCorner;
+                w[k] = 0.f;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!(cm >> k & 1)) {
+                off[k] = kNoCorner;
+                w[k] = 0.f;
+            }
+        }
+    }
+    lo = make_uint4(off[0], __float_as_uint(w[0]), off[1], __float_as_uint(w[1]));
+    hi = make_uint4(off[2], __float_as_uint(w[2]), off[3], __float_as_uint(w[3]));
+}
+
+// address = base + off16 * 16 in ONE instruction (IMAD.WIDE.U32); the compiler otherwise
+// splits a 64-bit base that depends on the image index into several adds per access
+template <typename T>
+__device__ __forceinline__ T *at_off16(T *base, uint32_t off16) {
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(r) : "r"(off16), "l"((unsigned long long)base));
+    return reinterpret_cast<T *>(r);
+}
+
+// ---------------------------------------------------------------------------
 // cache-hinted global accesses
 // ---------------------------------------------------------------------------
 // value rows are re-used by neighbouring queries: keep them in L1 (default .ca)
@@ -146,6 +208,11 @@ __device__ __forceinline__ float4 ldg_keep_f4(const float4 *p) {
     float4 r;
     asm("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ldg_keep_f1(const float *p) {
+    float r;
+    asm("ld.global.nc.f32 %0, [%1];" : "=f"(r) : "l"(p));
     return r;
 }
 // streamed once: do not allocate in L1

@@ -35,13 +35,17 @@ struct FwdCfg {
     static_assert(TILE_W % 8 == 0 && kGroup % TILE_W == 0, "tile shape");
 };
 
-template <int LP, int WARPS, int TILE_W>
+// LANES_PER_ROW = 8 : lane = corner*8 + chunk, one LDG.128 per point covers its 4 corner rows
+// LANES_PER_ROW = 32: lane = channel, one LDG.32 per corner row (a warp instruction touches
+//                     exactly one 128-byte line: one L1 wavefront, no intra-instruction replay)
+template <int LP, int WARPS, int TILE_W, int LANES_PER_ROW>
 __global__ void __launch_bounds__(WARPS * 32)
 msda_fwd_d32_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes,
                     const int64_t *__restrict__ lstart, const float *__restrict__ loc,
                     const float *__restrict__ attw, const Dims d, const int want_spatial,
                     float *__restrict__ out) {
     using Cfg = FwdCfg<LP, WARPS, TILE_W>;
+    constexpr bool kRowwise = LANES_PER_ROW == 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ LevelTable lt;
 
@@ -66,33 +70,32 @@ msda_fwd_d32_kernel(const float *__restrict__ value, const int64_t *__restrict__
         warp_queries(lt, d.L, g, warp, Cfg::kGroup, Cfg::kTileH, TILE_W, d.Lq, q0, cnt);
 
         // ---- phase 1: one sampling point per lane per round -> records ----
+        // all global loads of the item are issued before any of them is consumed
+        float2 xy[Cfg::kRounds];
+        float aw[Cfg::kRounds];
+#pragma unroll
+        for (int r = 0; r < Cfg::kRounds; ++r) {
+            const int s = r * 32 + lane;
+            const int qi = s / LP, sp = s - qi * LP;
+            xy[r] = make_float2(0.f, 0.f);
+            aw[r] = 0.f;
+            if (qi < cnt) {
+                const long long row = ((n * d.Lq + q0 + qi) * M + m) * (long long)LP + sp;
+                xy[r] = ldg_stream_f2(reinterpret_cast<const float2 *>(loc) + row);
+                aw[r] = ldg_stream_f1(attw + row);
+            }
+        }
 #pragma unroll
         for (int r = 0; r < Cfg::kRounds; ++r) {
             const int s = r * 32 + lane;
             const int qi = s / LP, sp = s - qi * LP;
             if (qi < cnt) {
-                const long long row = ((n * d.Lq + q0 + qi) * M + m) * (long long)LP + sp;
-                const float2 xy = ldg_stream_f2(reinterpret_cast<const float2 *>(loc) + row);
-                const float aw = ldg_stream_f1(attw + row);
                 const int l = lt.level_of[sp];
                 const int H = lt.H[l], W = lt.W[l];
-                const Geom<float> gm = decompose(xy.x, xy.y, H, W);
-                const float hh = 1.f - gm.lh, hw = 1.f - gm.lw;
-                // offset (float4 units inside image n) of pixel (h_low, w_low), head m
-                // (modular uint32 arithmetic: h_low / w_low may be -1; contributing corners
-                // always land on a true offset < 2^31, checked on the host)
-                const uint32_t base = ((uint32_t)lt.start[l] + (uint32_t)gm.h_low * (uint32_t)W +
-                                       (uint32_t)gm.w_low) * pix_stride + (uint32_t)m * 8u;
-                const uint32_t row_stride = (uint32_t)W * pix_stride;
+                const Geom<float> gm = decompose(xy[r].x, xy[r].y, H, W);
                 uint4 lo, hi;   // {off0, w0, off1, w1}, {off2, w2, off3, w3}
-                lo.x = (gm.cmask & 1) ? base : kNoCorner;
-                lo.y = __float_as_uint((gm.cmask & 1) ? (hh * hw) * aw : 0.f);
-                lo.z = (gm.cmask & 2) ? base + pix_stride : kNoCorner;
-                lo.w = __float_as_uint((gm.cmask & 2) ? (hh * gm.lw) * aw : 0.f);
-                hi.x = (gm.cmask & 4) ? base + row_stride : kNoCorner;
-                hi.y = __float_as_uint((gm.cmask & 4) ? (gm.lh * hw) * aw : 0.f);
-                hi.z = (gm.cmask & 8) ? base + row_stride + pix_stride : kNoCorner;
-                hi.w = __float_as_uint((gm.cmask & 8) ? (gm.lh * gm.lw) * aw : 0.f);
+                make_record<kRowwise>(gm, aw[r], (uint32_t)lt.start[l], (uint32_t)W, pix_stride,
+                                      (uint32_t)m * 8u, lo, hi);
                 uint4 *dst = reinterpret_cast<uint4 *>(rec + (size_t)s * 4);
                 dst[0] = lo;
                 dst[1] = hi;
@@ -101,32 +104,56 @@ msda_fwd_d32_kernel(const float *__restrict__ value, const int64_t *__restrict__
         __syncwarp();
 
         // ---- phase 2: gather + weighted reduction, one query at a time ----
-        const float4 *vb = reinterpret_cast<const float4 *>(value) + n * (long long)d.S * M * 8 + chunk;
-        for (int qi = 0; qi < cnt; ++qi) {
-            const uint2 *rq = rec + (size_t)qi * LP * 4 + corner;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kRowwise) {
+            const float *vb = value + n * (long long)d.S * M * 32 + lane;
+            for (int qi = 0; qi < cnt; ++qi) {
+                const uint4 *rq = reinterpret_cast<const uint4 *>(rec + (size_t)qi * LP * 4);
+                float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
-            for (int sp = 0; sp < LP; ++sp) {
-                const uint2 e = rq[sp * 4];
-                if (e.x != kNoCorner) {
-                    const float4 v = ldg_keep_f4(vb + e.x);
-                    const float w = __uint_as_float(e.y);
-                    acc.x = fmaf(w, v.x, acc.x);
-                    acc.y = fmaf(w, v.y, acc.y);
-                    acc.z = fmaf(w, v.z, acc.z);
-                    acc.w = fmaf(w, v.w, acc.w);
+                for (int sp = 0; sp < LP; ++sp) {
+                    const uint4 a = rq[2 * sp], b = rq[2 * sp + 1];   // broadcast reads
+                    if (a.x != kNoCorner) {                           // point in range (warp-uniform)
+                        const float v0 = ldg_keep_f1(at_off16(vb, a.x));
+                        const float v1 = ldg_keep_f1(at_off16(vb, a.z));
+                        const float v2 = ldg_keep_f1(at_off16(vb, b.x));
+                        const float v3 = ldg_keep_f1(at_off16(vb, b.z));
+                        acc0 = fmaf(__uint_as_float(a.y), v0, acc0);
+                        acc1 = fmaf(__uint_as_float(a.w), v1, acc1);
+                        acc0 = fmaf(__uint_as_float(b.y), v2, acc0);
+                        acc1 = fmaf(__uint_as_float(b.w), v3, acc1);
+                    }
                 }
+                float *o = out + ((n * d.Lq + q0 + qi) * M + m) * 32LL + lane;
+                stg_stream_f1(o, acc0 + acc1);
             }
-            // sum the 4 corner groups (lane bits 3 and 4); lane ends with channel 4*chunk+corner
-            const bool up16 = lane & 16, up8 = lane & 8;
-            float a0 = up16 ? acc.z : acc.x, a1 = up16 ? acc.w : acc.y;
-            const float s0 = up16 ? acc.x : acc.z, s1 = up16 ? acc.y : acc.w;
-            a0 += __shfl_xor_sync(kFullMask, s0, 16);
-            a1 += __shfl_xor_sync(kFullMask, s1, 16);
-            const float keep = up8 ? a1 : a0, send = up8 ? a0 : a1;
-            const float res = keep + __shfl_xor_sync(kFullMask, send, 8);
-            float *o = out + ((n * d.Lq + q0 + qi) * M + m) * 32LL + chunk * 4 + corner;
-            stg_stream_f1(o, res);
+        } else {
+            const float4 *vb = reinterpret_cast<const float4 *>(value) + n * (long long)d.S * M * 8 + chunk;
+            for (int qi = 0; qi < cnt; ++qi) {
+                const uint2 *rq = rec + (size_t)qi * LP * 4 + corner;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int sp = 0; sp < LP; ++sp) {
+                    const uint2 e = rq[sp * 4];
+                    if (e.x != kNoCorner) {
+                        const float4 v = ldg_keep_f4(at_off16(vb, e.x));
+                        const float w = __uint_as_float(e.y);
+                        acc.x = fmaf(w, v.x, acc.x);
+                        acc.y = fmaf(w, v.y, acc.y);
+                        acc.z = fmaf(w, v.z, acc.z);
+                        acc.w = fmaf(w, v.w, acc.w);
+                    }
+                }
+                // sum the 4 corner groups (lane bits 3 and 4); lane ends with channel 4*chunk+corner
+                const bool up16 = lane & 16, up8 = lane & 8;
+                float a0 = up16 ? acc.z : acc.x, a1 = up16 ? acc.w : acc.y;
+                const float s0 = up16 ? acc.x : acc.z, s1 = up16 ? acc.y : acc.w;
+                a0 += __shfl_xor_sync(kFullMask, s0, 16);
+                a1 += __shfl_xor_sync(kFullMask, s1, 16);
+                const float keep = up8 ? a1 : a0, send = up8 ? a0 : a1;
+                const float res = keep + __shfl_xor_sync(kFullMask, send, 8);
+                float *o = out + ((n * d.Lq + q0 + qi) * M + m) * 32LL + chunk * 4 + corner;
+                stg_stream_f1(o, res);
+            }
         }
         __syncwarp();   // records are overwritten by the next item
     }
@@ -135,12 +162,12 @@ msda_fwd_d32_kernel(const float *__restrict__ value, const int64_t *__restrict__
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
-template <int LP, int WARPS, int TILE_W>
+template <int LP, int WARPS, int TILE_W, int LANES_PER_ROW>
 static cudaError_t launch_fwd_cfg(const float *value, const int64_t *shapes, const int64_t *lstart,
                                   const float *loc, const float *attw, const Dims &d,
                                   float *out, cudaStream_t stream) {
     using Cfg = FwdCfg<LP, WARPS, TILE_W>;
-    auto kern = msda_fwd_d32_kernel<LP, WARPS, TILE_W>;
+    auto kern = msda_fwd_d32_kernel<LP, WARPS, TILE_W, LANES_PER_ROW>;
     static int ctas_per_sm = 0;   // immutable after first use
     if (ctas_per_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -171,11 +198,16 @@ static cudaError_t launch_fwd_lp(const float *value, const int64_t *shapes, cons
                                  const float *loc, const float *attw, const Dims &d, float *out,
                                  cudaStream_t stream) {
     switch (option_value(OPT_FWD_VARIANT)) {
-        case 1: return launch_fwd_cfg<LP, 8, 8>(value, shapes, lstart, loc, attw, d, out, stream);
-        case 3: return launch_fwd_cfg<LP, 32, 16>(value, shapes, lstart, loc, attw, d, out, stream);
-        case 4: return launch_fwd_cfg<LP, 16, 8>(value, shapes, lstart, loc, attw, d, out, stream);
-        case 2:
-        default: return launch_fwd_cfg<LP, 16, 16>(value, shapes, lstart, loc, attw, d, out, stream);
+        // 1-4: lane = corner*8 + chunk (LDG.128);  5-8: lane = channel (LDG.32, one line per instruction)
+        case 1: return launch_fwd_cfg<LP, 8, 8, 8>(value, shapes, lstart, loc, attw, d, out, stream);
+        case 2: return launch_fwd_cfg<LP, 16, 16, 8>(value, shapes, lstart, loc, attw, d, out, stream);
+        case 3: return launch_fwd_cfg<LP, 32, 16, 8>(value, shapes, lstart, loc, attw, d, out, stream);
+        case 4: return launch_fwd_cfg<LP, 16, 8, 8>(value, shapes, lstart, loc, attw, d, out, stream);
+        case 5: return launch_fwd_cfg<LP, 8, 8, 32>(value, shapes, lstart, loc, attw, d, out, stream);
+        case 7: return launch_fwd_cfg<LP, 32, 16, 32>(value, shapes, lstart, loc, attw, d, out, stream);
+        case 8: return launch_fwd_cfg<LP, 16, 8, 32>(value, shapes, lstart, loc, attw, d, out, stream);
+        case 6:
+        default: return launch_fwd_cfg<LP, 16, 16, 32>(value, shapes, lstart, loc, attw, d, out, stream);
     }
 }
 
