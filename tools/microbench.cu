@@ -1,0 +1,220 @@
+// microbench.cu -- per-SM cost (cycles per warp instruction) of the memory-pipe operations
+// the MSDA kernels are built from, measured on the B200 they run on.  Results are
+// summarised in profiles/ and drive the kernel design in DESIGN.md.
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/microbench tools/microbench.cu
+//   ./tools/microbench > gpurun_out/microbench.txt
+//
+// Every test runs 148*2 CTAs of 512 threads; each warp executes ITERS x UNROLL copies of the
+// operation; the figure of merit is SM cycles per warp-level instruction with all 32 warps of
+// an SM competing (i.e. reciprocal throughput of the shared LSU / L1TEX / XBAR path).
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define CHECK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
+
+constexpr int THREADS = 512;
+constexpr int ITERS = 256;
+constexpr int UNROLL = 8;
+constexpr int ROW_BYTES = 128;
+
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16; return x;
+}
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+enum Test { LDS32_BCAST, LDS32_DISTINCT, LDS64_4ADDR, LDS64_DISTINCT, LDS128_4ADDR, LDS128_BCAST,
+            LDS128_DISTINCT, LDS128_2SAMPLES, SHFL, STS32_DISTINCT, LDS_STS_RMW,
+            LDG128_4ROWS_L1, LDG32_1ROW_L1, LDG64_2ROWS_L1, LDG128_4ROWS_L2, LDG32_1ROW_L2,
+            RED128_4ROWS, RED32_1ROW, RED64_2ROWS, TMA_RED_ROW, STG128_4ROWS,
+            SHFL2, ATOMS_INT_SPREAD, ATOMS_F32_ROW, ATOMS_F32_ROW_SMALLWIN, ATOMS_INT_RET, NUM_TESTS };
+const char *kNames[] = {"lds32 broadcast (1 addr)", "lds32 32 distinct banks", "lds64 4 addrs (corner groups)",
+    "lds64 32 distinct", "lds128 4 addrs (corner groups)", "lds128 broadcast (1 addr)", "lds128 32 distinct",
+    "lds128 4 addrs x 16B contiguous 64B", "shfl.bfly", "sts32 32 distinct banks", "lds32+fadd+sts32 row RMW",
+    "ldg128 4 rows/instr, L1-resident", "ldg32 1 row/instr, L1-resident", "ldg64 2 rows/instr, L1-resident",
+    "ldg128 4 rows/instr, L2-resident random", "ldg32 1 row/instr, L2-resident random",
+    "red.v4.f32 4 rows/instr, random rows", "red.f32 1 row/instr, random rows", "red.v2.f32 2 rows/instr, random rows",
+    "TMA cp.reduce.async.bulk 128B row (sts row + 1 bulk op)", "stg128 4 rows/instr, random rows",
+    "shfl.bfly (dependent chain, 32 warps)", "smem red.add.s32, 32 random words of 8K", "smem atomicAdd(float) one row of 256 (32 lanes = 32 banks)",
+    "smem atomicAdd(float) one row of 16 (cross-warp conflicts)", "smem atomicAdd(int) with return, 32 random words of 8K"};
+
+template <int TEST>
+__global__ void __launch_bounds__(THREADS) bench(float *gbuf, uint32_t nrows_mask, float *sink, long long *cycles) {
+    __shared__ __align__(128) float sm[8192];   // 32 KB
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 8192; i += THREADS) sm[i] = (float)i;
+    __syncthreads();
+    float acc = 0.f;
+    // address generation is kept to ~2 integer instructions per operation so that it does not
+    // hide a 1-cycle-per-wavefront pipe: per-lane base + (iteration * stride) & mask
+    uint32_t rows[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) rows[u] = hash32(blockIdx.x * 977u + warp * 131u + u * 17u + 7u);
+    uint32_t lane_base = 0;   // float index into sm
+    if (TEST == LDS32_DISTINCT || TEST == STS32_DISTINCT || TEST == LDS_STS_RMW) lane_base = lane;
+    if (TEST == LDS64_4ADDR) lane_base = (lane >> 3) * 2;
+    if (TEST == LDS64_DISTINCT) lane_base = lane * 2;
+    if (TEST == LDS128_4ADDR) lane_base = (lane >> 3) * 8;        // {off,w} of a 32-byte record, stride 8 floats? (4 x 16B slots 32B apart)
+    if (TEST == LDS128_DISTINCT) lane_base = lane * 4;
+    if (TEST == LDS128_2SAMPLES) lane_base = (lane >> 3) * 4;     // 4 contiguous 16-byte slots
+    const uint32_t sbase = smem_u32(sm + lane_base);
+    const long long t0 = clock64();
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const uint32_t k = (uint32_t)(it * UNROLL + u);
+            if (TEST == LDS32_BCAST || TEST == LDS32_DISTINCT) {
+                float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(sbase + ((k * 128u) & 32767u))); acc += v;
+            } else if (TEST == LDS64_4ADDR || TEST == LDS64_DISTINCT) {
+                float2 v; asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(sbase + ((k * 256u) & 32767u))); acc += v.x + v.y;
+            } else if (TEST == LDS128_4ADDR || TEST == LDS128_BCAST || TEST == LDS128_DISTINCT || TEST == LDS128_2SAMPLES) {
+                float4 v; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sbase + ((k * 512u) & 32767u))); acc += v.x + v.w;
+            } else if (TEST == SHFL) {
+                acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+            } else if (TEST == SHFL2) {
+                acc = __shfl_xor_sync(0xffffffffu, acc + (float)lane, 8) * 1.0001f;
+            } else if (TEST == ATOMS_INT_SPREAD) {
+                const uint32_t w = (rows[u] + k * 2654435761u + lane * 40503u) & 8191u;
+                asm volatile("red.shared.add.s32 [%0], %1;" :: "r"(smem_u32(sm + w)), "r"(1) : "memory");
+            } else if (TEST == ATOMS_INT_RET) {
+                const uint32_t w = (rows[u] + k * 2654435761u + lane * 40503u) & 8191u;
+                int old; asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(sm + w)), "r"(1) : "memory");
+                acc += (float)old;
+            } else if (TEST == ATOMS_F32_ROW) {
+                const uint32_t row = (rows[u] + k * 2654435761u) >> 24;           // 0..255
+                atomicAdd(sm + row * 32 + lane, 1.0f);
+            } else if (TEST == ATOMS_F32_ROW_SMALLWIN) {
+                const uint32_t row = (rows[u] + k * 2654435761u) >> 28;           // 0..15
+                atomicAdd(sm + row * 32 + lane, 1.0f);
+            } else if (TEST == STS32_DISTINCT) {
+                asm volatile("st.shared.f32 [%0], %1;" :: "r"(sbase + ((k * 128u) & 32767u)), "f"(acc) : "memory");
+            } else if (TEST == LDS_STS_RMW) {
+                const uint32_t a = sbase + ((k * 128u) & 32767u);
+                float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+                asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v + 1.0f) : "memory");
+            } else {
+                // global-memory tests: a row index per (warp, u), advanced every iteration
+                const bool l1 = (TEST == LDG128_4ROWS_L1 || TEST == LDG32_1ROW_L1 || TEST == LDG64_2ROWS_L1);
+                const uint32_t step = rows[u] + (uint32_t)it * 40503u;
+                if (TEST == LDG128_4ROWS_L1 || TEST == LDG128_4ROWS_L2 || TEST == RED128_4ROWS || TEST == STG128_4ROWS) {
+                    uint32_t row = step + (uint32_t)(lane >> 3) * 7919u;
+                    row = l1 ? (row & 255u) + blockIdx.x * 256u : (row & nrows_mask);
+                    float *p = gbuf + (size_t)row * 32 + (lane & 7) * 4;
+                    if (TEST == RED128_4ROWS) {
+                        asm volatile("red.global.add.v4.f32 [%0], {%1,%1,%1,%1};" :: "l"(p), "f"(1.0f) : "memory");
+                    } else if (TEST == STG128_4ROWS) {
+                        asm volatile("st.global.v4.f32 [%0], {%1,%1,%1,%1};" :: "l"(p), "f"(1.0f) : "memory");
+                    } else {
+                        float4 v; asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p)); acc += v.x + v.w;
+                    }
+                } else if (TEST == LDG64_2ROWS_L1 || TEST == RED64_2ROWS) {
+                    uint32_t row = step + (uint32_t)(lane >> 4) * 7919u;
+                    row = l1 ? (row & 255u) + blockIdx.x * 256u : (row & nrows_mask);
+                    float *p = gbuf + (size_t)row * 32 + (lane & 15) * 2;
+                    if (TEST == RED64_2ROWS) {
+                        asm volatile("red.global.add.v2.f32 [%0], {%1,%1};" :: "l"(p), "f"(1.0f) : "memory");
+                    } else {
+                        float2 v; asm volatile("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p)); acc += v.x + v.y;
+                    }
+                } else if (TEST == LDG32_1ROW_L1 || TEST == LDG32_1ROW_L2 || TEST == RED32_1ROW) {
+                    uint32_t row = l1 ? (step & 255u) + blockIdx.x * 256u : (step & nrows_mask);
+                    float *p = gbuf + (size_t)row * 32 + lane;
+                    if (TEST == RED32_1ROW) {
+                        asm volatile("red.global.add.f32 [%0], %1;" :: "l"(p), "f"(1.0f) : "memory");
+                    } else {
+                        float v; asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p)); acc += v;
+                    }
+                } else if (TEST == TMA_RED_ROW) {
+                    // each warp owns UNROLL 128-byte staging rows in shared memory
+                    float *srow = sm + (warp * UNROLL + u) * 32;
+                    asm volatile("st.shared.f32 [%0], %1;" :: "r"(smem_u32(srow + lane)), "f"(1.0f) : "memory");
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        float *p = gbuf + (size_t)(step & nrows_mask) * 32;
+                        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                                     :: "l"(p), "r"(smem_u32(srow)), "n"(ROW_BYTES) : "memory");
+                    }
+                }
+            }
+        }
+        if (TEST == TMA_RED_ROW) {
+            if (lane == 0) {
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            __syncwarp();
+        }
+    }
+    const long long t1 = clock64();
+    if (acc == 123.456f) sink[0] = acc;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int TEST>
+void run(float *gbuf, uint32_t nrows_mask, float *sink, long long *cycles_d, int sms) {
+    const int ctas_per_sm = 2;
+    const int grid = sms * ctas_per_sm;
+    cudaEvent_t e0, e1;
+    CHECK(cudaEventCreate(&e0)); CHECK(cudaEventCreate(&e1));
+    bench<TEST><<<grid, THREADS>>>(gbuf, nrows_mask, sink, cycles_d);   // warm-up
+    CHECK(cudaDeviceSynchronize());
+    CHECK(cudaEventRecord(e0));
+    bench<TEST><<<grid, THREADS>>>(gbuf, nrows_mask, sink, cycles_d);
+    CHECK(cudaEventRecord(e1));
+    CHECK(cudaDeviceSynchronize());
+    float ms = 0; CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    long long *h = (long long *)malloc(sizeof(long long) * grid);
+    CHECK(cudaMemcpy(h, cycles_d, sizeof(long long) * grid, cudaMemcpyDeviceToHost));
+    double mean = 0; for (int i = 0; i < grid; ++i) mean += (double)h[i]; mean /= grid;
+    free(h);
+    // warp instructions per SM = ctas_per_sm * warps * ITERS * UNROLL
+    const double instr_per_sm = (double)ctas_per_sm * (THREADS / 32) * ITERS * UNROLL;
+    printf("%-58s  %8.3f ms  %9.0f clk/CTA  %7.2f SM-cycles per warp-instr  (%6.1f GB/s row payload @128B/row-instr)\n",
+           kNames[TEST], ms, mean, mean / instr_per_sm,
+           instr_per_sm * sms * 128.0 / (ms * 1e-3) / 1e9);
+}
+
+int main() {
+    int dev = 0, sms = 0, clk = 0;
+    CHECK(cudaGetDevice(&dev));
+    CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CHECK(cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, dev));
+    printf("SMs %d, max clock %d kHz; %d threads/CTA, 2 CTAs/SM, %d x %d ops per warp\n", sms, clk, THREADS, ITERS, UNROLL);
+    const uint32_t nrows = (64u << 20) / ROW_BYTES;   // 64 MB of 128-byte rows (L2-resident, like grad_value at configs[1])
+    float *gbuf, *sink; long long *cycles;
+    CHECK(cudaMalloc(&gbuf, (size_t)nrows * ROW_BYTES));
+    CHECK(cudaMemset(gbuf, 0, (size_t)nrows * ROW_BYTES));
+    CHECK(cudaMalloc(&sink, 16));
+    CHECK(cudaMalloc(&cycles, sizeof(long long) * sms * 4));
+    run<LDS32_BCAST>(gbuf, nrows - 1, sink, cycles, sms);
+    run<LDS32_DISTINCT>(gbuf, nrows - 1, sink, cycles, sms);
+    run<LDS64_4ADDR>(gbuf, nrows - 1, sink, cycles, sms);
+    run<LDS64_DISTINCT>(gbuf, nrows - 1, sink, cycles, sms);
+    run<LDS128_4ADDR>(gbuf, nrows - 1, sink, cycles, sms);
+    run<LDS128_BCAST>(gbuf, nrows - 1, sink, cycles, sms);
+    run<LDS128_DISTINCT>(gbuf, nrows - 1, sink, cycles, sms);
+    run<LDS128_2SAMPLES>(gbuf, nrows - 1, sink, cycles, sms);
+    run<SHFL>(gbuf, nrows - 1, sink, cycles, sms);
+    run<STS32_DISTINCT>(gbuf, nrows - 1, sink, cycles, sms);
+    run<LDS_STS_RMW>(gbuf, nrows - 1, sink, cycles, sms);
+    run<LDG128_4ROWS_L1>(gbuf, nrows - 1, sink, cycles, sms);
+    run<LDG32_1ROW_L1>(gbuf, nrows - 1, sink, cycles, sms);
+    run<LDG64_2ROWS_L1>(gbuf, nrows - 1, sink, cycles, sms);
+    run<LDG128_4ROWS_L2>(gbuf, nrows - 1, sink, cycles, sms);
+    run<LDG32_1ROW_L2>(gbuf, nrows - 1, sink, cycles, sms);
+    run<RED128_4ROWS>(gbuf, nrows - 1, sink, cycles, sms);
+    run<RED32_1ROW>(gbuf, nrows - 1, sink, cycles, sms);
+    run<RED64_2ROWS>(gbuf, nrows - 1, sink, cycles, sms);
+    run<TMA_RED_ROW>(gbuf, nrows - 1, sink, cycles, sms);
+    run<STG128_4ROWS>(gbuf, nrows - 1, sink, cycles, sms);
+    run<SHFL2>(gbuf, nrows - 1, sink, cycles, sms);
+    run<ATOMS_INT_SPREAD>(gbuf, nrows - 1, sink, cycles, sms);
+    run<ATOMS_INT_RET>(gbuf, nrows - 1, sink, cycles, sms);
+    run<ATOMS_F32_ROW>(gbuf, nrows - 1, sink, cycles, sms);
+    run<ATOMS_F32_ROW_SMALLWIN>(gbuf, nrows - 1, sink, cycles, sms);
+    printf("done\n");
+    return 0;
+}

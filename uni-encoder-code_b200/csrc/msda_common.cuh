@@ -200,6 +200,17 @@ __device__ __forceinline__ T *at_off16(T *base, uint32_t off16) {
     return reinterpret_cast<T *>(r);
 }
 
+// one 128-bit shared load (the compiler otherwise splits it when half of it is only
+// needed under a predicate); "memory": it reads records written earlier by other lanes
+__device__ __forceinline__ uint4 lds_u4(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "r"((uint32_t)__cvta_generic_to_shared(p))
+                 : "memory");
+    return r;
+}
+
 // ---------------------------------------------------------------------------
 // cache-hinted global accesses
 // ---------------------------------------------------------------------------
@@ -208,6 +219,11 @@ __device__ __forceinline__ float4 ldg_keep_f4(const float4 *p) {
     float4 r;
     asm("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float2 ldg_keep_f2(const float2 *p) {
+    float2 r;
+    asm("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
     return r;
 }
 __device__ __forceinline__ float ldg_keep_f1(const float *p) {

@@ -46,6 +46,7 @@ msda_fwd_d32_kernel(const float *__restrict__ value, const int64_t *__restrict__
                     float *__restrict__ out) {
     using Cfg = FwdCfg<LP, WARPS, TILE_W>;
     constexpr bool kRowwise = LANES_PER_ROW == 32;
+    constexpr bool kHalfwise = LANES_PER_ROW == 16;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ LevelTable lt;
 
@@ -94,17 +95,48 @@ msda_fwd_d32_kernel(const float *__restrict__ value, const int64_t *__restrict__
                 const int H = lt.H[l], W = lt.W[l];
                 const Geom<float> gm = decompose(xy[r].x, xy[r].y, H, W);
                 uint4 lo, hi;   // {off0, w0, off1, w1}, {off2, w2, off3, w3}
-                make_record<kRowwise>(gm, aw[r], (uint32_t)lt.start[l], (uint32_t)W, pix_stride,
-                                      (uint32_t)m * 8u, lo, hi);
+                make_record<kRowwise || kHalfwise>(gm, aw[r], (uint32_t)lt.start[l], (uint32_t)W,
+                                                   pix_stride, (uint32_t)m * 8u, lo, hi);
                 uint4 *dst = reinterpret_cast<uint4 *>(rec + (size_t)s * 4);
-                dst[0] = lo;
-                dst[1] = hi;
+                if (kHalfwise) {   // slot h holds corners (h, h+2): what half-warp h reads
+                    dst[0] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+                    dst[1] = make_uint4(lo.z, lo.w, hi.z, hi.w);
+                } else {
+                    dst[0] = lo;
+                    dst[1] = hi;
+                }
             }
         }
         __syncwarp();
 
         // ---- phase 2: gather + weighted reduction, one query at a time ----
-        if (kRowwise) {
+        if (kHalfwise) {
+            // lane = half*16 + j: half-warp `half` reads corner rows (half, half+2), lane j channels 2j, 2j+1
+            const int half = lane >> 4, j = lane & 15;
+            const float2 *vb = reinterpret_cast<const float2 *>(value + n * (long long)d.S * M * 32) + j;
+            for (int qi = 0; qi < cnt; ++qi) {
+                const uint4 *rq = reinterpret_cast<const uint4 *>(rec + (size_t)qi * LP * 4) + half;
+                float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int sp = 0; sp < LP; ++sp) {
+                    const uint4 e = lds_u4(rq + 2 * sp);
+                    if (e.x != kNoCorner) {                           // point in range (warp-uniform)
+                        const float2 va = ldg_keep_f2(at_off16(vb, e.x));
+                        const float2 vc = ldg_keep_f2(at_off16(vb, e.z));
+                        const float wa = __uint_as_float(e.y), wc = __uint_as_float(e.w);
+                        acc.x = fmaf(wa, va.x, acc.x);
+                        acc.y = fmaf(wa, va.y, acc.y);
+                        acc.x = fmaf(wc, vc.x, acc.x);
+                        acc.y = fmaf(wc, vc.y, acc.y);
+                    }
+                }
+                // sum the two halves; lane ends with channel 2j + half
+                const float keep = half ? acc.y : acc.x, send = half ? acc.x : acc.y;
+                const float res = keep + __shfl_xor_sync(kFullMask, send, 16);
+                float *o = out + ((n * d.Lq + q0 + qi) * M + m) * 32LL + 2 * j + half;
+                stg_stream_f1(o, res);
+            }
+        } else if (kRowwise) {
             const float *vb = value + n * (long long)d.S * M * 32 + lane;
             for (int qi = 0; qi < cnt; ++qi) {
                 const uint4 *rq = reinterpret_cast<const uint4 *>(rec + (size_t)qi * LP * 4);
@@ -204,6 +236,11 @@ static cudaError_t launch_fwd_lp(const float *value, const int64_t *shapes, cons
         case 3: return launch_fwd_cfg<LP, 32, 16, 8>(value, shapes, lstart, loc, attw, d, out, stream);
         case 4: return launch_fwd_cfg<LP, 16, 8, 8>(value, shapes, lstart, loc, attw, d, out, stream);
         case 5: return launch_fwd_cfg<LP, 8, 8, 32>(value, shapes, lstart, loc, attw, d, out, stream);
+        // 9-12: lane = half*16 + pair (LDG.64, two rows per instruction)
+        case 9: return launch_fwd_cfg<LP, 8, 8, 16>(value, shapes, lstart, loc, attw, d, out, stream);
+        case 10: return launch_fwd_cfg<LP, 16, 16, 16>(value, shapes, lstart, loc, attw, d, out, stream);
+        case 11: return launch_fwd_cfg<LP, 32, 16, 16>(value, shapes, lstart, loc, attw, d, out, stream);
+        case 12: return launch_fwd_cfg<LP, 16, 8, 16>(value, shapes, lstart, loc, attw, d, out, stream);
         case 7: return launch_fwd_cfg<LP, 32, 16, 32>(value, shapes, lstart, loc, attw, d, out, stream);
         case 8: return launch_fwd_cfg<LP, 16, 8, 32>(value, shapes, lstart, loc, attw, d, out, stream);
         case 6:
