@@ -11,8 +11,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
-GOLDEN_NAMES = sorted(os.path.splitext(os.path.basename(p))[0]
-                      for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+GOLDEN_NAMES = sorted(n for n in (os.path.splitext(os.path.basename(p))[0]
+                                  for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+                      if not n.startswith("encoder"))       # op-level fixtures only
 
 # tolerances of BASELINE.json's north_star
 FWD_ABS_TOL = 1e-5      # fp32 forward, max abs error vs the fp64 oracle, value ~ N(0,1)

@@ -82,7 +82,49 @@ def cases(syn):
     return out
 
 
+def encoder_golden():
+    """A small reference MSDeformAttnTransformerEncoderOnly (msdeformattn.py:26-99) in fp64 on CPU:
+    weights, inputs, memory and the gradient of <memory, cotangent> w.r.t. the finest-level input.
+    Pins the host-side mirror in uni-encoder-code_b200/modules.py (and, on the GPU, mirror + op)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ref_import
+    ns = ref_import.load()
+    torch.manual_seed(1234)
+    levels = [(2, 3), (4, 6), (8, 12)]
+    enc = ns.MSDeformAttnTransformerEncoderOnly(d_model=64, nhead=2, num_encoder_layers=2,
+                                                dim_feedforward=128, dropout=0.0,
+                                                num_feature_levels=3, enc_n_points=4).double().eval()
+    # default init puts every offset on an integer pixel step (ms_deform_attn.py:69-77), where
+    # the gradient w.r.t. locations is discontinuous: randomise the offset projection
+    gen = torch.Generator().manual_seed(99)
+    with torch.no_grad():
+        for layer in enc.encoder.layers:
+            layer.self_attn.sampling_offsets.weight.copy_(
+                torch.randn(layer.self_attn.sampling_offsets.weight.shape, generator=gen, dtype=torch.float64) * 0.05)
+            layer.self_attn.sampling_offsets.bias.add_(
+                torch.rand(layer.self_attn.sampling_offsets.bias.shape, generator=gen, dtype=torch.float64) * 0.6 + 0.2)
+            layer.self_attn.attention_weights.weight.copy_(
+                torch.randn(layer.self_attn.attention_weights.weight.shape, generator=gen, dtype=torch.float64) * 0.1)
+    srcs = [torch.randn(2, 64, h, w, generator=gen, dtype=torch.float64) for h, w in levels]
+    srcs[2].requires_grad_(True)
+    pe = ns.PositionEmbeddingSine(32, normalize=True)
+    pos = [pe(s).double() for s in srcs]
+    memory, shapes, lsi, _ = enc(srcs, pos)
+    cot = torch.randn(memory.shape, generator=gen, dtype=torch.float64)
+    (memory * cot).sum().backward()
+    out = {"state::" + k: v.detach().numpy() for k, v in enc.state_dict().items()}
+    for i, (s_, p_) in enumerate(zip(srcs, pos)):
+        out[f"src{i}"] = s_.detach().numpy()
+        out[f"pos{i}"] = p_.detach().numpy()
+    out.update(memory=memory.detach().numpy(), cotangent=cot.numpy(), grad_src2=srcs[2].grad.numpy(),
+               spatial_shapes=shapes.numpy(), level_start_index=lsi.numpy())
+    path = os.path.join(HERE, "encoder_small.npz")
+    np.savez_compressed(path, **out)
+    print(f"encoder_small: memory {tuple(memory.shape)} -> {os.path.getsize(path) / 1024:.1f} KiB")
+
+
 def main():
+    encoder_golden()
     core = load_reference()
     syn = load_package().synthetic if os.path.exists(
         os.path.join(ROOT, "uni-encoder-code_b200", "lib", "libmsda_b200.so")) else None

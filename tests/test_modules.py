@@ -1,0 +1,130 @@
+"""Host-side mirrors of the callers (uni-encoder-code_b200/modules.py) against the reference's own
+classes: parameter names / init / forward on CPU (core op injected from the oracle: test
+infrastructure), and mirror + CUDA op on the GPU against the committed encoder golden."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+import ref_import
+
+LEVELS = [(2, 3), (4, 6), (8, 12)]
+
+
+def oracle_core(oracle):
+    def core(value, shapes, lsi, loc, w, im2col_step):
+        return oracle.core_grid_sample(value, shapes, loc, w)
+    return core
+
+
+def build_small(pkg, core=None, dtype=torch.float64, device="cpu"):
+    m = pkg.modules.MSDeformAttnTransformerEncoderOnly(
+        d_model=64, nhead=2, num_encoder_layers=2, dim_feedforward=128, dropout=0.0,
+        num_feature_levels=3, enc_n_points=4, core=core)
+    g = load_golden("encoder_small")
+    state = {k[len("state::"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("state::")}
+    m = m.double()                      # load at full precision, then cast
+    missing, unexpected = m.load_state_dict(state, strict=True)
+    assert not missing and not unexpected
+    return m.to(device=device, dtype=dtype).eval(), g
+
+
+def test_mirror_loads_reference_checkpoint_and_matches_reference_forward_cpu(pkg, oracle):
+    m, g = build_small(pkg, core=oracle_core(oracle))
+    srcs = [torch.from_numpy(g[f"src{i}"]) for i in range(3)]
+    srcs[2].requires_grad_(True)
+    pos = [torch.from_numpy(g[f"pos{i}"]) for i in range(3)]
+    memory, shapes, lsi, vr = m(srcs, pos)
+    assert shapes.tolist() == g["spatial_shapes"].tolist() and lsi.tolist() == g["level_start_index"].tolist()
+    assert torch.equal(vr, torch.ones_like(vr))
+    assert (memory.detach().numpy() - g["memory"]).__abs__().max() <= 1e-11
+    (memory * torch.from_numpy(g["cotangent"])).sum().backward()
+    assert np.abs(srcs[2].grad.numpy() - g["grad_src2"]).max() <= 1e-10
+
+
+def test_reference_points_match_reference_formula(pkg):
+    enc = pkg.modules.MSDeformAttnTransformerEncoder
+    shapes = torch.tensor(LEVELS)
+    vr = torch.rand(2, 3, 2) * 0.5 + 0.5
+    got = enc.get_reference_points(shapes, vr, "cpu")
+    # restated from msdeformattn.py:152-166
+    want = []
+    for lvl, (H, W) in enumerate(LEVELS):
+        ys, xs = torch.meshgrid(torch.linspace(0.5, H - 0.5, H), torch.linspace(0.5, W - 0.5, W), indexing="ij")
+        y = ys.reshape(-1)[None] / (vr[:, None, lvl, 1] * H)
+        x = xs.reshape(-1)[None] / (vr[:, None, lvl, 0] * W)
+        want.append(torch.stack((x, y), -1))
+    want = torch.cat(want, 1)[:, :, None] * vr[:, None]
+    assert torch.allclose(got, want, atol=1e-6)
+    ones = pkg.modules.reference_points_for(LEVELS, "cpu").expand(2, -1, -1, -1)
+    assert torch.allclose(enc.get_reference_points(shapes, torch.ones(2, 3, 2), "cpu"), ones, atol=1e-7)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference checkout not present")
+def test_mirror_init_and_forward_equal_live_reference(pkg, oracle):
+    """Same seed -> same parameters as the reference classes; same forward on CPU."""
+    ns = ref_import.load()
+    kw = dict(d_model=64, nhead=2, num_encoder_layers=2, dim_feedforward=128, dropout=0.0,
+              num_feature_levels=3, enc_n_points=4)
+    torch.manual_seed(7)
+    ref = ns.MSDeformAttnTransformerEncoderOnly(**kw).eval()
+    torch.manual_seed(7)
+    mine = pkg.modules.MSDeformAttnTransformerEncoderOnly(core=oracle_core(oracle), **kw).eval()
+    rs, ms = ref.state_dict(), mine.state_dict()
+    assert list(rs) == list(ms)
+    for k in rs:
+        assert torch.equal(rs[k], ms[k]), k
+    srcs = [torch.randn(2, 64, h, w) for h, w in LEVELS]
+    pe = ns.PositionEmbeddingSine(32, normalize=True)
+    pos = [pe(s) for s in srcs]
+    with torch.no_grad():
+        a = ref(srcs, pos)[0]
+        b = mine(srcs, pos)[0]
+    assert (a - b).abs().max().item() <= 2e-5
+
+    # module level: the reference MSDeformAttn CPU branch (ms_deform_attn.py:122-124) vs the mirror
+    torch.manual_seed(3)
+    r_attn = ns.MSDeformAttn(64, 3, 2, 4).double()
+    m_attn = pkg.modules.MSDeformAttn(64, 3, 2, 4, core=oracle_core(oracle)).double()
+    m_attn.load_state_dict(r_attn.state_dict())
+    q = torch.randn(2, 126, 64, dtype=torch.float64)
+    x = torch.randn(2, 126, 64, dtype=torch.float64)
+    refp = torch.rand(2, 126, 3, 2, dtype=torch.float64)
+    shapes = torch.tensor(LEVELS)
+    lsi = torch.tensor([0, 6, 30])
+    mask = torch.rand(2, 126) > 0.8
+    with torch.no_grad():
+        assert (r_attn(q, refp, x, shapes, lsi, mask) - m_attn(q, refp, x, shapes, lsi, mask)).abs().max() <= 1e-12
+        box = torch.rand(2, 126, 3, 4, dtype=torch.float64)      # 4-d reference boxes (ms_deform_attn.py:113-115)
+        assert (r_attn(q, box, x, shapes, lsi) - m_attn(q, box, x, shapes, lsi)).abs().max() <= 1e-12
+
+
+def test_module_refuses_cpu_without_injected_core(pkg):
+    m = pkg.modules.MSDeformAttn(64, 3, 2, 4)
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        m(torch.randn(1, 126, 64), torch.rand(1, 126, 3, 2), torch.randn(1, 126, 64),
+          torch.tensor(LEVELS), torch.tensor([0, 6, 30]))
+
+
+@pytest.mark.gpu
+def test_mirror_plus_cuda_op_matches_reference_encoder_golden(pkg):
+    """Reference encoder (fp64, CPU, in the build container) vs mirror + sm_100a kernels in fp32."""
+    m, g = build_small(pkg, dtype=torch.float32, device="cuda:0")
+    srcs = [torch.from_numpy(g[f"src{i}"]).float().cuda() for i in range(3)]
+    srcs[2].requires_grad_(True)
+    pos = [torch.from_numpy(g[f"pos{i}"]).float().cuda() for i in range(3)]
+    memory = m(srcs, pos)[0]
+    assert np.abs(memory.detach().double().cpu().numpy() - g["memory"]).max() <= 2e-4
+    (memory * torch.from_numpy(g["cotangent"]).float().cuda()).sum().backward()
+    ref = g["grad_src2"]
+    assert np.abs(srcs[2].grad.double().cpu().numpy() - ref).max() <= 2e-4 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.gpu
+def test_mirror_fp64_cuda_op_matches_reference_encoder_golden(pkg):
+    m, g = build_small(pkg, dtype=torch.float64, device="cuda:0")
+    srcs = [torch.from_numpy(g[f"src{i}"]).cuda() for i in range(3)]
+    pos = [torch.from_numpy(g[f"pos{i}"]).cuda() for i in range(3)]
+    with torch.no_grad():
+        memory = m(srcs, pos)[0]
+    assert np.abs(memory.cpu().numpy() - g["memory"]).max() <= 1e-9

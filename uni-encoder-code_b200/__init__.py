@@ -19,10 +19,11 @@ from ._lib import get_option, launch_count, set_option
 from .functions import MSDeformAttnFunction
 from .ops import debug_indices, ms_deform_attn_backward, ms_deform_attn_forward
 from . import synthetic
+from . import modules, sharding
 
 __all__ = [
     "ms_deform_attn_forward", "ms_deform_attn_backward", "MSDeformAttnFunction", "debug_indices",
-    "install_dropin", "set_option", "get_option", "launch_count", "synthetic",
+    "install_dropin", "set_option", "get_option", "launch_count", "synthetic", "modules", "sharding",
 ]
 
 DROPIN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dropin")

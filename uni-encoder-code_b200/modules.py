@@ -1,0 +1,223 @@
+"""Host-side mirror of the callers on either side of the MSDA op, for boxes that do not have
+the reference checkout (the GPU box, bench tools) and for the "next" rows of SURVEY.md section 8f.
+
+Same class names, constructor arguments, parameter names (so reference checkpoints load with
+``load_state_dict``) and forward signatures as the reference:
+
+* ``MSDeformAttn``                         ops/modules/ms_deform_attn.py:35-126
+* ``MSDeformAttnTransformerEncoderLayer``  model/modeling/pixel_decoder/msdeformattn.py:102-142
+* ``MSDeformAttnTransformerEncoder``       msdeformattn.py:145-176
+* ``MSDeformAttnTransformerEncoderOnly``   msdeformattn.py:26-99
+
+The reference's own classes also run unchanged on the drop-in shim; these mirrors exist so the
+encoder-level configs (BASELINE configs[2..4]) can be measured without it, and differ only where
+SURVEY 8f ranks a saving: reference points are built without iterating a CUDA tensor on the host
+(msdeformattn.py:154 syncs), and the encoder does not allocate / apply the all-False padding masks
+(msdeformattn.py:68-69, ms_deform_attn.py:102-103 rewrite ``value`` with an unchanged copy).
+
+The core op is always the CUDA one (``MSDeformAttnFunction``); there is no CPU branch.  Tests of the
+host logic on CPU pass ``core=`` explicitly.
+"""
+from __future__ import annotations
+
+import copy
+import math
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .functions import MSDeformAttnFunction
+
+CoreFn = Callable[..., torch.Tensor]
+
+
+def _cuda_core(value, spatial_shapes, level_start_index, sampling_locations, attention_weights,
+               im2col_step):
+    return MSDeformAttnFunction.apply(value, spatial_shapes, level_start_index, sampling_locations,
+                                      attention_weights, im2col_step)
+
+
+class MSDeformAttn(nn.Module):
+    """Multi-scale deformable attention module (ms_deform_attn.py:35-126)."""
+
+    def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4, core: Optional[CoreFn] = None):
+        super().__init__()
+        if d_model % n_heads:
+            raise ValueError(f"d_model must be divisible by n_heads, but got {d_model} and {n_heads}")
+        self.im2col_step = 128                    # ms_deform_attn.py:55
+        self.d_model, self.n_levels, self.n_heads, self.n_points = d_model, n_levels, n_heads, n_points
+        self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 2)
+        self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
+        self.value_proj = nn.Linear(d_model, d_model)
+        self.output_proj = nn.Linear(d_model, d_model)
+        self._core = core or _cuda_core
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        # ms_deform_attn.py:69-83: zero offset weights, offsets biased along 8 compass directions
+        # scaled by the point index; uniform attention; xavier value / output projections
+        with torch.no_grad():
+            self.sampling_offsets.weight.zero_()
+            ang = torch.arange(self.n_heads, dtype=torch.float32) * (2.0 * math.pi / self.n_heads)
+            dirs = torch.stack((ang.cos(), ang.sin()), -1)
+            dirs = dirs / dirs.abs().amax(-1, keepdim=True)
+            scale = torch.arange(1, self.n_points + 1, dtype=torch.float32).view(1, 1, -1, 1)
+            bias = dirs.view(self.n_heads, 1, 1, 2) * scale            # broadcast over levels
+            bias = bias.expand(self.n_heads, self.n_levels, self.n_points, 2)
+            self.sampling_offsets.bias.copy_(bias.reshape(-1))
+            self.attention_weights.weight.zero_()
+            self.attention_weights.bias.zero_()
+            nn.init.xavier_uniform_(self.value_proj.weight)
+            self.value_proj.bias.zero_()
+            nn.init.xavier_uniform_(self.output_proj.weight)
+            self.output_proj.bias.zero_()
+
+    def sampling_inputs(self, query, reference_points, input_spatial_shapes):
+        """(sampling_locations [N,Lq,M,L,P,2], attention_weights [N,Lq,M,L,P]) from the query
+        (ms_deform_attn.py:105-118)."""
+        N, Lq, _ = query.shape
+        M, L, P = self.n_heads, self.n_levels, self.n_points
+        offsets = self.sampling_offsets(query).view(N, Lq, M, L, P, 2)
+        weights = F.softmax(self.attention_weights(query).view(N, Lq, M, L * P), -1).view(N, Lq, M, L, P)
+        if reference_points.shape[-1] == 2:
+            wh = input_spatial_shapes.flip(-1).to(offsets.dtype)       # (W_l, H_l)
+            loc = reference_points[:, :, None, :, None, :] + offsets / wh[None, None, None, :, None, :]
+        elif reference_points.shape[-1] == 4:
+            loc = (reference_points[:, :, None, :, None, :2]
+                   + offsets / P * reference_points[:, :, None, :, None, 2:] * 0.5)
+        else:
+            raise ValueError(
+                f"Last dim of reference_points must be 2 or 4, but get {reference_points.shape[-1]} instead.")
+        return loc, weights
+
+    def project_value(self, input_flatten, input_padding_mask=None):
+        N, S, _ = input_flatten.shape
+        value = self.value_proj(input_flatten)
+        if input_padding_mask is not None:
+            value = value.masked_fill(input_padding_mask[..., None], 0.0)
+        return value.view(N, S, self.n_heads, self.d_model // self.n_heads)
+
+    def forward(self, query, reference_points, input_flatten, input_spatial_shapes,
+                input_level_start_index, input_padding_mask=None):
+        value = self.project_value(input_flatten, input_padding_mask)
+        loc, weights = self.sampling_inputs(query, reference_points, input_spatial_shapes)
+        out = self._core(value, input_spatial_shapes, input_level_start_index, loc.contiguous(),
+                         weights.contiguous(), self.im2col_step)
+        return self.output_proj(out)
+
+
+def _activation(name):
+    return {"relu": F.relu, "gelu": F.gelu, "glu": F.glu}[name]
+
+
+class MSDeformAttnTransformerEncoderLayer(nn.Module):
+    """msdeformattn.py:102-142 (post-norm: attention, add & norm, FFN, add & norm)."""
+
+    def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8,
+                 n_points=4, core: Optional[CoreFn] = None):
+        super().__init__()
+        self.self_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points, core=core)
+        self.dropout1 = nn.Dropout(dropout)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.linear1 = nn.Linear(d_model, d_ffn)
+        self.activation = _activation(activation)
+        self.dropout2 = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(d_ffn, d_model)
+        self.dropout3 = nn.Dropout(dropout)
+        self.norm2 = nn.LayerNorm(d_model)
+
+    def forward_ffn(self, src):
+        return self.norm2(src + self.dropout3(self.linear2(self.dropout2(self.activation(self.linear1(src))))))
+
+    def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
+        q = src if pos is None else src + pos
+        attn = self.self_attn(q, reference_points, src, spatial_shapes, level_start_index, padding_mask)
+        return self.forward_ffn(self.norm1(src + self.dropout1(attn)))
+
+
+def reference_points_for(levels: Sequence[Tuple[int, int]], device, dtype=torch.float32):
+    """[1, S, L, 2] pixel-centre reference points of every query, replicated over levels, for
+    valid_ratios == 1 (msdeformattn.py:152-166 with the all-False masks of :68-69).  `levels` is a
+    host-side list, so no CUDA tensor is iterated."""
+    pts = []
+    for H, W in levels:
+        ys = torch.linspace(0.5, H - 0.5, H, dtype=dtype, device=device) / H
+        xs = torch.linspace(0.5, W - 0.5, W, dtype=dtype, device=device) / W
+        yy, xx = torch.meshgrid(ys, xs, indexing="ij")
+        pts.append(torch.stack((xx.reshape(-1), yy.reshape(-1)), -1))
+    ref = torch.cat(pts, 0)
+    return ref[None, :, None, :].expand(1, ref.shape[0], len(levels), 2)
+
+
+class MSDeformAttnTransformerEncoder(nn.Module):
+    """msdeformattn.py:145-176."""
+
+    def __init__(self, encoder_layer, num_layers):
+        super().__init__()
+        self.layers = nn.ModuleList([copy.deepcopy(encoder_layer) for _ in range(num_layers)])
+        self.num_layers = num_layers
+
+    @staticmethod
+    def get_reference_points(spatial_shapes, valid_ratios, device):
+        """Reference signature (msdeformattn.py:152-166); general valid_ratios."""
+        levels = [(int(h), int(w)) for h, w in
+                  (spatial_shapes.tolist() if torch.is_tensor(spatial_shapes) else spatial_shapes)]
+        base = reference_points_for(levels, device)[0, :, 0]            # [S, 2] at ratio 1
+        sizes = torch.tensor([h * w for h, w in levels])
+        lvl_of = torch.repeat_interleave(torch.arange(len(levels)), sizes).to(device)
+        own = valid_ratios[:, lvl_of]                                    # [N, S, 2] ratio of own level
+        return (base[None] / own)[:, :, None] * valid_ratios[:, None]    # [N, S, L, 2]
+
+    def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None,
+                levels: Optional[List[Tuple[int, int]]] = None):
+        if levels is not None and valid_ratios is None:
+            ref = reference_points_for(levels, src.device).expand(src.shape[0], -1, -1, -1)
+        else:
+            ref = self.get_reference_points(spatial_shapes, valid_ratios, src.device)
+        out = src
+        for layer in self.layers:
+            out = layer(out, pos, ref, spatial_shapes, level_start_index, padding_mask)
+        return out
+
+
+class MSDeformAttnTransformerEncoderOnly(nn.Module):
+    """msdeformattn.py:26-99: flattens the per-level maps, adds the level embedding to the position
+    embedding and runs the encoder.  Returns (memory, spatial_shapes, level_start_index, valid_ratios)."""
+
+    def __init__(self, d_model=256, nhead=8, num_encoder_layers=6, dim_feedforward=1024, dropout=0.1,
+                 activation="relu", num_feature_levels=4, enc_n_points=4, core: Optional[CoreFn] = None):
+        super().__init__()
+        self.d_model, self.nhead = d_model, nhead
+        layer = MSDeformAttnTransformerEncoderLayer(d_model, dim_feedforward, dropout, activation,
+                                                    num_feature_levels, nhead, enc_n_points, core=core)
+        self.encoder = MSDeformAttnTransformerEncoder(layer, num_encoder_layers)
+        self.level_embed = nn.Parameter(torch.empty(num_feature_levels, d_model))
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        for m in self.modules():
+            if isinstance(m, MSDeformAttn):
+                m._reset_parameters()
+        nn.init.normal_(self.level_embed)
+
+    def flatten_inputs(self, srcs, pos_embeds):
+        levels = [(int(s.shape[2]), int(s.shape[3])) for s in srcs]
+        src = torch.cat([s.flatten(2).transpose(1, 2) for s in srcs], 1)
+        pos = torch.cat([p.flatten(2).transpose(1, 2) + self.level_embed[i].view(1, 1, -1)
+                         for i, p in enumerate(pos_embeds)], 1)
+        shapes = torch.as_tensor(levels, dtype=torch.long, device=src.device)
+        lsi = torch.cat((shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]))
+        return src, pos, shapes, lsi, levels
+
+    def forward(self, srcs, pos_embeds):
+        src, pos, shapes, lsi, levels = self.flatten_inputs(srcs, pos_embeds)
+        # masks are all-False in the reference (msdeformattn.py:68-69): valid ratios are exactly 1
+        # and the padding mask changes nothing, so neither is materialised
+        memory = self.encoder(src, shapes, lsi, None, pos, None, levels=levels)
+        valid_ratios = src.new_ones(src.shape[0], len(levels), 2)
+        return memory, shapes, lsi, valid_ratios

@@ -23,6 +23,34 @@ import torch
 
 from . import _lib
 
+# Optional per-call CUDA-event timing of the two C-ABI launches (bench tools only; off by
+# default, no effect on results).  When enabled, every call appends (kind, start, end).
+_TIMING = None
+
+
+def enable_timing(on: bool = True):
+    """Start (or stop) collecting CUDA events around each kernel launch; returns the list."""
+    global _TIMING
+    _TIMING = [] if on else None
+    return _TIMING
+
+
+class _timed:
+    def __init__(self, kind):
+        self.kind = kind
+
+    def __enter__(self):
+        if _TIMING is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if _TIMING is not None:
+            self.e1.record()
+            _TIMING.append((self.kind, self.e0, self.e1))
+
+
 _FWD = {torch.float32: _lib.lib.msda_b200_forward_f32, torch.float64: _lib.lib.msda_b200_forward_f64}
 _BWD = {torch.float32: _lib.lib.msda_b200_backward_f32, torch.float64: _lib.lib.msda_b200_backward_f64}
 
@@ -73,10 +101,11 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     N, S, M, D, L, Lq, P = _check_common(named, im2col_step, "ms_deform_attn_forward_cuda")
     with torch.cuda.device(value.device):
         output = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
-        rc = _FWD[value.dtype](
-            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
-            sampling_loc.data_ptr(), attn_weight.data_ptr(), N, S, M, D, L, Lq, P,
-            output.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        with _timed("forward"):
+            rc = _FWD[value.dtype](
+                value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                sampling_loc.data_ptr(), attn_weight.data_ptr(), N, S, M, D, L, Lq, P,
+                output.data_ptr(), torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "ms_deform_attn_forward")
     return output
 
@@ -94,11 +123,12 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
         grad_value = torch.zeros_like(value)            # accumulated by reductions (cu:126)
         grad_loc = torch.empty_like(sampling_loc)       # fully overwritten (cf. cu:127)
         grad_w = torch.empty_like(attn_weight)          # fully overwritten (cf. cu:128)
-        rc = _BWD[value.dtype](
-            grad_output.data_ptr(), value.data_ptr(), spatial_shapes.data_ptr(),
-            level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
-            N, S, M, D, L, Lq, P, grad_value.data_ptr(), grad_loc.data_ptr(), grad_w.data_ptr(),
-            torch.cuda.current_stream().cuda_stream)
+        with _timed("backward"):
+            rc = _BWD[value.dtype](
+                grad_output.data_ptr(), value.data_ptr(), spatial_shapes.data_ptr(),
+                level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
+                N, S, M, D, L, Lq, P, grad_value.data_ptr(), grad_loc.data_ptr(), grad_w.data_ptr(),
+                torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "ms_deform_attn_backward")
     return [grad_value, grad_loc, grad_w]
 

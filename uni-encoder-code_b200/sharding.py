@@ -1,0 +1,104 @@
+"""Multi-GPU partitioning of the MSDA path.  One process per GPU,
+``torch.distributed`` for the plumbing; collectives only where the path has a real exchange.
+
+* **Batch sharding** (training and batched inference): every image is independent in forward and
+  backward (the reference already chunks the batch, ms_deform_attn_cuda.cu:66-80), so ranks own
+  disjoint images and the op needs no collective.  Training adds the usual DDP gradient all-reduce
+  (the reference's only strategy, tools/trainers/trainer.py:110).
+* **Query-range sharding** (single-image inference): a rank owns a contiguous range of the
+  ``Lq == S`` query/pixel rows.  Per-row work (projections, softmax, LayerNorm, FFN) stays local;
+  the only exchange is one all-gather of the projected ``value`` rows per encoder layer, because a
+  query may sample any pixel.  The op is then called with the full ``value`` and the rank's slice
+  of ``sampling_locations`` / ``attention_weights``.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .modules import MSDeformAttnTransformerEncoderOnly, reference_points_for
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced [start, stop) of `total` items for `rank` (first ranks get the remainder)."""
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside world of {world}")
+    base, rem = divmod(total, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def shard_batch(tensors: Dict[str, torch.Tensor], rank: int, world: int,
+                replicated=("spatial_shapes", "level_start_index")) -> Dict[str, torch.Tensor]:
+    """Slice dim 0 of every per-image tensor; the level tables are replicated."""
+    n = next(v for k, v in tensors.items() if k not in replicated).shape[0]
+    a, b = shard_range(n, rank, world)
+    return {k: (v if k in replicated else v[a:b].contiguous()) for k, v in tensors.items()}
+
+
+def all_gather_rows(local: torch.Tensor, sizes: List[int], group=None) -> torch.Tensor:
+    """Concatenate per-rank row blocks ``[N, rows_r, C]`` along dim 1 (ragged sizes allowed)."""
+    world = dist.get_world_size(group)
+    n = local.shape[0]
+    if len(set(sizes)) == 1:
+        out = local.new_empty((world * n,) + tuple(local.shape[1:]))     # rank-major along dim 0
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return torch.cat(list(out.view((world, n) + tuple(local.shape[1:])).unbind(0)), 1)
+    # ragged: pad every block to the largest one (one collective; the backends' list-based
+    # all_gather does not accept uneven sizes everywhere), then drop the padding
+    top = max(sizes)
+    padded = local.new_zeros((local.shape[0], top) + tuple(local.shape[2:]))
+    padded[:, :local.shape[1]] = local
+    out = local.new_empty((world * n,) + tuple(padded.shape[1:]))
+    dist.all_gather_into_tensor(out, padded, group=group)
+    out = out.view((world,) + tuple(padded.shape))
+    return torch.cat([out[r, :, :s] for r, s in enumerate(sizes)], 1)
+
+
+class QueryShardedEncoder:
+    """Inference-only query-range sharding of an ``MSDeformAttnTransformerEncoderOnly``.
+
+    Every rank holds the same weights and the same flattened inputs; rank r keeps rows
+    ``shard_range(S, r, world)`` of the running ``src``.  Per layer: local ``value_proj`` on the
+    rank's rows, all-gather of ``value`` (S*256*4 bytes in total), the MSDA op on the rank's
+    queries against the full ``value``, then the local output projection / LayerNorm / FFN.
+    A final all-gather returns the full memory on every rank.
+    """
+
+    def __init__(self, encoder_only: MSDeformAttnTransformerEncoderOnly, group=None):
+        self.model = encoder_only
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    @torch.no_grad()
+    def forward(self, srcs, pos_embeds):
+        m = self.model
+        src, pos, shapes, lsi, levels = m.flatten_inputs(srcs, pos_embeds)
+        S = src.shape[1]
+        sizes = [b - a for a, b in (shard_range(S, r, self.world) for r in range(self.world))]
+        a, b = shard_range(S, self.rank, self.world)
+        ref = reference_points_for(levels, src.device)[:, a:b].expand(src.shape[0], -1, -1, -1)
+        x, p = src[:, a:b], pos[:, a:b]
+        for layer in m.encoder.layers:
+            attn = layer.self_attn
+            value_local = attn.value_proj(x)
+            value = all_gather_rows(value_local, sizes, self.group)
+            value = value.view(value.shape[0], S, attn.n_heads, attn.d_model // attn.n_heads)
+            loc, w = attn.sampling_inputs(x + p, ref, shapes)
+            out = attn._core(value, shapes, lsi, loc.contiguous(), w.contiguous(), attn.im2col_step)
+            x = layer.forward_ffn(layer.norm1(x + layer.dropout1(attn.output_proj(out))))
+        return all_gather_rows(x, sizes, self.group), shapes, lsi
+
+    __call__ = forward
+
+
+def ddp_wrap(module: torch.nn.Module, device: Optional[torch.device] = None):
+    """DistributedDataParallel with the reference's settings (broadcast_buffers=False,
+    tools/trainers/trainer.py:110); gradients are all-reduced over NCCL in 25 MB buckets."""
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    if device is not None and device.type == "cuda":
+        return DDP(module, device_ids=[device.index], broadcast_buffers=False)
+    return DDP(module, broadcast_buffers=False)
