@@ -182,6 +182,9 @@ def run_b200_arm(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner there at VERSION/INFO
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     pkg = load_package()

@@ -232,7 +232,7 @@ static cudaError_t launch_fwd_lp(const float *value, const int64_t *shapes, cons
     switch (option_value(OPT_FWD_VARIANT)) {
         // 1-4: lane = corner*8 + chunk (LDG.128);  5-8: lane = channel (LDG.32, one line per instruction)
         case 1: return launch_fwd_cfg<LP, 8, 8, 8>(value, shapes, lstart, loc, attw, d, out, stream);
-        case 2: return launch_fwd_cfg<LP, 16, 16, 8>(value, shapes, lstart, loc, attw, d, out, stream);
+
         case 3: return launch_fwd_cfg<LP, 32, 16, 8>(value, shapes, lstart, loc, attw, d, out, stream);
         case 4: return launch_fwd_cfg<LP, 16, 8, 8>(value, shapes, lstart, loc, attw, d, out, stream);
         case 5: return launch_fwd_cfg<LP, 8, 8, 32>(value, shapes, lstart, loc, attw, d, out, stream);
@@ -243,8 +243,9 @@ static cudaError_t launch_fwd_lp(const float *value, const int64_t *shapes, cons
         case 12: return launch_fwd_cfg<LP, 16, 8, 16>(value, shapes, lstart, loc, attw, d, out, stream);
         case 7: return launch_fwd_cfg<LP, 32, 16, 32>(value, shapes, lstart, loc, attw, d, out, stream);
         case 8: return launch_fwd_cfg<LP, 16, 8, 32>(value, shapes, lstart, loc, attw, d, out, stream);
-        case 6:
-        default: return launch_fwd_cfg<LP, 16, 16, 32>(value, shapes, lstart, loc, attw, d, out, stream);
+        case 6: return launch_fwd_cfg<LP, 16, 16, 32>(value, shapes, lstart, loc, attw, d, out, stream);
+        case 2:
+        default: return launch_fwd_cfg<LP, 16, 16, 8>(value, shapes, lstart, loc, attw, d, out, stream);
     }
 }
 

@@ -137,18 +137,30 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
         return self.forward_ffn(self.norm1(src + self.dropout1(attn)))
 
 
+_REF_CACHE = {}
+
+
 def reference_points_for(levels: Sequence[Tuple[int, int]], device, dtype=torch.float32):
     """[1, S, L, 2] pixel-centre reference points of every query, replicated over levels, for
-    valid_ratios == 1 (msdeformattn.py:152-166 with the all-False masks of :68-69).  `levels` is a
-    host-side list, so no CUDA tensor is iterated."""
-    pts = []
-    for H, W in levels:
-        ys = torch.linspace(0.5, H - 0.5, H, dtype=dtype, device=device) / H
-        xs = torch.linspace(0.5, W - 0.5, W, dtype=dtype, device=device) / W
-        yy, xx = torch.meshgrid(ys, xs, indexing="ij")
-        pts.append(torch.stack((xx.reshape(-1), yy.reshape(-1)), -1))
-    ref = torch.cat(pts, 0)
-    return ref[None, :, None, :].expand(1, ref.shape[0], len(levels), 2)
+    valid_ratios == 1 (msdeformattn.py:152-166 with the all-False masks of :68-69).
+
+    `levels` is a host-side list, so no CUDA tensor is iterated (msdeformattn.py:154 syncs).  The
+    points are input-independent: they are computed once per (levels, device, dtype) on the host
+    with true IEEE division -- torch's CUDA tensor/scalar division multiplies by a reciprocal and
+    lands 1 ulp away from the reference's tensor/tensor division -- and cached on the device."""
+    key = (tuple((int(h), int(w)) for h, w in levels), str(device), dtype)
+    hit = _REF_CACHE.get(key)
+    if hit is None:
+        pts = []
+        for H, W in key[0]:
+            ys = torch.linspace(0.5, H - 0.5, H, dtype=dtype) / torch.tensor(float(H), dtype=dtype)
+            xs = torch.linspace(0.5, W - 0.5, W, dtype=dtype) / torch.tensor(float(W), dtype=dtype)
+            yy, xx = torch.meshgrid(ys, xs, indexing="ij")
+            pts.append(torch.stack((xx.reshape(-1), yy.reshape(-1)), -1))
+        ref = torch.cat(pts, 0)
+        hit = ref[None, :, None, :].expand(1, ref.shape[0], len(key[0]), 2).contiguous().to(device)
+        _REF_CACHE[key] = hit
+    return hit
 
 
 class MSDeformAttnTransformerEncoder(nn.Module):
