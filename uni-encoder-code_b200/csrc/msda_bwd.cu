@@ -7,7 +7,10 @@
 // 128 scalar atomicAdds, writes 3 partials per thread to shared memory and lets
 // thread 0 add them up serially between two __syncthreads.
 //
-// Design (same work decomposition and phase 1 as msda_fwd.cu):
+// Design (same work decomposition, phase 1 and record layout as msda_fwd.cu):
+//   * the L*P points of a query are consumed in two batches: all value loads of a
+//     batch are issued before the first of them is used, so a warp has 6 x 512 bytes
+//     in flight instead of paying one memory latency per point;
 //   * lane = corner*8 + chunk.  Per sampling point a lane loads 16 bytes of its
 //     corner's value row, forms the partial dot product with its 4 grad_output
 //     channels (d) and adds weight*grad_output to grad_value with ONE 128-bit
@@ -28,20 +31,25 @@ namespace msda {
 
 template <int LP, int WARPS, int TILE_W>
 struct BwdCfg {
+    static_assert(LP % 2 == 0, "points are consumed in pairs");
+    static constexpr int kPairs = LP / 2;            // record pairs per query
     static constexpr int kQPW = 8;
     static constexpr int kGroup = WARPS * kQPW;
     static constexpr int kTileH = kGroup / TILE_W;
     static constexpr int kRounds = (kQPW * LP + 31) / 32;
     static constexpr int kRecPerWarp = kRounds * 32;
-    // per record: 4 x {offset, weight} (32 B) + {lh, lw, aw*W, aw*H} (16 B)
-    static constexpr size_t kSmem = (size_t)WARPS * kRecPerWarp * (4 * sizeof(uint2) + sizeof(float4));
+    static constexpr int kPlane = kRecPerWarp + 2;   // padded corner-plane stride, see msda_fwd.cu
+    // per warp: 4 corner planes of {offset, weight} + one {lh, lw, aw*W, aw*H} per point
+    static constexpr size_t kRecBytes = (size_t)WARPS * 4 * kPlane * sizeof(uint2);
+    static constexpr size_t kSmem = kRecBytes + (size_t)WARPS * kRecPerWarp * sizeof(float4);
     // sizes along the two reduce-scatters
     static constexpr int kN1 = (LP + 1) / 2, kN2 = (kN1 + 1) / 2, kN3 = (kN2 + 1) / 2;  // per-lane D count
     static constexpr int kT0 = 3 * kN3, kT1 = (kT0 + 1) / 2, kT2 = (kT1 + 1) / 2;
 };
 
-template <int LP, int WARPS, int TILE_W, bool VEC_RED>
-__global__ void __launch_bounds__(WARPS * 32)
+// BATCH = record pairs whose 2*BATCH value loads are in flight together (register budget)
+template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int BATCH>
+__global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
 msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict__ value,
                     const int64_t *__restrict__ shapes, const int64_t *__restrict__ lstart,
                     const float *__restrict__ loc, const float *__restrict__ attw, const Dims d,
@@ -53,9 +61,8 @@ msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int corner = lane >> 3, chunk = lane & 7;
-    uint2 *rec = reinterpret_cast<uint2 *>(smem_raw) + (size_t)warp * Cfg::kRecPerWarp * 4;
-    float4 *aux = reinterpret_cast<float4 *>(smem_raw + (size_t)WARPS * Cfg::kRecPerWarp * 4 * sizeof(uint2)) +
-                  (size_t)warp * Cfg::kRecPerWarp;
+    uint2 *rec = reinterpret_cast<uint2 *>(smem_raw) + (size_t)warp * 4 * Cfg::kPlane;
+    float4 *aux = reinterpret_cast<float4 *>(smem_raw + Cfg::kRecBytes) + (size_t)warp * Cfg::kRecPerWarp;
 
     fill_level_table(lt, shapes, lstart, d.L, d.P, d.S, d.Lq, Cfg::kGroup, Cfg::kTileH, TILE_W,
                      want_spatial);
@@ -78,27 +85,38 @@ msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict_
         int q0, cnt;
         warp_queries(lt, d.L, g, warp, Cfg::kGroup, Cfg::kTileH, TILE_W, d.Lq, q0, cnt);
 
-        // ---- phase 1: records ----
+        // ---- phase 1: records (one plane per corner) + per-point coefficients ----
+        float2 xy[Cfg::kRounds];
+        float aw[Cfg::kRounds];
+#pragma unroll
+        for (int r = 0; r < Cfg::kRounds; ++r) {
+            const int s = r * 32 + lane;
+            const int qi = s / LP, sp = s - qi * LP;
+            xy[r] = make_float2(0.f, 0.f);
+            aw[r] = 0.f;
+            if (qi < cnt) {
+                const long long row = ((n * d.Lq + q0 + qi) * M + m) * (long long)LP + sp;
+                xy[r] = ldg_stream_f2(reinterpret_cast<const float2 *>(loc) + row);
+                aw[r] = ldg_stream_f1(attw + row);
+            }
+        }
 #pragma unroll
         for (int r = 0; r < Cfg::kRounds; ++r) {
             const int s = r * 32 + lane;
             const int qi = s / LP, sp = s - qi * LP;
             if (qi < cnt) {
-                const long long row = ((n * d.Lq + q0 + qi) * M + m) * (long long)LP + sp;
-                const float2 xy = ldg_stream_f2(reinterpret_cast<const float2 *>(loc) + row);
-                const float aw = ldg_stream_f1(attw + row);
-                const int l = lt.level_of[sp];
-                const int H = lt.H[l], W = lt.W[l];
-                const Geom<float> gm = decompose(xy.x, xy.y, H, W);
+                const int4 lv = lt.hws[lt.level_of[sp]];     // {H, W, start, -}
+                const Geom<float> gm = decompose(xy[r].x, xy[r].y, lv.x, lv.y);
                 uint4 lo, hi;
-                make_record<false>(gm, aw, (uint32_t)lt.start[l], (uint32_t)W, pix_stride,
+                make_record<false>(gm, aw[r], (uint32_t)lv.z, (uint32_t)lv.y, pix_stride,
                                    (uint32_t)m * 8u, lo, hi);
-                uint4 *dst = reinterpret_cast<uint4 *>(rec + (size_t)s * 4);
-                dst[0] = lo;
-                dst[1] = hi;
+                rec[0 * Cfg::kPlane + s] = make_uint2(lo.x, lo.y);
+                rec[1 * Cfg::kPlane + s] = make_uint2(lo.z, lo.w);
+                rec[2 * Cfg::kPlane + s] = make_uint2(hi.x, hi.y);
+                rec[3 * Cfg::kPlane + s] = make_uint2(hi.z, hi.w);
                 // invalid point: every D_k is 0 (no corner is read), so any finite
                 // coefficients give the reference's zero gradients (cuh:370-372)
-                aux[s] = gm.valid ? make_float4(gm.lh, gm.lw, aw * (float)W, aw * (float)H)
+                aux[s] = gm.valid ? make_float4(gm.lh, gm.lw, aw[r] * (float)lv.y, aw[r] * (float)lv.x)
                                   : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
@@ -108,31 +126,40 @@ msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict_
         const long long img = n * (long long)d.S * M * 8 + chunk;
         const float4 *vb = reinterpret_cast<const float4 *>(value) + img;
         float4 *gvb = reinterpret_cast<float4 *>(grad_value) + img;
+        const uint4 *plane = reinterpret_cast<const uint4 *>(rec + corner * Cfg::kPlane);
         for (int qi = 0; qi < cnt; ++qi) {
             const long long qrow = (n * d.Lq + q0 + qi) * M + m;
             const float4 go = ldg_stream_f4(reinterpret_cast<const float4 *>(grad_out) + qrow * 8 + chunk);
-            const uint2 *rq = rec + (size_t)qi * LP * 4 + corner;
+            const uint4 *rq = plane + qi * Cfg::kPairs;
             float dpart[LP];
 #pragma unroll
-            for (int sp = 0; sp < LP; ++sp) {
-                const uint2 e = rq[sp * 4];
-                float dot = 0.f;
-                if (e.x != kNoCorner) {
-                    const float4 v = ldg_keep_f4(at_off16(vb, e.x));
-                    const float w = __uint_as_float(e.y);
-                    dot = fmaf(v.w, go.w, fmaf(v.z, go.z, fmaf(v.y, go.y, v.x * go.x)));
-                    const float4 gv = make_float4(w * go.x, w * go.y, w * go.z, w * go.w);
-                    if (VEC_RED) {
-                        red_add_f4(at_off16(gvb, e.x), gv);
-                    } else {
-                        float *p = reinterpret_cast<float *>(at_off16(gvb, e.x));
-                        atomicAdd(p + 0, gv.x);
-                        atomicAdd(p + 1, gv.y);
-                        atomicAdd(p + 2, gv.z);
-                        atomicAdd(p + 3, gv.w);
+            for (int b0 = 0; b0 < Cfg::kPairs; b0 += BATCH) {
+                constexpr int kB = BATCH;
+                uint4 e[kB];
+                float4 va[kB], vc[kB];
+#pragma unroll
+                for (int j = 0; j < kB; ++j)
+                    if (b0 + j < Cfg::kPairs) e[j] = lds_u4(rq + b0 + j);
+#pragma unroll
+                for (int j = 0; j < kB; ++j) {                  // 2*BATCH independent loads in flight
+                    if (b0 + j < Cfg::kPairs) {
+                        va[j] = ldg_keep_f4_if(vb, e[j].x);
+                        vc[j] = ldg_keep_f4_if(vb, e[j].z);
                     }
                 }
-                dpart[sp] = dot;
+#pragma unroll
+                for (int j = 0; j < kB; ++j) {
+                    if (b0 + j < Cfg::kPairs) {
+                        const int sp = 2 * (b0 + j);
+                        const float wa = __uint_as_float(e[j].y), wc = __uint_as_float(e[j].w);
+                        red_add_f4_if(gvb, e[j].x, make_float4(wa * go.x, wa * go.y, wa * go.z, wa * go.w));
+                        red_add_f4_if(gvb, e[j].z, make_float4(wc * go.x, wc * go.y, wc * go.z, wc * go.w));
+                        const float da = fmaf(va[j].w, go.w, fmaf(va[j].z, go.z, fmaf(va[j].y, go.y, va[j].x * go.x)));
+                        const float dc = fmaf(vc[j].w, go.w, fmaf(vc[j].z, go.z, fmaf(vc[j].y, go.y, vc[j].x * go.x)));
+                        dpart[sp] = (e[j].x != kNoCorner) ? da : 0.f;      // a corner outside contributes 0
+                        dpart[sp + 1] = (e[j].z != kNoCorner) ? dc : 0.f;
+                    }
+                }
             }
             // D_k for this lane's corner: sum over the 8 chunk lanes (lane bits 2,1,0)
             float r1[Cfg::kN1], r2[Cfg::kN2], r3[Cfg::kN3];
@@ -189,13 +216,13 @@ msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict_
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
-template <int LP, int WARPS, int TILE_W, bool VEC_RED>
+template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int BATCH>
 static cudaError_t launch_bwd_cfg(const float *grad_out, const float *value, const int64_t *shapes,
                                   const int64_t *lstart, const float *loc, const float *attw,
                                   const Dims &d, float *grad_value, float *grad_loc,
                                   float *grad_attw, cudaStream_t stream) {
     using Cfg = BwdCfg<LP, WARPS, TILE_W>;
-    auto kern = msda_bwd_d32_kernel<LP, WARPS, TILE_W, VEC_RED>;
+    auto kern = msda_bwd_d32_kernel<LP, WARPS, TILE_W, MIN_CTAS, BATCH>;
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -225,13 +252,20 @@ template <int LP>
 static cudaError_t launch_bwd_lp(const float *grad_out, const float *value, const int64_t *shapes,
                                  const int64_t *lstart, const float *loc, const float *attw,
                                  const Dims &d, float *gv, float *gl, float *gw, cudaStream_t st) {
+    // variant = (warps, query tile w, min CTAs per SM -> register budget, load batch in pairs)
+#define MSDA_BWD(W, TW, C, B) \
+    launch_bwd_cfg<LP, W, TW, C, B>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, st)
     switch (option_value(OPT_BWD_VARIANT)) {
-        case 1: return launch_bwd_cfg<LP, 8, 8, true>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, st);
-        case 3: return launch_bwd_cfg<LP, 16, 16, false>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, st);
-        case 4: return launch_bwd_cfg<LP, 16, 8, true>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, st);
+        case 1: return MSDA_BWD(8, 8, 4, 1);     //  8 warps, tile  8x8,  64 regs
+        case 3: return MSDA_BWD(32, 16, 1, 1);   // 32 warps, tile 16x16, 64 regs, one CTA per SM
+        case 4: return MSDA_BWD(16, 16, 2, 2);   // 16 warps, tile  8x16, 64 regs, 4 loads in flight (spills)
+        case 5: return MSDA_BWD(16, 16, 1, 3);   // 16 warps, tile  8x16, 128 regs, 6 loads in flight
+        case 6: return MSDA_BWD(8, 8, 2, 6);     //  8 warps, tile  8x8, 114 regs, 12 loads in flight
+        case 7: return MSDA_BWD(4, 8, 5, 3);     //  4 warps, tile  4x8,  96 regs
         case 2:
-        default: return launch_bwd_cfg<LP, 16, 16, true>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, st);
+        default: return MSDA_BWD(16, 16, 2, 1);  // 16 warps, tile  8x16, 64 regs, 2 loads in flight
     }
+#undef MSDA_BWD
 }
 
 cudaError_t launch_bwd_d32(const float *grad_out, const float *value, const int64_t *shapes,

@@ -71,6 +71,7 @@ __device__ __forceinline__ Geom<T> decompose(T loc_x, T loc_y, int H, int W) {
 // thread per level (the reference re-reads them inside its level loop, cuh:279-282).
 // ---------------------------------------------------------------------------
 struct LevelTable {
+    int4 hws[kMaxLevels];             // {H, W, start, 0}: one 128-bit shared load per point in phase 1
     int H[kMaxLevels];
     int W[kMaxLevels];
     int start[kMaxLevels];            // first pixel of the level inside one image
@@ -97,6 +98,7 @@ __device__ __forceinline__ void fill_level_table(LevelTable &lt, const int64_t *
             lt.H[l] = H;
             lt.W[l] = W;
             lt.start[l] = (int)st;
+            lt.hws[l] = make_int4(H, W, (int)st, 0);
             layout_ok = layout_ok && (st == pix) && H > 0 && W > 0;
             pix += (long long)H * W;
             lt.tiles_x[l] = (W + tile_w - 1) / tile_w;
@@ -261,6 +263,28 @@ __device__ __forceinline__ void stg_stream_f2(float2 *p, float2 v) {
 __device__ __forceinline__ void red_add_f4(float4 *p, float4 v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
                  "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+// Predicated forms used by the backward kernel: the validity test lives inside the asm block so
+// that no C++ branch surrounds the access -- the loads stay freely schedulable (a batch of them is
+// issued before the first use) and the reductions keep program order without fencing the loads.
+__device__ __forceinline__ float4 ldg_keep_f4_if(const float4 *base, uint32_t off16) {
+    float4 r;
+    const float4 *p = at_off16(base, off16);
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0xffffffff;\n\t"
+        "mov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\tmov.f32 %2, 0f00000000;\n\t"
+        "mov.f32 %3, 0f00000000;\n\t"
+        "@p ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];\n\t}"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+        : "l"(p), "r"(off16));
+    return r;
+}
+__device__ __forceinline__ void red_add_f4_if(float4 *base, uint32_t off16, float4 v) {
+    float4 *p = at_off16(base, off16);
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0xffffffff;\n\t"
+                 "@p red.global.add.v4.f32 [%0], {%1,%2,%3,%4};\n\t}"
+                 ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(off16)
                  : "memory");
 }
 

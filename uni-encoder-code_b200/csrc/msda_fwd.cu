@@ -5,54 +5,59 @@
 // (ms_deform_im2col_cuda.cuh:242-304), which runs one thread per output element
 // and recomputes every sampling point's geometry in all 32 lanes.
 //
-// Design (see DESIGN.md "forward kernel"):
+// Design:
 //   * persistent CTAs walk work items = (image n, head m, group of 8*WARPS queries);
 //     when the queries are laid out like the value pixels (encoder self-attention)
 //     a group is a 2-D tile of one level, so neighbouring queries' bilinear
 //     footprints overlap in L1;
 //   * each warp owns 8 consecutive queries of the item.  Phase 1: the 8*L*P
 //     sampling points are spread over the lanes (one point per lane per round):
-//     load (x, y, weight), run decompose() once per point and write a 32-byte
-//     record {offset, bilinear*attention weight} x 4 corners to shared memory;
-//   * phase 2, per query: lane = corner*8 + chunk.  Each lane reads its corner's
-//     record (one 8-byte shared load, broadcast over 8 lanes), fetches 16 bytes of
-//     that corner's 128-byte value row (one LDG.128; a warp instruction covers the
-//     four corner rows of a point) and accumulates 4 channels;
+//     load (x, y, weight), run decompose() once per point and write the four
+//     corner records {offset, bilinear*attention weight} to shared memory, one
+//     plane per corner (conflict-free 8-byte stores);
+//   * phase 2, per query: lane = corner*8 + chunk.  One 128-bit shared load gives a
+//     lane its corner's records of TWO points; per point it fetches 16 bytes of that
+//     corner's 128-byte value row (one LDG.128; a warp instruction covers the four
+//     corner rows of a point) and accumulates 4 channels;
 //   * the four corner groups are summed with a 3-shuffle reduce-scatter that leaves
 //     one output channel per lane: the store is a single coalesced 128-byte line.
+//
+// The kernel is bound by the L1TEX data pipe: one wavefront per 128-byte value row
+// (48 per (query, head)) plus the shared-memory wavefronts of the records
+// (profiles/); the record layout exists to keep the latter small.
 #include "msda_common.cuh"
 
 namespace msda {
 
 template <int LP, int WARPS, int TILE_W>
 struct FwdCfg {
+    static_assert(LP % 2 == 0, "points are consumed in pairs");
     static constexpr int kQPW = 8;                        // queries per warp per item
     static constexpr int kGroup = WARPS * kQPW;           // queries per item
     static constexpr int kTileH = kGroup / TILE_W;
     static constexpr int kRounds = (kQPW * LP + 31) / 32; // phase-1 rounds
-    static constexpr int kRecPerWarp = kRounds * 32;      // records, padded to full rounds
-    static constexpr size_t kSmem = (size_t)WARPS * kRecPerWarp * 4 * sizeof(uint2);
+    static constexpr int kRecPerWarp = kRounds * 32;      // records per corner plane
+    // plane stride in records: +2 (16 bytes) so the four corner planes start 4 banks apart and the
+    // 4-address LDS.128 of phase 2 is conflict-free (an unpadded stride is a multiple of 128 bytes)
+    static constexpr int kPlane = kRecPerWarp + 2;
+    static constexpr size_t kSmem = (size_t)WARPS * 4 * kPlane * sizeof(uint2);
     static_assert(TILE_W % 8 == 0 && kGroup % TILE_W == 0, "tile shape");
 };
 
-// LANES_PER_ROW = 8 : lane = corner*8 + chunk, one LDG.128 per point covers its 4 corner rows
-// LANES_PER_ROW = 32: lane = channel, one LDG.32 per corner row (a warp instruction touches
-//                     exactly one 128-byte line: one L1 wavefront, no intra-instruction replay)
-template <int LP, int WARPS, int TILE_W, int LANES_PER_ROW>
-__global__ void __launch_bounds__(WARPS * 32)
+template <int LP, int WARPS, int TILE_W, int MIN_CTAS>
+__global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
 msda_fwd_d32_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes,
                     const int64_t *__restrict__ lstart, const float *__restrict__ loc,
                     const float *__restrict__ attw, const Dims d, const int want_spatial,
                     float *__restrict__ out) {
     using Cfg = FwdCfg<LP, WARPS, TILE_W>;
-    constexpr bool kRowwise = LANES_PER_ROW == 32;
-    constexpr bool kHalfwise = LANES_PER_ROW == 16;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ LevelTable lt;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int corner = lane >> 3, chunk = lane & 7;
-    uint2 *rec = reinterpret_cast<uint2 *>(smem_raw) + (size_t)warp * Cfg::kRecPerWarp * 4;
+    // corner plane k of this warp: rec + k * kPlane, indexed by (query slot * LP + point)
+    uint2 *rec = reinterpret_cast<uint2 *>(smem_raw) + (size_t)warp * 4 * Cfg::kPlane;
 
     fill_level_table(lt, shapes, lstart, d.L, d.P, d.S, d.Lq, Cfg::kGroup, Cfg::kTileH, TILE_W,
                      want_spatial);
@@ -91,101 +96,55 @@ msda_fwd_d32_kernel(const float *__restrict__ value, const int64_t *__restrict__
             const int s = r * 32 + lane;
             const int qi = s / LP, sp = s - qi * LP;
             if (qi < cnt) {
-                const int l = lt.level_of[sp];
-                const int H = lt.H[l], W = lt.W[l];
-                const Geom<float> gm = decompose(xy[r].x, xy[r].y, H, W);
+                const int4 lv = lt.hws[lt.level_of[sp]];     // {H, W, start, -}
+                const Geom<float> gm = decompose(xy[r].x, xy[r].y, lv.x, lv.y);
                 uint4 lo, hi;   // {off0, w0, off1, w1}, {off2, w2, off3, w3}
-                make_record<kRowwise || kHalfwise>(gm, aw[r], (uint32_t)lt.start[l], (uint32_t)W,
-                                                   pix_stride, (uint32_t)m * 8u, lo, hi);
-                uint4 *dst = reinterpret_cast<uint4 *>(rec + (size_t)s * 4);
-                if (kHalfwise) {   // slot h holds corners (h, h+2): what half-warp h reads
-                    dst[0] = make_uint4(lo.x, lo.y, hi.x, hi.y);
-                    dst[1] = make_uint4(lo.z, lo.w, hi.z, hi.w);
-                } else {
-                    dst[0] = lo;
-                    dst[1] = hi;
-                }
+                make_record<false>(gm, aw[r], (uint32_t)lv.z, (uint32_t)lv.y, pix_stride,
+                                   (uint32_t)m * 8u, lo, hi);
+                rec[0 * Cfg::kPlane + s] = make_uint2(lo.x, lo.y);
+                rec[1 * Cfg::kPlane + s] = make_uint2(lo.z, lo.w);
+                rec[2 * Cfg::kPlane + s] = make_uint2(hi.x, hi.y);
+                rec[3 * Cfg::kPlane + s] = make_uint2(hi.z, hi.w);
             }
         }
         __syncwarp();
 
         // ---- phase 2: gather + weighted reduction, one query at a time ----
-        if (kHalfwise) {
-            // lane = half*16 + j: half-warp `half` reads corner rows (half, half+2), lane j channels 2j, 2j+1
-            const int half = lane >> 4, j = lane & 15;
-            const float2 *vb = reinterpret_cast<const float2 *>(value + n * (long long)d.S * M * 32) + j;
-            for (int qi = 0; qi < cnt; ++qi) {
-                const uint4 *rq = reinterpret_cast<const uint4 *>(rec + (size_t)qi * LP * 4) + half;
-                float2 acc = make_float2(0.f, 0.f);
+        const float4 *vb = reinterpret_cast<const float4 *>(value) + n * (long long)d.S * M * 8 + chunk;
+        const uint4 *plane = reinterpret_cast<const uint4 *>(rec + corner * Cfg::kPlane);
+        for (int qi = 0; qi < cnt; ++qi) {
+            const uint4 *rq = plane + qi * (LP / 2);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int sp = 0; sp < LP; ++sp) {
-                    const uint4 e = lds_u4(rq + 2 * sp);
-                    if (e.x != kNoCorner) {                           // point in range (warp-uniform)
-                        const float2 va = ldg_keep_f2(at_off16(vb, e.x));
-                        const float2 vc = ldg_keep_f2(at_off16(vb, e.z));
-                        const float wa = __uint_as_float(e.y), wc = __uint_as_float(e.w);
-                        acc.x = fmaf(wa, va.x, acc.x);
-                        acc.y = fmaf(wa, va.y, acc.y);
-                        acc.x = fmaf(wc, vc.x, acc.x);
-                        acc.y = fmaf(wc, vc.y, acc.y);
-                    }
+            for (int sp2 = 0; sp2 < LP / 2; ++sp2) {
+                const uint4 e = lds_u4(rq + sp2);           // this corner's records of 2 points
+                if (e.x != kNoCorner) {
+                    const float4 v = ldg_keep_f4(at_off16(vb, e.x));
+                    const float w = __uint_as_float(e.y);
+                    acc.x = fmaf(w, v.x, acc.x);
+                    acc.y = fmaf(w, v.y, acc.y);
+                    acc.z = fmaf(w, v.z, acc.z);
+                    acc.w = fmaf(w, v.w, acc.w);
                 }
-                // sum the two halves; lane ends with channel 2j + half
-                const float keep = half ? acc.y : acc.x, send = half ? acc.x : acc.y;
-                const float res = keep + __shfl_xor_sync(kFullMask, send, 16);
-                float *o = out + ((n * d.Lq + q0 + qi) * M + m) * 32LL + 2 * j + half;
-                stg_stream_f1(o, res);
-            }
-        } else if (kRowwise) {
-            const float *vb = value + n * (long long)d.S * M * 32 + lane;
-            for (int qi = 0; qi < cnt; ++qi) {
-                const uint4 *rq = reinterpret_cast<const uint4 *>(rec + (size_t)qi * LP * 4);
-                float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-                for (int sp = 0; sp < LP; ++sp) {
-                    const uint4 a = rq[2 * sp], b = rq[2 * sp + 1];   // broadcast reads
-                    if (a.x != kNoCorner) {                           // point in range (warp-uniform)
-                        const float v0 = ldg_keep_f1(at_off16(vb, a.x));
-                        const float v1 = ldg_keep_f1(at_off16(vb, a.z));
-                        const float v2 = ldg_keep_f1(at_off16(vb, b.x));
-                        const float v3 = ldg_keep_f1(at_off16(vb, b.z));
-                        acc0 = fmaf(__uint_as_float(a.y), v0, acc0);
-                        acc1 = fmaf(__uint_as_float(a.w), v1, acc1);
-                        acc0 = fmaf(__uint_as_float(b.y), v2, acc0);
-                        acc1 = fmaf(__uint_as_float(b.w), v3, acc1);
-                    }
+                if (e.z != kNoCorner) {
+                    const float4 v = ldg_keep_f4(at_off16(vb, e.z));
+                    const float w = __uint_as_float(e.w);
+                    acc.x = fmaf(w, v.x, acc.x);
+                    acc.y = fmaf(w, v.y, acc.y);
+                    acc.z = fmaf(w, v.z, acc.z);
+                    acc.w = fmaf(w, v.w, acc.w);
                 }
-                float *o = out + ((n * d.Lq + q0 + qi) * M + m) * 32LL + lane;
-                stg_stream_f1(o, acc0 + acc1);
             }
-        } else {
-            const float4 *vb = reinterpret_cast<const float4 *>(value) + n * (long long)d.S * M * 8 + chunk;
-            for (int qi = 0; qi < cnt; ++qi) {
-                const uint2 *rq = rec + (size_t)qi * LP * 4 + corner;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int sp = 0; sp < LP; ++sp) {
-                    const uint2 e = rq[sp * 4];
-                    if (e.x != kNoCorner) {
-                        const float4 v = ldg_keep_f4(at_off16(vb, e.x));
-                        const float w = __uint_as_float(e.y);
-                        acc.x = fmaf(w, v.x, acc.x);
-                        acc.y = fmaf(w, v.y, acc.y);
-                        acc.z = fmaf(w, v.z, acc.z);
-                        acc.w = fmaf(w, v.w, acc.w);
-                    }
-                }
-                // sum the 4 corner groups (lane bits 3 and 4); lane ends with channel 4*chunk+corner
-                const bool up16 = lane & 16, up8 = lane & 8;
-                float a0 = up16 ? acc.z : acc.x, a1 = up16 ? acc.w : acc.y;
-                const float s0 = up16 ? acc.x : acc.z, s1 = up16 ? acc.y : acc.w;
-                a0 += __shfl_xor_sync(kFullMask, s0, 16);
-                a1 += __shfl_xor_sync(kFullMask, s1, 16);
-                const float keep = up8 ? a1 : a0, send = up8 ? a0 : a1;
-                const float res = keep + __shfl_xor_sync(kFullMask, send, 8);
-                float *o = out + ((n * d.Lq + q0 + qi) * M + m) * 32LL + chunk * 4 + corner;
-                stg_stream_f1(o, res);
-            }
+            // sum the 4 corner groups (lane bits 3 and 4); lane ends with channel 4*chunk+corner
+            const bool up16 = lane & 16, up8 = lane & 8;
+            float a0 = up16 ? acc.z : acc.x, a1 = up16 ? acc.w : acc.y;
+            const float s0 = up16 ? acc.x : acc.z, s1 = up16 ? acc.y : acc.w;
+            a0 += __shfl_xor_sync(kFullMask, s0, 16);
+            a1 += __shfl_xor_sync(kFullMask, s1, 16);
+            const float keep = up8 ? a1 : a0, send = up8 ? a0 : a1;
+            const float res = keep + __shfl_xor_sync(kFullMask, send, 8);
+            float *o = out + ((n * d.Lq + q0 + qi) * M + m) * 32LL + chunk * 4 + corner;
+            stg_stream_f1(o, res);
         }
         __syncwarp();   // records are overwritten by the next item
     }
@@ -194,12 +153,12 @@ msda_fwd_d32_kernel(const float *__restrict__ value, const int64_t *__restrict__
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
-template <int LP, int WARPS, int TILE_W, int LANES_PER_ROW>
+template <int LP, int WARPS, int TILE_W, int MIN_CTAS>
 static cudaError_t launch_fwd_cfg(const float *value, const int64_t *shapes, const int64_t *lstart,
                                   const float *loc, const float *attw, const Dims &d,
                                   float *out, cudaStream_t stream) {
     using Cfg = FwdCfg<LP, WARPS, TILE_W>;
-    auto kern = msda_fwd_d32_kernel<LP, WARPS, TILE_W, LANES_PER_ROW>;
+    auto kern = msda_fwd_d32_kernel<LP, WARPS, TILE_W, MIN_CTAS>;
     static int ctas_per_sm = 0;   // immutable after first use
     if (ctas_per_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -229,28 +188,19 @@ template <int LP>
 static cudaError_t launch_fwd_lp(const float *value, const int64_t *shapes, const int64_t *lstart,
                                  const float *loc, const float *attw, const Dims &d, float *out,
                                  cudaStream_t stream) {
+    // variant = CTA shape: (warps, query tile h x w, min CTAs per SM for the register budget)
     switch (option_value(OPT_FWD_VARIANT)) {
-        // 1-4: lane = corner*8 + chunk (LDG.128);  5-8: lane = channel (LDG.32, one line per instruction)
-        case 1: return launch_fwd_cfg<LP, 8, 8, 8>(value, shapes, lstart, loc, attw, d, out, stream);
-
-        case 3: return launch_fwd_cfg<LP, 32, 16, 8>(value, shapes, lstart, loc, attw, d, out, stream);
-        case 4: return launch_fwd_cfg<LP, 16, 8, 8>(value, shapes, lstart, loc, attw, d, out, stream);
-        case 5: return launch_fwd_cfg<LP, 8, 8, 32>(value, shapes, lstart, loc, attw, d, out, stream);
-        // 9-12: lane = half*16 + pair (LDG.64, two rows per instruction)
-        case 9: return launch_fwd_cfg<LP, 8, 8, 16>(value, shapes, lstart, loc, attw, d, out, stream);
-        case 10: return launch_fwd_cfg<LP, 16, 16, 16>(value, shapes, lstart, loc, attw, d, out, stream);
-        case 11: return launch_fwd_cfg<LP, 32, 16, 16>(value, shapes, lstart, loc, attw, d, out, stream);
-        case 12: return launch_fwd_cfg<LP, 16, 8, 16>(value, shapes, lstart, loc, attw, d, out, stream);
-        case 7: return launch_fwd_cfg<LP, 32, 16, 32>(value, shapes, lstart, loc, attw, d, out, stream);
-        case 8: return launch_fwd_cfg<LP, 16, 8, 32>(value, shapes, lstart, loc, attw, d, out, stream);
-        case 6: return launch_fwd_cfg<LP, 16, 16, 32>(value, shapes, lstart, loc, attw, d, out, stream);
+        case 1: return launch_fwd_cfg<LP, 8, 8, 4>(value, shapes, lstart, loc, attw, d, out, stream);     // 8x8
+        case 3: return launch_fwd_cfg<LP, 32, 16, 1>(value, shapes, lstart, loc, attw, d, out, stream);   // 16x16
+        case 4: return launch_fwd_cfg<LP, 16, 8, 2>(value, shapes, lstart, loc, attw, d, out, stream);    // 16x8
+        case 5: return launch_fwd_cfg<LP, 8, 16, 4>(value, shapes, lstart, loc, attw, d, out, stream);    // 4x16
         case 2:
-        default: return launch_fwd_cfg<LP, 16, 16, 8>(value, shapes, lstart, loc, attw, d, out, stream);
+        default: return launch_fwd_cfg<LP, 16, 16, 2>(value, shapes, lstart, loc, attw, d, out, stream);  // 8x16
     }
 }
 
-// Returns cudaErrorInvalidConfiguration-free status; `handled` tells the caller
-// whether this specialised path took the problem (otherwise use the generic kernel).
+// `handled` tells the caller whether this specialised path took the problem
+// (otherwise the generic kernel is used).
 cudaError_t launch_fwd_d32(const float *value, const int64_t *shapes, const int64_t *lstart,
                            const float *loc, const float *attw, const Dims &d, float *out,
                            cudaStream_t stream, bool *handled) {
