@@ -30,6 +30,9 @@ METRIC = "msda_fwd_bwd_queries_per_s"
 UNIT = "queries/s"
 DEFAULT_WORKLOAD = "cityscapes_512x1024_b8"
 NOMINAL_HBM_GBS = 8000.0          # north_star's "~8 TB/s"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of
+# this command (profiles/r1_ncu_bench_summary.csv); only valid for the default workload / mode
+NCU_DRAM_TRAFFIC = {("cityscapes_512x1024_b8", "model"): {"forward": 249.0e6, "backward": 528.7e6}}
 FALLBACK_HBM_GBS = 6650.0         # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -292,7 +295,10 @@ def run_b200_arm(args):
         },
         "roofline": {
             "bound": "hbm", "kernel": "msda_bwd_d32_kernel", "achieved": achieved, "peak": peak,
-            "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "unit": "GB/s", "frac": achieved / peak,
+            "traffic": NCU_DRAM_TRAFFIC.get((args.workload, args.mode), {}).get("backward"),
+            "traffic_source": "profiles/r1_ncu_bench_summary.csv (ncu --set full, per launch)",
+            "peak_source": peak_src,
             "algorithmic_bytes_per_launch": bwd_bytes, "ms_per_launch": bwd_mean,
             "frac_of_nominal_8TBs": achieved / NOMINAL_HBM_GBS,
         },
