@@ -123,7 +123,8 @@ def test_kernels_match_oracle(pkg, oracle, levels, batch, heads, channels, point
 
 
 @pytest.mark.parametrize("fwd_variant,bwd_variant,tile_order", [
-    (1, 1, 0), (2, 2, 0), (3, 3, 0), (4, 4, 0), (5, 5, 0), (2, 6, 1), (1, 7, 1), (63, 63, 0)])
+    (1, 1, 0), (2, 2, 0), (3, 3, 0), (4, 4, 0), (5, 5, 0), (6, 6, 0), (7, 7, 0), (8, 8, 0), (2, 2, 1),
+    (7, 8, 1), (63, 63, 0)])
 def test_kernel_variants_agree(pkg, oracle, fwd_variant, bwd_variant, tile_order):
     """Every tile shape / query order / the generic kernel computes the same function."""
     inp = pkg.synthetic.make_inputs([(5, 11), (10, 22), (20, 44)], 2, mode="model", seed=3)

@@ -29,15 +29,17 @@
 
 namespace msda {
 
-template <int LP, int WARPS, int TILE_W>
+// QPW = queries per warp per item: their records are resident in shared memory together, so
+// a smaller QPW leaves more of the SM's 228 KB to L1 (the value rows)
+template <int LP, int WARPS, int TILE_W, int QPW>
 struct BwdCfg {
     static_assert(LP % 2 == 0, "points are consumed in pairs");
     static constexpr int kPairs = LP / 2;            // record pairs per query
-    static constexpr int kQPW = 8;
+    static constexpr int kQPW = QPW;
     static constexpr int kGroup = WARPS * kQPW;
     static constexpr int kTileH = kGroup / TILE_W;
     static constexpr int kRounds = (kQPW * LP + 31) / 32;
-    static constexpr int kRecPerWarp = kRounds * 32;
+    static constexpr int kRecPerWarp = kQPW * LP;
     static constexpr int kPlane = kRecPerWarp + 2;   // padded corner-plane stride, see msda_fwd.cu
     // per warp: 4 corner planes of {offset, weight} + one {lh, lw, aw*W, aw*H} per point
     static constexpr size_t kRecBytes = (size_t)WARPS * 4 * kPlane * sizeof(uint2);
@@ -48,14 +50,14 @@ struct BwdCfg {
 };
 
 // BATCH = record pairs whose 2*BATCH value loads are in flight together (register budget)
-template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int BATCH>
+template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int BATCH, int QPW>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
 msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict__ value,
                     const int64_t *__restrict__ shapes, const int64_t *__restrict__ lstart,
                     const float *__restrict__ loc, const float *__restrict__ attw, const Dims d,
                     const int want_spatial, float *__restrict__ grad_value,
                     float *__restrict__ grad_loc, float *__restrict__ grad_attw) {
-    using Cfg = BwdCfg<LP, WARPS, TILE_W>;
+    using Cfg = BwdCfg<LP, WARPS, TILE_W, QPW>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ LevelTable lt;
 
@@ -83,7 +85,7 @@ msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict_
         const int g = (int)(rest % lt.groups);
         const long long n = rest / lt.groups;
         int q0, cnt;
-        warp_queries(lt, d.L, g, warp, Cfg::kGroup, Cfg::kTileH, TILE_W, d.Lq, q0, cnt);
+        warp_queries(lt, d.L, g, warp, Cfg::kGroup, Cfg::kTileH, TILE_W, d.Lq, Cfg::kQPW, q0, cnt);
 
         // ---- phase 1: records (one plane per corner) + per-point coefficients ----
         float2 xy[Cfg::kRounds];
@@ -216,13 +218,13 @@ msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict_
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
-template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int BATCH>
+template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int BATCH, int QPW>
 static cudaError_t launch_bwd_cfg(const float *grad_out, const float *value, const int64_t *shapes,
                                   const int64_t *lstart, const float *loc, const float *attw,
                                   const Dims &d, float *grad_value, float *grad_loc,
                                   float *grad_attw, cudaStream_t stream) {
-    using Cfg = BwdCfg<LP, WARPS, TILE_W>;
-    auto kern = msda_bwd_d32_kernel<LP, WARPS, TILE_W, MIN_CTAS, BATCH>;
+    using Cfg = BwdCfg<LP, WARPS, TILE_W, QPW>;
+    auto kern = msda_bwd_d32_kernel<LP, WARPS, TILE_W, MIN_CTAS, BATCH, QPW>;
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -252,18 +254,20 @@ template <int LP>
 static cudaError_t launch_bwd_lp(const float *grad_out, const float *value, const int64_t *shapes,
                                  const int64_t *lstart, const float *loc, const float *attw,
                                  const Dims &d, float *gv, float *gl, float *gw, cudaStream_t st) {
-    // variant = (warps, query tile w, min CTAs per SM -> register budget, load batch in pairs)
-#define MSDA_BWD(W, TW, C, B) \
-    launch_bwd_cfg<LP, W, TW, C, B>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, st)
+    // variant = (warps, query tile width, min CTAs per SM -> register budget, load batch in pairs,
+    //            queries per warp)
+#define MSDA_BWD(W, TW, C, B, Q) \
+    launch_bwd_cfg<LP, W, TW, C, B, Q>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, st)
     switch (option_value(OPT_BWD_VARIANT)) {
-        case 1: return MSDA_BWD(8, 8, 4, 1);     //  8 warps, tile  8x8,  64 regs
-        case 3: return MSDA_BWD(32, 16, 1, 1);   // 32 warps, tile 16x16, 64 regs, one CTA per SM
-        case 4: return MSDA_BWD(16, 16, 2, 2);   // 16 warps, tile  8x16, 64 regs, 4 loads in flight (spills)
-        case 5: return MSDA_BWD(16, 16, 1, 3);   // 16 warps, tile  8x16, 128 regs, 6 loads in flight
-        case 6: return MSDA_BWD(8, 8, 2, 6);     //  8 warps, tile  8x8, 114 regs, 12 loads in flight
-        case 7: return MSDA_BWD(4, 8, 5, 3);     //  4 warps, tile  4x8,  96 regs
+        case 1: return MSDA_BWD(8, 8, 4, 1, 8);     //  8 warps, tile  8x8
+        case 3: return MSDA_BWD(32, 16, 1, 1, 8);   // 32 warps, tile 16x16, one CTA per SM
+        case 4: return MSDA_BWD(16, 16, 2, 2, 8);   // 16 warps, 4 loads in flight (spills at 64 regs)
+        case 5: return MSDA_BWD(16, 16, 2, 1, 4);   // 16 warps, tile  4x16, 4 queries per warp (76 KB smem per SM)
+        case 6: return MSDA_BWD(8, 8, 2, 6, 8);     //  8 warps, 114 regs, 12 loads in flight
+        case 7: return MSDA_BWD(16, 8, 2, 1, 4);    // 16 warps, tile  8x8,  4 queries per warp
+        case 8: return MSDA_BWD(32, 16, 1, 1, 4);   // 32 warps, tile  8x16, 4 queries per warp, one CTA per SM
         case 2:
-        default: return MSDA_BWD(16, 16, 2, 1);  // 16 warps, tile  8x16, 64 regs, 2 loads in flight
+        default: return MSDA_BWD(16, 16, 2, 1, 8);  // 16 warps, tile  8x16, 8 queries per warp (147 KB smem per SM)
     }
 #undef MSDA_BWD
 }

@@ -118,25 +118,25 @@ __device__ __forceinline__ void fill_level_table(LevelTable &lt, const int64_t *
         lt.level_of[s] = (unsigned char)(s / P);
 }
 
-// First query and number of consecutive queries (0..8) handled by `warp` in
-// query group `g` of an (image, head).
+// First query and number of consecutive queries (0..qpw) handled by `warp` in
+// query group `g` of an (image, head); qpw = queries per warp per item.
 __device__ __forceinline__ void warp_queries(const LevelTable &lt, int L, int g, int warp,
-                                             int group, int tile_h, int tile_w, int Lq,
+                                             int group, int tile_h, int tile_w, int Lq, int qpw,
                                              int &q0, int &cnt) {
     if (lt.spatial) {
         int l = 0;
         while (l + 1 < L && g >= lt.tile_begin[l + 1]) ++l;
         const int t = g - lt.tile_begin[l];
         const int ty = t / lt.tiles_x[l], tx = t - ty * lt.tiles_x[l];
-        const int per_row = tile_w >> 3;
+        const int per_row = tile_w / qpw;
         const int y = ty * tile_h + warp / per_row;
-        const int x = tx * tile_w + (warp % per_row) * 8;
+        const int x = tx * tile_w + (warp % per_row) * qpw;
         const int W = lt.W[l];
-        cnt = (y < lt.H[l]) ? min(max(W - x, 0), 8) : 0;
+        cnt = (y < lt.H[l]) ? min(max(W - x, 0), qpw) : 0;
         q0 = lt.start[l] + y * W + x;
     } else {
-        q0 = g * group + warp * 8;
-        cnt = min(max(Lq - q0, 0), 8);
+        q0 = g * group + warp * qpw;
+        cnt = min(max(Lq - q0, 0), qpw);
     }
 }
 
@@ -216,10 +216,13 @@ __device__ __forceinline__ uint4 lds_u4(const uint4 *p) {
 // ---------------------------------------------------------------------------
 // cache-hinted global accesses
 // ---------------------------------------------------------------------------
-// value rows are re-used by neighbouring queries: keep them in L1 (default .ca)
+// value rows are re-used by neighbouring queries: keep them in L1
+#ifndef MSDA_VALUE_LD
+#define MSDA_VALUE_LD "ld.global.nc.v4.f32"   /* L1::evict_last measured: no change */
+#endif
 __device__ __forceinline__ float4 ldg_keep_f4(const float4 *p) {
     float4 r;
-    asm("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
+    asm(MSDA_VALUE_LD " {%0,%1,%2,%3}, [%4];"
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
 }
@@ -275,7 +278,7 @@ __device__ __forceinline__ float4 ldg_keep_f4_if(const float4 *base, uint32_t of
     asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0xffffffff;\n\t"
         "mov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\tmov.f32 %2, 0f00000000;\n\t"
         "mov.f32 %3, 0f00000000;\n\t"
-        "@p ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];\n\t}"
+        "@p " MSDA_VALUE_LD " {%0,%1,%2,%3}, [%4];\n\t}"
         : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
         : "l"(p), "r"(off16));
     return r;

@@ -29,28 +29,30 @@
 
 namespace msda {
 
-template <int LP, int WARPS, int TILE_W>
+// QPW = queries per warp per item: their records are resident in shared memory together, so
+// a smaller QPW leaves more of the SM's 228 KB to L1 (the value rows)
+template <int LP, int WARPS, int TILE_W, int QPW>
 struct FwdCfg {
     static_assert(LP % 2 == 0, "points are consumed in pairs");
-    static constexpr int kQPW = 8;                        // queries per warp per item
+    static constexpr int kQPW = QPW;
     static constexpr int kGroup = WARPS * kQPW;           // queries per item
     static constexpr int kTileH = kGroup / TILE_W;
     static constexpr int kRounds = (kQPW * LP + 31) / 32; // phase-1 rounds
-    static constexpr int kRecPerWarp = kRounds * 32;      // records per corner plane
+    static constexpr int kRecPerWarp = kQPW * LP;         // records per corner plane
     // plane stride in records: +2 (16 bytes) so the four corner planes start 4 banks apart and the
     // 4-address LDS.128 of phase 2 is conflict-free (an unpadded stride is a multiple of 128 bytes)
     static constexpr int kPlane = kRecPerWarp + 2;
     static constexpr size_t kSmem = (size_t)WARPS * 4 * kPlane * sizeof(uint2);
-    static_assert(TILE_W % 8 == 0 && kGroup % TILE_W == 0, "tile shape");
+    static_assert(TILE_W % QPW == 0 && kGroup % TILE_W == 0, "tile shape");
 };
 
-template <int LP, int WARPS, int TILE_W, int MIN_CTAS>
+template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int QPW>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
 msda_fwd_d32_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes,
                     const int64_t *__restrict__ lstart, const float *__restrict__ loc,
                     const float *__restrict__ attw, const Dims d, const int want_spatial,
                     float *__restrict__ out) {
-    using Cfg = FwdCfg<LP, WARPS, TILE_W>;
+    using Cfg = FwdCfg<LP, WARPS, TILE_W, QPW>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ LevelTable lt;
 
@@ -73,7 +75,7 @@ msda_fwd_d32_kernel(const float *__restrict__ value, const int64_t *__restrict__
         const int g = (int)(rest % lt.groups);
         const long long n = rest / lt.groups;
         int q0, cnt;
-        warp_queries(lt, d.L, g, warp, Cfg::kGroup, Cfg::kTileH, TILE_W, d.Lq, q0, cnt);
+        warp_queries(lt, d.L, g, warp, Cfg::kGroup, Cfg::kTileH, TILE_W, d.Lq, Cfg::kQPW, q0, cnt);
 
         // ---- phase 1: one sampling point per lane per round -> records ----
         // all global loads of the item are issued before any of them is consumed
@@ -153,12 +155,12 @@ msda_fwd_d32_kernel(const float *__restrict__ value, const int64_t *__restrict__
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
-template <int LP, int WARPS, int TILE_W, int MIN_CTAS>
+template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int QPW>
 static cudaError_t launch_fwd_cfg(const float *value, const int64_t *shapes, const int64_t *lstart,
                                   const float *loc, const float *attw, const Dims &d,
                                   float *out, cudaStream_t stream) {
-    using Cfg = FwdCfg<LP, WARPS, TILE_W>;
-    auto kern = msda_fwd_d32_kernel<LP, WARPS, TILE_W, MIN_CTAS>;
+    using Cfg = FwdCfg<LP, WARPS, TILE_W, QPW>;
+    auto kern = msda_fwd_d32_kernel<LP, WARPS, TILE_W, MIN_CTAS, QPW>;
     static int ctas_per_sm = 0;   // immutable after first use
     if (ctas_per_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -188,15 +190,20 @@ template <int LP>
 static cudaError_t launch_fwd_lp(const float *value, const int64_t *shapes, const int64_t *lstart,
                                  const float *loc, const float *attw, const Dims &d, float *out,
                                  cudaStream_t stream) {
-    // variant = CTA shape: (warps, query tile h x w, min CTAs per SM for the register budget)
+    // variant = (warps, query tile width, min CTAs per SM -> register budget, queries per warp)
+#define MSDA_FWD(W, TW, C, Q) launch_fwd_cfg<LP, W, TW, C, Q>(value, shapes, lstart, loc, attw, d, out, stream)
     switch (option_value(OPT_FWD_VARIANT)) {
-        case 1: return launch_fwd_cfg<LP, 8, 8, 4>(value, shapes, lstart, loc, attw, d, out, stream);     // 8x8
-        case 3: return launch_fwd_cfg<LP, 32, 16, 1>(value, shapes, lstart, loc, attw, d, out, stream);   // 16x16
-        case 4: return launch_fwd_cfg<LP, 16, 8, 2>(value, shapes, lstart, loc, attw, d, out, stream);    // 16x8
-        case 5: return launch_fwd_cfg<LP, 8, 16, 4>(value, shapes, lstart, loc, attw, d, out, stream);    // 4x16
+        case 1: return MSDA_FWD(8, 8, 4, 8);     //  8 warps, tile  8x8
+        case 3: return MSDA_FWD(32, 16, 1, 8);   // 32 warps, tile 16x16, one CTA per SM
+        case 4: return MSDA_FWD(16, 8, 2, 8);    // 16 warps, tile 16x8
+        case 5: return MSDA_FWD(16, 16, 2, 4);   // 16 warps, tile  4x16, 4 queries per warp (50 KB smem per SM)
+        case 6: return MSDA_FWD(16, 8, 2, 4);    // 16 warps, tile  8x8,  4 queries per warp
+        case 7: return MSDA_FWD(32, 16, 1, 4);   // 32 warps, tile  8x16, 4 queries per warp, one CTA per SM
+        case 8: return MSDA_FWD(16, 16, 3, 4);   // 16 warps, tile  4x16, 48 warps per SM (40 regs)
         case 2:
-        default: return launch_fwd_cfg<LP, 16, 16, 2>(value, shapes, lstart, loc, attw, d, out, stream);  // 8x16
+        default: return MSDA_FWD(16, 16, 2, 8);  // 16 warps, tile  8x16, 8 queries per warp (98 KB smem per SM)
     }
+#undef MSDA_FWD
 }
 
 // `handled` tells the caller whether this specialised path took the problem
