@@ -404,10 +404,29 @@ def run_e2e(pkg, host, dev, world, steps, dist):
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        run_reference_arm(args)
-    else:
-        run_b200_arm(args)
+    # stdout carries exactly ONE JSON line: anything libraries print on fd 1 while the run is in
+    # progress (e.g. NCCL's version banner at communicator creation) is sent to stderr instead
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    line_holder = []
+    real_print = print
+
+    def capture(*a, **k):
+        line_holder.append(" ".join(str(x) for x in a))
+    globals()["print"] = capture
+    try:
+        if args.impl == "reference":
+            run_reference_arm(args)
+        else:
+            run_b200_arm(args)
+    finally:
+        globals()["print"] = real_print
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    for line in line_holder:
+        real_print(line, flush=True)
 
 
 if __name__ == "__main__":
