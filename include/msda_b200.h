@@ -101,6 +101,35 @@ int msda_b200_backward_f64(const double *grad_output, const double *value,
                            double *grad_attn_weight, void *stream);
 
 /*
+ * Fused producers: the same op with the three elementwise steps of its caller
+ * folded into the kernels -- ops/modules/ms_deform_attn.py:105-112:
+ *     attention_weights = softmax(attn_logits over num_levels*num_point)
+ *     sampling_loc      = reference_points[:, :, None, :, None, :] + sampling_offsets / (W_l, H_l)
+ *   reference_points  [batch or 1, num_query, num_levels, 2]; ref_batch_stride = elements between
+ *                     images (num_query*num_levels*2), or 0 when one set is shared by the batch
+ *   sampling_offsets  [batch, num_query, num_heads, num_levels, num_point, 2]  (raw Linear output)
+ *   attn_logits       [batch, num_query, num_heads, num_levels*num_point]      (raw Linear output)
+ * The backward returns the gradients with respect to sampling_offsets and attn_logits (softmax
+ * backward and the 1/(W,H) scaling folded in); reference_points get no gradient here.
+ * Only the 32-channel fp32 fast path exists (num_levels*num_point in {4,8,12,16});
+ * MSDA_ERR_UNSUPPORTED otherwise -- the caller then composes the unfused entry points.
+ */
+int msda_b200_fused_forward_f32(const float *value, const int64_t *spatial_shapes,
+                                const int64_t *level_start, const float *reference_points,
+                                long long ref_batch_stride, const float *sampling_offsets,
+                                const float *attn_logits, int batch, int spatial_size,
+                                int num_heads, int channels, int num_levels, int num_query,
+                                int num_point, float *output, void *stream);
+int msda_b200_fused_backward_f32(const float *grad_output, const float *value,
+                                 const int64_t *spatial_shapes, const int64_t *level_start,
+                                 const float *reference_points, long long ref_batch_stride,
+                                 const float *sampling_offsets, const float *attn_logits,
+                                 int batch, int spatial_size, int num_heads, int channels,
+                                 int num_levels, int num_query, int num_point, float *grad_value,
+                                 float *grad_sampling_offsets, float *grad_attn_logits,
+                                 void *stream);
+
+/*
  * Integer known-answer hook (no counterpart in the reference; it exposes the
  * integer work of cuh:43-58, 279-293 so tests can pin it bit-exactly).
  * For every (n, q, m, l, p), in sampling_loc order:

@@ -1,0 +1,123 @@
+"""GPU tests of the fused-producer kernels: softmax over the L*P logits and
+`ref + offset / (W, H)` inside the forward / backward kernels, against the unfused composition the
+reference module performs (ops/modules/ms_deform_attn.py:105-121) evaluated in fp64 with the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import FWD_ABS_TOL, GRAD_REL_TOL, load_golden, rel_err
+from test_modules import build_small
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def make_case(pkg, levels, batch, heads, points, shared_ref, seed):
+    gen = torch.Generator().manual_seed(seed)
+    L = len(levels)
+    S = sum(h * w for h, w in levels)
+    value = torch.randn(batch, S, heads, 32, generator=gen)
+    ref = pkg.modules.reference_points_for(levels, "cpu")                      # [1, S, L, 2]
+    if not shared_ref:
+        ref = (ref + (torch.rand(batch, S, L, 2, generator=gen) - 0.5) * 0.01).contiguous()
+    off = torch.randn(batch, S, heads, L, points, 2, generator=gen) * 2.0 + \
+        torch.rand(batch, S, heads, L, points, 2, generator=gen) - 0.5
+    logits = torch.randn(batch, S, heads, L * points, generator=gen) * 1.5
+    grad_out = torch.randn(batch, S, heads * 32, generator=gen)
+    shapes, lsi = pkg.synthetic.level_tensors(levels)
+    return dict(value=value, ref=ref.contiguous(), off=off, logits=logits, grad_out=grad_out,
+                shapes=shapes, lsi=lsi, levels=levels)
+
+
+def reference_composition(oracle, c):
+    """The reference module's arithmetic around the op (ms_deform_attn.py:105-112) on the CPU: the
+    location `ref + off / (W, H)` in fp32 exactly as the module (and the fused kernel) computes it --
+    a 1-ulp difference in a location can move a point into another bilinear cell, where the location
+    gradient is discontinuous -- the softmax in fp64, the op in the fp64 oracle with fp32 geometry,
+    and the chain rule back to offsets / logits through torch autograd."""
+    L = len(c["levels"])
+    N, S, M = c["off"].shape[:3]
+    P = c["off"].shape[4]
+    off = c["off"].clone().requires_grad_(True)
+    logits = c["logits"].double().requires_grad_(True)
+    w = torch.softmax(logits, -1).view(N, S, M, L, P)
+    wh = c["shapes"].flip(-1).float()
+    loc = c["ref"][:, :, None, :, None, :] + off / wh[None, None, None, :, None, :]      # fp32, IEEE
+    a = (c["value"], c["shapes"], c["lsi"], loc.detach(), w.detach())
+    out = oracle.forward(*a, geometry=np.float32)
+    gv, gl, gw = oracle.backward(c["grad_out"], *a, geometry=np.float32)
+    (loc.double() * torch.from_numpy(gl)).sum().backward()
+    (w * torch.from_numpy(gw)).sum().backward()
+    return out, gv, off.grad.double().numpy(), logits.grad.numpy()
+
+
+@pytest.mark.parametrize("levels,batch,heads,points,shared_ref", [
+    ([(8, 16), (16, 32), (32, 64)], 2, 8, 4, True),      # pixel-decoder shape, L*P = 12
+    ([(12, 39), (24, 78)], 1, 4, 4, False),              # odd sizes, per-image reference points, L*P = 8
+    ([(7, 9), (5, 3), (4, 4), (2, 2)], 2, 2, 4, True),   # L*P = 16
+    ([(9, 13)], 3, 2, 4, True),                          # L*P = 4
+])
+def test_fused_matches_unfused_composition(pkg, oracle, levels, batch, heads, points, shared_ref):
+    c = make_case(pkg, levels, batch, heads, points, shared_ref, seed=21)
+    d = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in c.items()}
+    value = d["value"].clone().requires_grad_(True)
+    off = d["off"].clone().requires_grad_(True)
+    logits = d["logits"].clone().requires_grad_(True)
+    n0 = pkg.launch_count()
+    out = pkg.MSDeformAttnFusedFunction.apply(value, d["shapes"], d["lsi"], d["ref"], off, logits)
+    out.backward(d["grad_out"])
+    torch.cuda.synchronize()
+    assert pkg.launch_count() - n0 == 2
+    ref_out, ref_gv, ref_goff, ref_glog = reference_composition(oracle, c)
+    assert np.abs(out.detach().double().cpu().numpy() - ref_out).max() <= 2 * FWD_ABS_TOL
+    assert rel_err(value.grad.cpu().numpy(), ref_gv.reshape(value.shape)) <= GRAD_REL_TOL
+    assert rel_err(off.grad.cpu().numpy(), ref_goff) <= GRAD_REL_TOL
+    assert rel_err(logits.grad.cpu().numpy(), ref_glog) <= GRAD_REL_TOL
+
+    # and against the unfused kernels fed by torch's own fp32 softmax / location arithmetic
+    v2 = d["value"].clone().requires_grad_(True)
+    o2 = d["off"].clone().requires_grad_(True)
+    l2 = d["logits"].clone().requires_grad_(True)
+    L, P = len(levels), points
+    w = torch.softmax(l2, -1).view(*l2.shape[:3], L, P)
+    wh = d["shapes"].flip(-1).float()
+    loc = d["ref"][:, :, None, :, None, :] + o2 / wh[None, None, None, :, None, :]
+    out2 = pkg.MSDeformAttnFunction.apply(v2, d["shapes"], d["lsi"], loc.contiguous(), w.contiguous(), 128)
+    out2.backward(d["grad_out"])
+    assert (out - out2).abs().max().item() <= 2e-5
+    assert rel_err(value.grad.cpu().numpy(), v2.grad.cpu().numpy()) <= 1e-5
+    assert rel_err(logits.grad.cpu().numpy(), l2.grad.cpu().numpy()) <= 1e-4
+    assert rel_err(off.grad.cpu().numpy(), o2.grad.cpu().numpy()) <= 1e-4
+
+
+def test_fused_encoder_matches_reference_golden(pkg):
+    """Reference encoder (fp64, build container) vs mirror with fused=True on the sm_100a kernels."""
+    m, g = build_small(pkg, dtype=torch.float32, device=DEV)
+    for layer in m.encoder.layers:
+        layer.self_attn.fused = True
+    srcs = [torch.from_numpy(g[f"src{i}"]).float().cuda() for i in range(3)]
+    srcs[2].requires_grad_(True)
+    pos = [torch.from_numpy(g[f"pos{i}"]).float().cuda() for i in range(3)]
+    n0 = pkg.launch_count()
+    memory = m(srcs, pos)[0]
+    assert np.abs(memory.detach().double().cpu().numpy() - g["memory"]).max() <= 2e-4
+    (memory * torch.from_numpy(g["cotangent"]).float().cuda()).sum().backward()
+    assert pkg.launch_count() - n0 == 4           # 2 layers x (fused forward + fused backward)
+    ref = g["grad_src2"]
+    assert np.abs(srcs[2].grad.double().cpu().numpy() - ref).max() <= 2e-4 * max(1.0, np.abs(ref).max())
+
+
+def test_fused_rejects_unsupported_shapes_and_module_falls_back(pkg):
+    c = make_case(pkg, [(6, 7), (3, 4)], 1, 2, 3, True, seed=3)          # L*P = 6: no fused kernel
+    d = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in c.items()}
+    with pytest.raises(RuntimeError, match="fused MSDA covers"):
+        pkg.ms_deform_attn_fused_forward(d["value"], d["shapes"], d["lsi"], d["ref"], d["off"], d["logits"])
+    attn = pkg.modules.MSDeformAttn(64, 2, 2, 3, fused=True).to(DEV)         # same shape through the module
+    q = torch.randn(1, 54, 64, device=DEV)
+    ref = pkg.modules.reference_points_for([(6, 7), (3, 4)], DEV)
+    attn_unfused = pkg.modules.MSDeformAttn(64, 2, 2, 3).to(DEV)
+    attn_unfused.load_state_dict(attn.state_dict())
+    with torch.no_grad():
+        a = attn(q, ref, q, d["shapes"], d["lsi"])
+        b = attn_unfused(q, ref, q, d["shapes"], d["lsi"])
+    assert torch.equal(a, b)

@@ -18,6 +18,12 @@ cudaError_t launch_fwd_d32(const float *, const int64_t *, const int64_t *, cons
 cudaError_t launch_bwd_d32(const float *, const float *, const int64_t *, const int64_t *,
                            const float *, const float *, const Dims &, float *, float *, float *,
                            cudaStream_t, bool *handled);
+cudaError_t launch_fwd_d32_fused(const float *, const int64_t *, const int64_t *, const float *,
+                                 long long, const float *, const float *, const Dims &, float *,
+                                 cudaStream_t, bool *handled);
+cudaError_t launch_bwd_d32_fused(const float *, const float *, const int64_t *, const int64_t *,
+                                 const float *, long long, const float *, const float *,
+                                 const Dims &, float *, float *, float *, cudaStream_t, bool *handled);
 template <typename T>
 cudaError_t launch_fwd_generic(const T *, const int64_t *, const int64_t *, const T *, const T *,
                                const Dims &, T *, cudaStream_t);
@@ -75,7 +81,7 @@ const char *msda_b200_error_string(int code) {
         case MSDA_OK: return "success";
         case MSDA_ERR_NULL_POINTER: return "msda_b200: a required pointer is NULL";
         case MSDA_ERR_BAD_SHAPE: return "msda_b200: a tensor size is zero or negative";
-        case MSDA_ERR_UNSUPPORTED: return "msda_b200: unsupported configuration (num_levels > 16)";
+        case MSDA_ERR_UNSUPPORTED: return "msda_b200: unsupported configuration (num_levels > 16, or a shape the fused path does not cover)";
         case MSDA_ERR_BAD_OPTION: return "msda_b200: unknown option name or value out of range";
         default: break;
     }
@@ -171,6 +177,50 @@ int msda_b200_backward_f64(const double *grad_output, const double *value,
     return (int)launch_bwd_generic<double>(grad_output, value, spatial_shapes, level_start,
                                            sampling_loc, attn_weight, d, grad_value,
                                            grad_sampling_loc, grad_attn_weight, (cudaStream_t)stream);
+}
+
+int msda_b200_fused_forward_f32(const float *value, const int64_t *spatial_shapes,
+                                const int64_t *level_start, const float *reference_points,
+                                long long ref_batch_stride, const float *sampling_offsets,
+                                const float *attn_logits, int batch, int spatial_size, int num_heads,
+                                int channels, int num_levels, int num_query, int num_point,
+                                float *output, void *stream) {
+    if (!value || !spatial_shapes || !level_start || !reference_points || !sampling_offsets ||
+        !attn_logits || !output)
+        return MSDA_ERR_NULL_POINTER;
+    const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+    if (int rc = check_dims(d)) return rc;
+    if (ref_batch_stride != 0 && ref_batch_stride != (long long)num_query * num_levels * 2)
+        return MSDA_ERR_BAD_SHAPE;
+    bool handled = false;
+    cudaError_t e = launch_fwd_d32_fused(value, spatial_shapes, level_start, reference_points,
+                                         ref_batch_stride, sampling_offsets, attn_logits, d, output,
+                                         (cudaStream_t)stream, &handled);
+    if (e == cudaSuccess && !handled) return MSDA_ERR_UNSUPPORTED;
+    return (int)e;
+}
+
+int msda_b200_fused_backward_f32(const float *grad_output, const float *value,
+                                 const int64_t *spatial_shapes, const int64_t *level_start,
+                                 const float *reference_points, long long ref_batch_stride,
+                                 const float *sampling_offsets, const float *attn_logits, int batch,
+                                 int spatial_size, int num_heads, int channels, int num_levels,
+                                 int num_query, int num_point, float *grad_value,
+                                 float *grad_sampling_offsets, float *grad_attn_logits, void *stream) {
+    if (!grad_output || !value || !spatial_shapes || !level_start || !reference_points ||
+        !sampling_offsets || !attn_logits || !grad_value || !grad_sampling_offsets || !grad_attn_logits)
+        return MSDA_ERR_NULL_POINTER;
+    const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+    if (int rc = check_dims(d)) return rc;
+    if (ref_batch_stride != 0 && ref_batch_stride != (long long)num_query * num_levels * 2)
+        return MSDA_ERR_BAD_SHAPE;
+    bool handled = false;
+    cudaError_t e = launch_bwd_d32_fused(grad_output, value, spatial_shapes, level_start,
+                                         reference_points, ref_batch_stride, sampling_offsets,
+                                         attn_logits, d, grad_value, grad_sampling_offsets,
+                                         grad_attn_logits, (cudaStream_t)stream, &handled);
+    if (e == cudaSuccess && !handled) return MSDA_ERR_UNSUPPORTED;
+    return (int)e;
 }
 
 int msda_b200_debug_indices_f32(const int64_t *spatial_shapes, const int64_t *level_start,

@@ -50,13 +50,17 @@ struct BwdCfg {
 };
 
 // BATCH = record pairs whose 2*BATCH value loads are in flight together (register budget)
-template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int BATCH, int QPW>
+// FUSED: `loc` / `attw` are the raw sampling offsets / attention logits and `grad_loc` / `grad_attw`
+// receive the gradients with respect to THEM (offset gradient = location gradient / (W, H);
+// softmax backward folded in), see phase1_records() in msda_common.cuh.
+template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int BATCH, int QPW, bool FUSED>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
 msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict__ value,
                     const int64_t *__restrict__ shapes, const int64_t *__restrict__ lstart,
-                    const float *__restrict__ loc, const float *__restrict__ attw, const Dims d,
-                    const int want_spatial, float *__restrict__ grad_value,
-                    float *__restrict__ grad_loc, float *__restrict__ grad_attw) {
+                    const float *__restrict__ loc, const float *__restrict__ attw,
+                    const Producers pr, const Dims d, const int want_spatial,
+                    float *__restrict__ grad_value, float *__restrict__ grad_loc,
+                    float *__restrict__ grad_attw) {
     using Cfg = BwdCfg<LP, WARPS, TILE_W, QPW>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ LevelTable lt;
@@ -88,40 +92,8 @@ msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict_
         warp_queries(lt, d.L, g, warp, Cfg::kGroup, Cfg::kTileH, TILE_W, d.Lq, Cfg::kQPW, q0, cnt);
 
         // ---- phase 1: records (one plane per corner) + per-point coefficients ----
-        float2 xy[Cfg::kRounds];
-        float aw[Cfg::kRounds];
-#pragma unroll
-        for (int r = 0; r < Cfg::kRounds; ++r) {
-            const int s = r * 32 + lane;
-            const int qi = s / LP, sp = s - qi * LP;
-            xy[r] = make_float2(0.f, 0.f);
-            aw[r] = 0.f;
-            if (qi < cnt) {
-                const long long row = ((n * d.Lq + q0 + qi) * M + m) * (long long)LP + sp;
-                xy[r] = ldg_stream_f2(reinterpret_cast<const float2 *>(loc) + row);
-                aw[r] = ldg_stream_f1(attw + row);
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < Cfg::kRounds; ++r) {
-            const int s = r * 32 + lane;
-            const int qi = s / LP, sp = s - qi * LP;
-            if (qi < cnt) {
-                const int4 lv = lt.hws[lt.level_of[sp]];     // {H, W, start, -}
-                const Geom<float> gm = decompose(xy[r].x, xy[r].y, lv.x, lv.y);
-                uint4 lo, hi;
-                make_record<false>(gm, aw[r], (uint32_t)lv.z, (uint32_t)lv.y, pix_stride,
-                                   (uint32_t)m * 8u, lo, hi);
-                rec[0 * Cfg::kPlane + s] = make_uint2(lo.x, lo.y);
-                rec[1 * Cfg::kPlane + s] = make_uint2(lo.z, lo.w);
-                rec[2 * Cfg::kPlane + s] = make_uint2(hi.x, hi.y);
-                rec[3 * Cfg::kPlane + s] = make_uint2(hi.z, hi.w);
-                // invalid point: every D_k is 0 (no corner is read), so any finite
-                // coefficients give the reference's zero gradients (cuh:370-372)
-                aux[s] = gm.valid ? make_float4(gm.lh, gm.lw, aw[r] * (float)lv.y, aw[r] * (float)lv.x)
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
+        phase1_records<FUSED, LP, Cfg::kQPW, Cfg::kPlane, true>(lt, rec, aux, loc, attw, pr, n, q0, cnt, m, M,
+                                                                d.Lq, d.L, pix_stride, lane);
         __syncwarp();
 
         // ---- phase 2 ----
@@ -170,6 +142,7 @@ msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict_
             rs_step<Cfg::kN2>(r2, r3, b0, 1);
             // coefficient of D_corner in (d/dx, d/dy, d/dweight) of each finalised point
             float t0[Cfg::kT0];
+            float prob[Cfg::kN3], lvW[Cfg::kN3], lvH[Cfg::kN3];   // of the points this lane finalises
 #pragma unroll
             for (int j = 0; j < Cfg::kN3; ++j) {
                 const int i2 = j + (b0 ? Cfg::kN3 : 0);          // index before step 3
@@ -177,14 +150,21 @@ msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict_
                 const int sp = i1 + (b2 ? Cfg::kN1 : 0);         // index before step 1 = point
                 const bool live = (i2 < Cfg::kN2) && (i1 < Cfg::kN1) && (sp < LP);
                 float cx = 0.f, cy = 0.f, ca = 0.f;
+                prob[j] = 0.f;
+                lvW[j] = 1.f;
+                lvH[j] = 1.f;
                 if (live) {
-                    const float4 a = aux[qi * LP + sp];
+                    const float4 a = aux[qi * LP + sp];          // {lh, lw, attention weight, level}
+                    const int4 lv = lt.hws[__float_as_int(a.w)];
                     const float lh = a.x, lw = a.y, hh = 1.f - a.x, hw = 1.f - a.y;
                     const float fh = c1 ? lh : hh;               // factor along h of this corner's weight
                     const float fw = c0 ? lw : hw;               // factor along w
+                    prob[j] = a.z;
+                    lvW[j] = (float)lv.y;
+                    lvH[j] = (float)lv.x;
                     ca = fh * fw;                                // d val / d weight part (cuh:161)
-                    cx = (c0 ? fh : -fh) * a.z;                  // W * aw * d w_k / d w  (cuh:128-156,162)
-                    cy = (c1 ? fw : -fw) * a.w;                  // H * aw * d w_k / d h  (cuh:128-156,163)
+                    cx = (c0 ? fh : -fh) * (a.z * lvW[j]);       // W * aw * d w_k / d w  (cuh:128-156,162)
+                    cy = (c1 ? fw : -fw) * (a.z * lvH[j]);       // H * aw * d w_k / d h  (cuh:128-156,163)
                 }
                 t0[3 * j + 0] = cx * r3[j];
                 t0[3 * j + 1] = cy * r3[j];
@@ -194,6 +174,19 @@ msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict_
             float t1[Cfg::kT1], t2[Cfg::kT2];
             rs_step<Cfg::kT0>(t0, t1, c1, 16);
             rs_step<Cfg::kT1>(t1, t2, c0, 8);
+            // softmax backward (FUSED): grad_logit_i = a_i * (ga_i - sum_j a_j * ga_j)  (torch's
+            // softmax_backward: (grad - sum(grad * out)) * out); the ga_j sit on different lanes
+            float dot_a = 0.f;
+            if (FUSED) {
+#pragma unroll
+                for (int i = 0; i < Cfg::kT2; ++i) {
+                    const int u1 = i + (c0 ? Cfg::kT2 : 0);
+                    const int u0 = u1 + (c1 ? Cfg::kT1 : 0);
+                    if (u1 < Cfg::kT1 && u0 < Cfg::kT0 && (u0 % 3) == 2) dot_a += prob[u0 / 3] * t2[i];
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) dot_a += __shfl_xor_sync(kFullMask, dot_a, o);
+            }
 #pragma unroll
             for (int i = 0; i < Cfg::kT2; ++i) {
                 const int u1 = i + (c0 ? Cfg::kT2 : 0);
@@ -205,8 +198,13 @@ msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict_
                     const int sp = i1 + (b2 ? Cfg::kN1 : 0);
                     if (i2 < Cfg::kN2 && i1 < Cfg::kN1 && sp < LP) {
                         const long long sidx = qrow * LP + sp;
-                        if (comp == 2) stg_stream_f1(grad_attw + sidx, t2[i]);
-                        else stg_stream_f1(grad_loc + 2 * sidx + comp, t2[i]);
+                        float v = t2[i];
+                        if (FUSED) {
+                            // d loc / d offset = 1 / (W, H)  (mod.py:110-112)
+                            v = comp == 2 ? prob[j] * (v - dot_a) : __fdiv_rn(v, comp == 0 ? lvW[j] : lvH[j]);
+                        }
+                        if (comp == 2) stg_stream_f1(grad_attw + sidx, v);
+                        else stg_stream_f1(grad_loc + 2 * sidx + comp, v);
                     }
                 }
             }
@@ -218,13 +216,14 @@ msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict_
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
-template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int BATCH, int QPW>
+template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int BATCH, int QPW, bool FUSED = false>
 static cudaError_t launch_bwd_cfg(const float *grad_out, const float *value, const int64_t *shapes,
                                   const int64_t *lstart, const float *loc, const float *attw,
                                   const Dims &d, float *grad_value, float *grad_loc,
-                                  float *grad_attw, cudaStream_t stream) {
+                                  float *grad_attw, cudaStream_t stream,
+                                  Producers pr = Producers{nullptr, 0}) {
     using Cfg = BwdCfg<LP, WARPS, TILE_W, QPW>;
-    auto kern = msda_bwd_d32_kernel<LP, WARPS, TILE_W, MIN_CTAS, BATCH, QPW>;
+    auto kern = msda_bwd_d32_kernel<LP, WARPS, TILE_W, MIN_CTAS, BATCH, QPW, FUSED>;
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -244,7 +243,7 @@ static cudaError_t launch_bwd_cfg(const float *grad_out, const float *value, con
     if (blocks < 1) blocks = 1;
     const int want_spatial = option_value(OPT_TILE_ORDER) != 1;
     kern<<<(unsigned)blocks, WARPS * 32, Cfg::kSmem, stream>>>(grad_out, value, shapes, lstart, loc,
-                                                              attw, d, want_spatial, grad_value,
+                                                              attw, pr, d, want_spatial, grad_value,
                                                               grad_loc, grad_attw);
     note_launch();
     return cudaGetLastError();
@@ -288,6 +287,29 @@ cudaError_t launch_bwd_d32(const float *grad_out, const float *value, const int6
         case 16: return launch_bwd_lp<16>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, stream);
         default: *handled = false; return cudaSuccess;
     }
+}
+
+// Fused producers: gradients w.r.t. the raw sampling offsets and attention logits.
+cudaError_t launch_bwd_d32_fused(const float *grad_out, const float *value, const int64_t *shapes,
+                                 const int64_t *lstart, const float *ref, long long ref_bstride,
+                                 const float *off, const float *logits, const Dims &d, float *gv,
+                                 float *g_off, float *g_logits, cudaStream_t st, bool *handled) {
+    *handled = true;
+    const Producers pr{ref, ref_bstride};
+    if (d.D != 32 || (long long)d.S * d.M * 8 >= 0x7fffffffLL) {
+        *handled = false;
+        return cudaSuccess;
+    }
+#define MSDA_BWD_FUSED(LPV) \
+    launch_bwd_cfg<LPV, 16, 16, 2, 1, 8, true>(grad_out, value, shapes, lstart, off, logits, d, gv, g_off, g_logits, st, pr)
+    switch (d.L * d.P) {
+        case 4: return MSDA_BWD_FUSED(4);
+        case 8: return MSDA_BWD_FUSED(8);
+        case 12: return MSDA_BWD_FUSED(12);
+        case 16: return MSDA_BWD_FUSED(16);
+        default: *handled = false; return cudaSuccess;
+    }
+#undef MSDA_BWD_FUSED
 }
 
 }  // namespace msda

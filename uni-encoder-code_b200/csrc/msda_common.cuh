@@ -313,6 +313,100 @@ __device__ __forceinline__ void rs_step(const float (&in)[N], float (&out)[(N + 
 }
 
 // ---------------------------------------------------------------------------
+// Phase 1 of the 32-channel kernels: the QPW*LP sampling points of a warp's queries are spread
+// over the lanes (one point per lane per round); each lane produces its point's four corner
+// records (one shared-memory plane per corner) and, for the backward kernel, the per-point
+// coefficients {lh, lw, attention weight, level}.
+//
+// FUSED == false: (x, y) and the attention weight are read from sampling_locations /
+//                 attention_weights, as in the reference op.
+// FUSED == true : the producers of ops/modules/ms_deform_attn.py:105-112 are folded in:
+//                 `loc`  = raw sampling_offsets  [N, Lq, M, L, P, 2]   (Linear output)
+//                 `attw` = raw attention logits  [N, Lq, M, L*P]       (Linear output)
+//                 `ref`  = reference points      [N or 1, Lq, L, 2]
+//                 location = ref + offset / (W_l, H_l)  (IEEE division, then add: the same two
+//                 roundings as the reference's tensor expression) and the weight is the softmax
+//                 of the query-head's L*P logits (each lane re-reduces its row's logits).
+// ---------------------------------------------------------------------------
+struct Producers {
+    const float *ref;          // FUSED only
+    long long ref_bstride;     // elements between images in `ref` (0: shared by the batch)
+};
+
+template <bool FUSED, int LP, int QPW, int PLANE, bool WITH_AUX>
+__device__ __forceinline__ void phase1_records(const LevelTable &lt, uint2 *rec, float4 *aux,
+                                               const float *__restrict__ loc,
+                                               const float *__restrict__ attw, const Producers pr,
+                                               long long n, int q0, int cnt, int m, int M, int Lq,
+                                               int L, uint32_t pix_stride, int lane) {
+    constexpr int kRounds = (QPW * LP + 31) / 32;
+    float2 xy[kRounds];
+    float aw[kRounds];
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {          // all global loads first
+        const int s = r * 32 + lane;
+        const int qi = s / LP, sp = s - qi * LP;
+        xy[r] = make_float2(0.f, 0.f);
+        aw[r] = 0.f;
+        if (qi < cnt) {                           // also false for the padding lanes of the last round
+            const long long qrow = (n * Lq + q0 + qi) * M + m;
+            xy[r] = ldg_stream_f2(reinterpret_cast<const float2 *>(loc) + qrow * LP + sp);
+            if (!FUSED) {
+                aw[r] = ldg_stream_f1(attw + qrow * LP + sp);
+            } else {
+                // softmax over the row's LP logits; lanes of the same (query, head) read the same 16-byte words
+                const float4 *lg = reinterpret_cast<const float4 *>(attw + qrow * LP);
+                float4 v[LP / 4];
+#pragma unroll
+                for (int k = 0; k < LP / 4; ++k) v[k] = ldg_stream_f4(lg + k);
+                float mx = v[0].x;
+#pragma unroll
+                for (int k = 0; k < LP / 4; ++k) mx = fmaxf(fmaxf(fmaxf(mx, v[k].x), v[k].y), fmaxf(v[k].z, v[k].w));
+                float sum = 0.f, mine = 0.f;
+#pragma unroll
+                for (int k = 0; k < LP / 4; ++k) {
+                    const float e0 = expf(v[k].x - mx), e1 = expf(v[k].y - mx);
+                    const float e2 = expf(v[k].z - mx), e3 = expf(v[k].w - mx);
+                    sum += (e0 + e1) + (e2 + e3);
+                    mine = (sp == 4 * k) ? e0 : (sp == 4 * k + 1) ? e1 : (sp == 4 * k + 2) ? e2
+                         : (sp == 4 * k + 3) ? e3 : mine;
+                }
+                aw[r] = __fdiv_rn(mine, sum);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        const int s = r * 32 + lane;
+        const int qi = s / LP, sp = s - qi * LP;
+        if (qi < cnt) {
+            const int l = lt.level_of[sp];
+            const int4 lv = lt.hws[l];            // {H, W, start, -}
+            float x = xy[r].x, y = xy[r].y;
+            if (FUSED) {
+                const long long rrow = n * pr.ref_bstride + ((long long)(q0 + qi) * L + l) * 2;
+                const float2 rp = ldg_stream_f2(reinterpret_cast<const float2 *>(pr.ref + rrow));
+                x = rp.x + __fdiv_rn(x, (float)lv.y);          // mod.py:110-112: ref + off / (W, H)
+                y = rp.y + __fdiv_rn(y, (float)lv.x);
+            }
+            const Geom<float> gm = decompose(x, y, lv.x, lv.y);
+            uint4 lo, hi;   // {off0, w0, off1, w1}, {off2, w2, off3, w3}
+            make_record<false>(gm, aw[r], (uint32_t)lv.z, (uint32_t)lv.y, pix_stride, (uint32_t)m * 8u, lo, hi);
+            rec[0 * PLANE + s] = make_uint2(lo.x, lo.y);
+            rec[1 * PLANE + s] = make_uint2(lo.z, lo.w);
+            rec[2 * PLANE + s] = make_uint2(hi.x, hi.y);
+            rec[3 * PLANE + s] = make_uint2(hi.z, hi.w);
+            if (WITH_AUX) {
+                // invalid point: every D_k is 0 (no corner is read), so any finite lh / lw give the
+                // reference's zero location / weight gradients (cuh:370-372); its attention weight is
+                // kept because the fused softmax backward needs it (-a_i * sum_j a_j g_j)
+                aux[s] = make_float4(gm.valid ? gm.lh : 0.f, gm.valid ? gm.lw : 0.f, aw[r], __int_as_float(l));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // launch bookkeeping shared by the translation units
 // ---------------------------------------------------------------------------
 struct Dims {

@@ -46,12 +46,12 @@ struct FwdCfg {
     static_assert(TILE_W % QPW == 0 && kGroup % TILE_W == 0, "tile shape");
 };
 
-template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int QPW>
+template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int QPW, bool FUSED>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
 msda_fwd_d32_kernel(const float *__restrict__ value, const int64_t *__restrict__ shapes,
                     const int64_t *__restrict__ lstart, const float *__restrict__ loc,
-                    const float *__restrict__ attw, const Dims d, const int want_spatial,
-                    float *__restrict__ out) {
+                    const float *__restrict__ attw, const Producers pr, const Dims d,
+                    const int want_spatial, float *__restrict__ out) {
     using Cfg = FwdCfg<LP, WARPS, TILE_W, QPW>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ LevelTable lt;
@@ -78,37 +78,8 @@ msda_fwd_d32_kernel(const float *__restrict__ value, const int64_t *__restrict__
         warp_queries(lt, d.L, g, warp, Cfg::kGroup, Cfg::kTileH, TILE_W, d.Lq, Cfg::kQPW, q0, cnt);
 
         // ---- phase 1: one sampling point per lane per round -> records ----
-        // all global loads of the item are issued before any of them is consumed
-        float2 xy[Cfg::kRounds];
-        float aw[Cfg::kRounds];
-#pragma unroll
-        for (int r = 0; r < Cfg::kRounds; ++r) {
-            const int s = r * 32 + lane;
-            const int qi = s / LP, sp = s - qi * LP;
-            xy[r] = make_float2(0.f, 0.f);
-            aw[r] = 0.f;
-            if (qi < cnt) {
-                const long long row = ((n * d.Lq + q0 + qi) * M + m) * (long long)LP + sp;
-                xy[r] = ldg_stream_f2(reinterpret_cast<const float2 *>(loc) + row);
-                aw[r] = ldg_stream_f1(attw + row);
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < Cfg::kRounds; ++r) {
-            const int s = r * 32 + lane;
-            const int qi = s / LP, sp = s - qi * LP;
-            if (qi < cnt) {
-                const int4 lv = lt.hws[lt.level_of[sp]];     // {H, W, start, -}
-                const Geom<float> gm = decompose(xy[r].x, xy[r].y, lv.x, lv.y);
-                uint4 lo, hi;   // {off0, w0, off1, w1}, {off2, w2, off3, w3}
-                make_record<false>(gm, aw[r], (uint32_t)lv.z, (uint32_t)lv.y, pix_stride,
-                                   (uint32_t)m * 8u, lo, hi);
-                rec[0 * Cfg::kPlane + s] = make_uint2(lo.x, lo.y);
-                rec[1 * Cfg::kPlane + s] = make_uint2(lo.z, lo.w);
-                rec[2 * Cfg::kPlane + s] = make_uint2(hi.x, hi.y);
-                rec[3 * Cfg::kPlane + s] = make_uint2(hi.z, hi.w);
-            }
-        }
+        phase1_records<FUSED, LP, Cfg::kQPW, Cfg::kPlane, false>(lt, rec, nullptr, loc, attw, pr, n, q0, cnt, m,
+                                                                 M, d.Lq, d.L, pix_stride, lane);
         __syncwarp();
 
         // ---- phase 2: gather + weighted reduction, one query at a time ----
@@ -155,12 +126,12 @@ msda_fwd_d32_kernel(const float *__restrict__ value, const int64_t *__restrict__
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
-template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int QPW>
+template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int QPW, bool FUSED = false>
 static cudaError_t launch_fwd_cfg(const float *value, const int64_t *shapes, const int64_t *lstart,
                                   const float *loc, const float *attw, const Dims &d,
-                                  float *out, cudaStream_t stream) {
+                                  float *out, cudaStream_t stream, Producers pr = Producers{nullptr, 0}) {
     using Cfg = FwdCfg<LP, WARPS, TILE_W, QPW>;
-    auto kern = msda_fwd_d32_kernel<LP, WARPS, TILE_W, MIN_CTAS, QPW>;
+    auto kern = msda_fwd_d32_kernel<LP, WARPS, TILE_W, MIN_CTAS, QPW, FUSED>;
     static int ctas_per_sm = 0;   // immutable after first use
     if (ctas_per_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -180,7 +151,7 @@ static cudaError_t launch_fwd_cfg(const float *value, const int64_t *shapes, con
     if (blocks > items_ub) blocks = items_ub;
     if (blocks < 1) blocks = 1;
     const int want_spatial = option_value(OPT_TILE_ORDER) != 1;
-    kern<<<(unsigned)blocks, WARPS * 32, Cfg::kSmem, stream>>>(value, shapes, lstart, loc, attw, d,
+    kern<<<(unsigned)blocks, WARPS * 32, Cfg::kSmem, stream>>>(value, shapes, lstart, loc, attw, pr, d,
                                                               want_spatial, out);
     note_launch();
     return cudaGetLastError();
@@ -222,6 +193,27 @@ cudaError_t launch_fwd_d32(const float *value, const int64_t *shapes, const int6
         case 8: return launch_fwd_lp<8>(value, shapes, lstart, loc, attw, d, out, stream);
         case 12: return launch_fwd_lp<12>(value, shapes, lstart, loc, attw, d, out, stream);
         case 16: return launch_fwd_lp<16>(value, shapes, lstart, loc, attw, d, out, stream);
+        default: *handled = false; return cudaSuccess;
+    }
+}
+
+// Fused producers: `off` = raw sampling offsets, `logits` = raw attention logits,
+// `ref` = reference points [N or 1, Lq, L, 2].  Only the default CTA shape is instantiated.
+cudaError_t launch_fwd_d32_fused(const float *value, const int64_t *shapes, const int64_t *lstart,
+                                 const float *ref, long long ref_bstride, const float *off,
+                                 const float *logits, const Dims &d, float *out, cudaStream_t stream,
+                                 bool *handled) {
+    *handled = true;
+    const Producers pr{ref, ref_bstride};
+    if (d.D != 32 || (long long)d.S * d.M * 8 >= 0x7fffffffLL) {
+        *handled = false;
+        return cudaSuccess;
+    }
+    switch (d.L * d.P) {
+        case 4: return launch_fwd_cfg<4, 16, 16, 2, 8, true>(value, shapes, lstart, off, logits, d, out, stream, pr);
+        case 8: return launch_fwd_cfg<8, 16, 16, 2, 8, true>(value, shapes, lstart, off, logits, d, out, stream, pr);
+        case 12: return launch_fwd_cfg<12, 16, 16, 2, 8, true>(value, shapes, lstart, off, logits, d, out, stream, pr);
+        case 16: return launch_fwd_cfg<16, 16, 16, 2, 8, true>(value, shapes, lstart, off, logits, d, out, stream, pr);
         default: *handled = false; return cudaSuccess;
     }
 }

@@ -32,3 +32,28 @@ class MSDeformAttnFunction(Function):
         grad_value, grad_loc, grad_w = ops.ms_deform_attn_backward(
             value, shapes, lsi, loc, w, grad_output, ctx.im2col_step)
         return grad_value, None, None, grad_loc, grad_w, None
+
+
+class MSDeformAttnFusedFunction(Function):
+    """``apply(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
+    attn_logits)`` -- the op with its caller's softmax and location arithmetic
+    (ops/modules/ms_deform_attn.py:105-112) inside the kernels.  Gradients flow to value,
+    sampling_offsets and attn_logits; reference_points are treated as constants (they are in the
+    encoder, msdeformattn.py:152-166)."""
+
+    @staticmethod
+    def forward(ctx, value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
+                attn_logits):
+        output = ops.ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index,
+                                                  reference_points, sampling_offsets, attn_logits)
+        ctx.save_for_backward(value, spatial_shapes, level_start_index, reference_points,
+                              sampling_offsets, attn_logits)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, lsi, ref, off, logits = ctx.saved_tensors
+        grad_value, grad_off, grad_logits = ops.ms_deform_attn_fused_backward(
+            value, shapes, lsi, ref, off, logits, grad_output)
+        return grad_value, None, None, None, grad_off, grad_logits

@@ -28,7 +28,8 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .functions import MSDeformAttnFunction
+from . import ops
+from .functions import MSDeformAttnFunction, MSDeformAttnFusedFunction
 
 CoreFn = Callable[..., torch.Tensor]
 
@@ -42,8 +43,12 @@ def _cuda_core(value, spatial_shapes, level_start_index, sampling_locations, att
 class MSDeformAttn(nn.Module):
     """Multi-scale deformable attention module (ms_deform_attn.py:35-126)."""
 
-    def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4, core: Optional[CoreFn] = None):
+    def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4, core: Optional[CoreFn] = None,
+                 fused: bool = False):
+        """`fused=True` (not in the reference): softmax and location arithmetic run inside the
+        kernels whenever the shapes allow; results agree to rounding."""
         super().__init__()
+        self.fused = fused
         if d_model % n_heads:
             raise ValueError(f"d_model must be divisible by n_heads, but got {d_model} and {n_heads}")
         self.im2col_step = 128                    # ms_deform_attn.py:55
@@ -102,6 +107,18 @@ class MSDeformAttn(nn.Module):
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes,
                 input_level_start_index, input_padding_mask=None):
         value = self.project_value(input_flatten, input_padding_mask)
+        if self.fused and self._core is _cuda_core and not reference_points.requires_grad:
+            N, Lq, _ = query.shape
+            offsets = self.sampling_offsets(query).view(N, Lq, self.n_heads, self.n_levels, self.n_points, 2)
+            logits = self.attention_weights(query).view(N, Lq, self.n_heads, self.n_levels * self.n_points)
+            ref = reference_points
+            if ref.dim() == 4 and ref.stride(0) == 0:        # expanded over the batch: pass one copy
+                ref = ref[:1]
+            ref = ref.contiguous()
+            if ops.fused_supported(value, ref, offsets, logits):
+                out = MSDeformAttnFusedFunction.apply(value, input_spatial_shapes, input_level_start_index,
+                                                      ref, offsets, logits)
+                return self.output_proj(out)
         loc, weights = self.sampling_inputs(query, reference_points, input_spatial_shapes)
         out = self._core(value, input_spatial_shapes, input_level_start_index, loc.contiguous(),
                          weights.contiguous(), self.im2col_step)
@@ -116,9 +133,9 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
     """msdeformattn.py:102-142 (post-norm: attention, add & norm, FFN, add & norm)."""
 
     def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8,
-                 n_points=4, core: Optional[CoreFn] = None):
+                 n_points=4, core: Optional[CoreFn] = None, fused: bool = False):
         super().__init__()
-        self.self_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points, core=core)
+        self.self_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points, core=core, fused=fused)
         self.dropout1 = nn.Dropout(dropout)
         self.norm1 = nn.LayerNorm(d_model)
         self.linear1 = nn.Linear(d_model, d_ffn)
@@ -199,11 +216,13 @@ class MSDeformAttnTransformerEncoderOnly(nn.Module):
     embedding and runs the encoder.  Returns (memory, spatial_shapes, level_start_index, valid_ratios)."""
 
     def __init__(self, d_model=256, nhead=8, num_encoder_layers=6, dim_feedforward=1024, dropout=0.1,
-                 activation="relu", num_feature_levels=4, enc_n_points=4, core: Optional[CoreFn] = None):
+                 activation="relu", num_feature_levels=4, enc_n_points=4, core: Optional[CoreFn] = None,
+                 fused: bool = False):
         super().__init__()
         self.d_model, self.nhead = d_model, nhead
         layer = MSDeformAttnTransformerEncoderLayer(d_model, dim_feedforward, dropout, activation,
-                                                    num_feature_levels, nhead, enc_n_points, core=core)
+                                                    num_feature_levels, nhead, enc_n_points, core=core,
+                                                    fused=fused)
         self.encoder = MSDeformAttnTransformerEncoder(layer, num_encoder_layers)
         self.level_embed = nn.Parameter(torch.empty(num_feature_levels, d_model))
         self._reset_parameters()

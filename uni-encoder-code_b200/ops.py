@@ -149,3 +149,82 @@ def debug_indices(value_shape, spatial_shapes, level_start_index, sampling_loc):
             torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "debug_indices")
     return idx, off
+
+
+# ----------------------------------------------------------------------------------------------
+# Fused producers: softmax over the L*P logits and `ref + offset / (W, H)` inside
+# the kernels (ops/modules/ms_deform_attn.py:105-112).  No counterpart in the reference's extension.
+# ----------------------------------------------------------------------------------------------
+def fused_supported(value, reference_points, sampling_offsets, attn_logits):
+    """The fused kernels cover the pixel-decoder shape only: fp32, 32 channels per head,
+    L*P in {4, 8, 12, 16}, 2-d reference points shared by the batch or per image."""
+    if not (isinstance(value, torch.Tensor) and value.is_cuda and value.dtype == torch.float32):
+        return False
+    if value.dim() != 4 or value.size(3) != 32 or sampling_offsets.dim() != 6:
+        return False
+    L, P = sampling_offsets.size(3), sampling_offsets.size(4)
+    if L * P not in (4, 8, 12, 16) or value.size(1) * value.size(2) * 8 >= 0x7fffffff:
+        return False
+    return (reference_points.dim() == 4 and reference_points.size(-1) == 2
+            and reference_points.size(0) in (1, value.size(0)))
+
+
+def _check_fused(value, shapes, lsi, ref, off, logits, extra=()):
+    named = [("value", value), ("spatial_shapes", shapes), ("level_start_index", lsi),
+             ("reference_points", ref), ("sampling_offsets", off), ("attn_logits", logits)] + list(extra)
+    if not value.is_cuda:
+        raise RuntimeError("Not implemented on the CPU")
+    for name, t in named:
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name} tensor has to be contiguous")
+        if not t.is_cuda or t.device != value.device:
+            raise RuntimeError(f"{name} must be a CUDA tensor on {value.device}")
+    if not fused_supported(value, ref, off, logits):
+        raise RuntimeError("fused MSDA covers fp32, 32 channels per head, L*P in {4,8,12,16}, 2-d "
+                           "reference points only; compose the unfused op for other shapes")
+    N, S, M, D = value.shape
+    _, Lq, _, L, P, _ = off.shape
+    if tuple(off.shape) != (N, Lq, M, L, P, 2) or logits.numel() != N * Lq * M * L * P \
+            or tuple(ref.shape[1:]) != (Lq, L, 2) or shapes.size(0) != L:
+        raise RuntimeError("inconsistent shapes for fused MSDA")
+    for t in (ref, off, logits) + tuple(t for _, t in extra):
+        if t.dtype != torch.float32:
+            raise RuntimeError("fused MSDA is float32 only")
+    ref_stride = 0 if ref.size(0) == 1 and N > 1 else Lq * L * 2
+    return N, S, M, D, L, Lq, P, ref_stride
+
+
+def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, reference_points,
+                                 sampling_offsets, attn_logits):
+    """output [N, Lq, M*D] from raw offsets / logits (msda_b200_fused_forward_f32)."""
+    N, S, M, D, L, Lq, P, rs = _check_fused(value, spatial_shapes, level_start_index, reference_points,
+                                            sampling_offsets, attn_logits)
+    with torch.cuda.device(value.device):
+        output = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+        with _timed("forward"):
+            rc = _lib.lib.msda_b200_fused_forward_f32(
+                value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                reference_points.data_ptr(), rs, sampling_offsets.data_ptr(), attn_logits.data_ptr(),
+                N, S, M, D, L, Lq, P, output.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "ms_deform_attn_fused_forward")
+    return output
+
+
+def ms_deform_attn_fused_backward(value, spatial_shapes, level_start_index, reference_points,
+                                  sampling_offsets, attn_logits, grad_output):
+    """[grad_value, grad_sampling_offsets, grad_attn_logits] (msda_b200_fused_backward_f32)."""
+    N, S, M, D, L, Lq, P, rs = _check_fused(value, spatial_shapes, level_start_index, reference_points,
+                                            sampling_offsets, attn_logits, [("grad_output", grad_output)])
+    with torch.cuda.device(value.device):
+        grad_value = torch.zeros_like(value)
+        grad_off = torch.empty_like(sampling_offsets)
+        grad_logits = torch.empty_like(attn_logits)
+        with _timed("backward"):
+            rc = _lib.lib.msda_b200_fused_backward_f32(
+                grad_output.data_ptr(), value.data_ptr(), spatial_shapes.data_ptr(),
+                level_start_index.data_ptr(), reference_points.data_ptr(), rs,
+                sampling_offsets.data_ptr(), attn_logits.data_ptr(), N, S, M, D, L, Lq, P,
+                grad_value.data_ptr(), grad_off.data_ptr(), grad_logits.data_ptr(),
+                torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "ms_deform_attn_fused_backward")
+    return [grad_value, grad_off, grad_logits]
