@@ -9,8 +9,12 @@
  * What it restates (all file:line relative to
  * /root/reference/model/modeling/pixel_decoder/ops/src/cuda/):
  *   - pixel coordinate from a normalised location, `loc*size - 0.5`
- *     (ms_deform_im2col_cuda.cuh:290-291), with the multiply and subtract kept
- *     as two separately rounded operations (build with -ffp-contract=off);
+ *     (ms_deform_im2col_cuda.cuh:290-291), evaluated as ONE fused multiply-add:
+ *     that is what nvcc makes of the expression with the reference's build flags
+ *     (`FFMA R, R, R, -0.5` in the SASS of the reference op compiled for sm_100,
+ *     see baseline/build_reference_cuda.py), so it is the reference kernel's actual
+ *     integer-deciding arithmetic.  fmaf()/fma() are exact here whatever
+ *     -ffp-contract says;
  *   - the point validity test (cuh:293);
  *   - floor / fractional split and the per-corner bounds test (cuh:43-50, 60-83);
  *   - flat element offsets: level base `level_start*M*D` (cuh:279-283), row
@@ -45,7 +49,7 @@
  *   f32     = (float,  float)   the reference CUDA kernel's fp32 arithmetic
  *   f64     = (double, double)  the float golden
  *   f64g32  = (double, float)   fp32 geometry exactly as the reference kernel computes
- *             it (its `loc*W - 0.5` is rounded to fp32, cuh:290-291), everything after
+ *             it (its `loc*W - 0.5` is one fp32 FMA, cuh:290-291), everything after
  *             that in fp64: "the reference fp32 kernel with exact accumulation".  This
  *             is what an fp32 implementation can be held to 1e-5 against on level
  *             sizes that are not powers of two, where the fp32 product loc*W is
@@ -54,31 +58,37 @@
 #define GEO float
 #define SUFFIX(name) name##_f32
 #define FLOOR floorf
+#define FMA fmaf
 #include "msda_oracle.c"
 #undef REAL
 #undef GEO
 #undef SUFFIX
 #undef FLOOR
+#undef FMA
 
 #define REAL double
 #define GEO double
 #define SUFFIX(name) name##_f64
 #define FLOOR floor
+#define FMA fma
 #include "msda_oracle.c"
 #undef REAL
 #undef GEO
 #undef SUFFIX
 #undef FLOOR
+#undef FMA
 
 #define REAL double
 #define GEO float
 #define SUFFIX(name) name##_f64g32
 #define FLOOR floorf
+#define FMA fmaf
 #include "msda_oracle.c"
 #undef REAL
 #undef GEO
 #undef SUFFIX
 #undef FLOOR
+#undef FMA
 
 int msda_oracle_abi_version(void) { return 1; }
 
@@ -100,11 +110,9 @@ SUFFIX(decompose)(REAL loc_x_, REAL loc_y_, int H, int W)
 {
     SUFFIX(point_t) pt;
     const GEO loc_x = (GEO)loc_x_, loc_y = (GEO)loc_y_;
-    /* two roundings each: product, then difference (cuh:290-291) */
-    volatile GEO hm = loc_y * (GEO)H;
-    volatile GEO wm = loc_x * (GEO)W;
-    const GEO h_im = hm - (GEO)0.5;
-    const GEO w_im = wm - (GEO)0.5;
+    /* one rounding: fused multiply-add, as the compiled reference kernel (cuh:290-291) */
+    const GEO h_im = FMA(loc_y, (GEO)H, (GEO)-0.5);
+    const GEO w_im = FMA(loc_x, (GEO)W, (GEO)-0.5);
     pt.valid = (h_im > -1 && w_im > -1 && h_im < H && w_im < W);
     pt.h_low = (int)FLOOR(h_im);
     pt.w_low = (int)FLOOR(w_im);

@@ -345,3 +345,32 @@ def test_launches_are_counted(pkg):
     n0 = pkg.launch_count()
     run_fwd_bwd(pkg, d)
     assert pkg.launch_count() - n0 == 2
+
+
+# ---------------------------------------------------------------- the reference's own CUDA kernels
+def test_matches_reference_cuda_op_on_same_gpu(pkg):
+    """When baseline/_ref/ref_msda_cuda.so exists (the reference's extension compiled for sm_100 by
+    baseline/build_reference_cuda.py in the build container) the two CUDA implementations are run on
+    identical inputs: fp32 forward within 1e-5 of each other, gradients within 1e-4."""
+    import importlib.util
+    import os
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref",
+                      "ref_msda_cuda.so")
+    if not os.path.exists(so):
+        pytest.skip("reference CUDA op not built")
+    spec = importlib.util.spec_from_file_location("ref_msda_cuda", so)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    for levels, batch, mode in (([(16, 32), (32, 64), (64, 128)], 2, "model"),
+                                ([(12, 39), (24, 78), (48, 156)], 2, "uniform")):
+        inp = pkg.synthetic.make_inputs(levels, batch, mode=mode, seed=17)
+        d = to_dev(inp)
+        a = (d["value"], d["spatial_shapes"], d["level_start_index"], d["sampling_locations"],
+             d["attention_weights"])
+        o_ref = ref.ms_deform_attn_forward(*a, 128)
+        o_new = pkg.ms_deform_attn_forward(*a, 128)
+        assert (o_ref - o_new).abs().max().item() <= FWD_ABS_TOL
+        g_ref = ref.ms_deform_attn_backward(*a, d["grad_output"], 128)
+        g_new = pkg.ms_deform_attn_backward(*a, d["grad_output"], 128)
+        for x, y in zip(g_new, g_ref):
+            assert rel_err(x.cpu().numpy(), y.cpu().numpy()) <= GRAD_REL_TOL

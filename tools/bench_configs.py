@@ -35,6 +35,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="1,2,3,4,5")
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--fused", action="store_true", help="use the fused-producer kernels inside the encoder mirror")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "configs.jsonl"))
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -56,7 +57,7 @@ def main():
         return float(t.item())
 
     def emit(rec):
-        rec.update(n_gpus=world)
+        rec.update(n_gpus=world, fused_producers=bool(args.fused))
         if rank == 0:
             os.makedirs(os.path.dirname(args.out), exist_ok=True)
             with open(args.out, "a") as f:
@@ -93,7 +94,7 @@ def main():
         torch.manual_seed(seed)
         m = pkg.modules.MSDeformAttnTransformerEncoderOnly(
             d_model=256, nhead=8, num_encoder_layers=6, dim_feedforward=1024, dropout=0.1,
-            num_feature_levels=3, enc_n_points=4).to(dev)
+            num_feature_levels=3, enc_n_points=4, fused=args.fused).to(dev)
         # trained-model-like sampling: small learned offsets instead of the integer-lattice init
         gen = torch.Generator().manual_seed(seed + 1)
         with torch.no_grad():
@@ -167,6 +168,33 @@ def main():
                   "allreduce_bytes": nparam * 4, "msda_algorithmic_GBs": 6 * q * 8576 / (f_ms + b_ms) / 1e6,
                   "msda_frac_of_measured_hbm": 6 * q * 8576 / (f_ms + b_ms) / 1e6 / peak})
             del m, model, opt, srcs, pos
+        elif cfg == "f":
+            # op level, configs[1] shape: what the module does around the op (softmax + location
+            # arithmetic in torch, then the op) against the fused kernels, forward + backward
+            w = syn.WORKLOADS["cityscapes_512x1024_b8"]
+            gen = torch.Generator().manual_seed(40 + rank)
+            N, S, M, L, P = w.batch, w.spatial_size, 8, 3, 4
+            value = torch.randn(N, S, M, 32, generator=gen).to(dev).requires_grad_(True)
+            off = (torch.randn(N, S, M, L, P, 2, generator=gen) * 2 + torch.rand(N, S, M, L, P, 2, generator=gen) - 0.5).to(dev).requires_grad_(True)
+            logits = torch.randn(N, S, M, L * P, generator=gen).to(dev).requires_grad_(True)
+            go = torch.randn(N, S, M * 32, generator=gen).to(dev)
+            shapes, lsi = (t.to(dev) for t in syn.level_tensors(w.levels))
+            ref = pkg.modules.reference_points_for(w.levels, dev)
+            wh = shapes.flip(-1).float()
+
+            def unfused():
+                wts = torch.softmax(logits, -1).view(N, S, M, L, P)
+                loc = ref[:, :, None, :, None, :] + off / wh[None, None, None, :, None, :]
+                out = pkg.MSDeformAttnFunction.apply(value, shapes, lsi, loc, wts, 128)
+                torch.autograd.grad(out, (value, off, logits), go)
+
+            def fused():
+                out = pkg.MSDeformAttnFusedFunction.apply(value, shapes, lsi, ref, off, logits)
+                torch.autograd.grad(out, (value, off, logits), go)
+            ms_u = timed(unfused, args.steps * 3)
+            ms_f = timed(fused, args.steps * 3)
+            emit({"config": "f", "what": "op + its producers (softmax, ref + off/(W,H)) forward+backward at configs[1] shape",
+                  "unfused_ms": ms_u, "fused_ms": ms_f, "speedup": ms_u / ms_f})
         elif cfg == "q":
             levels = syn.pyramid(1024, 2048)
             m = encoder().eval()

@@ -17,10 +17,11 @@ constexpr int kMaxSamples = 64;          // L*P bound for the shared sample->lev
 constexpr uint32_t kNoCorner = 0xffffffffu;  // record marker: corner outside the level
 
 // ---------------------------------------------------------------------------
-// exact-rounding helpers: one rounding per operation, never contracted to FMA
+// explicitly rounded helpers: the coordinate arithmetic below must not depend on the
+// compiler's contraction choices
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float fma_rn(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double fma_rn(double a, double b, double c) { return __fma_rn(a, b, c); }
 __device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ int floor_to_int(float a) { return __float2int_rd(a); }
@@ -29,8 +30,13 @@ __device__ __forceinline__ int floor_to_int(double a) { return __double2int_rd(a
 // ---------------------------------------------------------------------------
 // Geometry of one sampling point.  This single function carries all the integer
 // work that the parity tests pin bit-exactly (through msda_b200_debug_indices_f32):
-//   pixel coordinate  x = loc_x*W - 0.5, y = loc_y*H - 0.5  as a rounded product
-//                     followed by a rounded difference          (cuh:290-291)
+//   pixel coordinate  x = fma(loc_x, W, -0.5), y = fma(loc_y, H, -0.5): ONE rounding.
+//                     The source reads `loc * size - 0.5` (cuh:290-291); nvcc with the
+//                     reference's build flags (default -fmad=true, ops/setup.py:44-49) folds the
+//                     double literal and contracts it to a single FFMA -- `FFMA R, R, R, -0.5`
+//                     in the SASS of the reference op built for sm_100
+//                     (baseline/build_reference_cuda.py) -- so this is what the reference's
+//                     kernels compute, and what we reproduce bit for bit
 //   point valid       y > -1 && x > -1 && y < H && x < W         (cuh:293)
 //   h_low, w_low      floor                                      (cuh:43-44)
 //   lh, lw            fractional parts                           (cuh:48-49)
@@ -48,8 +54,8 @@ struct Geom {
 template <typename T>
 __device__ __forceinline__ Geom<T> decompose(T loc_x, T loc_y, int H, int W) {
     Geom<T> g;
-    const T h_im = sub_rn(mul_rn(loc_y, (T)H), (T)0.5);
-    const T w_im = sub_rn(mul_rn(loc_x, (T)W), (T)0.5);
+    const T h_im = fma_rn(loc_y, (T)H, (T)-0.5);
+    const T w_im = fma_rn(loc_x, (T)W, (T)-0.5);
     g.valid = (h_im > (T)-1) && (w_im > (T)-1) && (h_im < (T)H) && (w_im < (T)W);
     g.h_low = floor_to_int(h_im);   // cvt.rmi saturates; NaN -> 0, and then valid == 0
     g.w_low = floor_to_int(w_im);
