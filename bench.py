@@ -316,12 +316,53 @@ def run_b200_arm(args):
     }
     if e2e is not None:
         line["e2e"] = e2e
+    if world == 1:
+        ref_cuda = reference_cuda_same_gpu(pkg, d, flush)
+        if ref_cuda is not None:
+            line["reference_cuda_same_gpu"] = ref_cuda
     if world == 1 and not args.no_cpu_baseline:
         base = cpu_reference_run(args.workload, args.mode, args.cpu_sample_batch, 3, 1)
         line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def reference_cuda_same_gpu(pkg, d, flush, iters=5):
+    """Context only (not an arm): the reference's own CUDA op, compiled for sm_100 in the build
+    container by baseline/build_reference_cuda.py, timed on the same tensors when its .so travelled."""
+    import importlib.util
+    import torch
+    so = os.path.join(ROOT, "baseline", "_ref", "ref_msda_cuda.so")
+    if not os.path.exists(so):
+        return None
+    try:
+        spec = importlib.util.spec_from_file_location("ref_msda_cuda", so)
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+        a = (d["value"], d["spatial_shapes"], d["level_start_index"], d["sampling_locations"],
+             d["attention_weights"])
+
+        def t(fn):
+            ts = []
+            for i in range(2 + iters):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                if i >= 2:
+                    ts.append(e0.elapsed_time(e1))
+            return sum(ts) / len(ts)
+        f = t(lambda: ref.ms_deform_attn_forward(*a, 128))
+        b = t(lambda: ref.ms_deform_attn_backward(*a, d["grad_output"], 128))
+        q = d["value"].shape[0] * d["sampling_locations"].shape[1]
+        return {"forward_ms": f, "backward_ms": b, "queries_per_s": q / ((f + b) * 1e-3),
+                "what": "reference ms_deform_attn_forward/backward (its CUDA kernels, sm_100 build) per call "
+                        "incl. its own zero-fills; see profiles/r1_vs_reference_cuda.md"}
+    except Exception as e:      # a comparison aid must never break the bench line
+        return {"unavailable": repr(e)[:200]}
 
 
 def run_e2e(pkg, host, dev, world, steps, dist):

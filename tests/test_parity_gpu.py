@@ -140,6 +140,28 @@ def test_kernel_variants_agree(pkg, oracle, fwd_variant, bwd_variant, tile_order
     check_against(out, gv, gl, gw, *refs, tag=f"variant {fwd_variant}")
 
 
+def test_random_shapes_match_oracle(pkg, oracle):
+    """Seeded random problem shapes (levels, heads, points, batch, query count, location spread)
+    through whichever kernel the dispatcher picks (fast path for D=32 and L*P in {4,8,12,16})."""
+    rng = np.random.default_rng(2024)
+    for case in range(12):
+        L = int(rng.integers(1, 5))
+        levels = [(int(rng.integers(1, 40)), int(rng.integers(1, 40))) for _ in range(L)]
+        heads = int(rng.integers(1, 9))
+        points = int(rng.choice([1, 2, 3, 4]))
+        channels = int(rng.choice([32, 32, 32, 8, 64]))
+        batch = int(rng.integers(1, 4))
+        S = sum(h * w for h, w in levels)
+        nq = None if rng.random() < 0.5 else int(rng.integers(1, 300))
+        mode = "model" if nq is None and rng.random() < 0.5 else "uniform"
+        inp = pkg.synthetic.make_inputs(levels, batch, heads, channels, points, num_query=nq, mode=mode,
+                                        seed=1000 + case)
+        if rng.random() < 0.3:       # widen the spread: many points outside, some far outside
+            inp["sampling_locations"] = (inp["sampling_locations"] - 0.5) * 3.0 + 0.5
+        out, gv, gl, gw = run_fwd_bwd(pkg, to_dev(inp))
+        check_against(out, gv, gl, gw, *oracle_refs(oracle, inp), tag=f"case {case}: {levels} M{heads} P{points} D{channels}")
+
+
 # ---------------------------------------------------------------- integer work, bit-exact
 @pytest.mark.parametrize("mode,seed", [("model", 0), ("uniform", 1)])
 def test_integer_work_bit_exact(pkg, oracle, mode, seed):
