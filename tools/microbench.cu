@@ -154,8 +154,7 @@ __global__ void __launch_bounds__(THREADS) bench(float *gbuf, uint32_t nrows_mas
 }
 
 template <int TEST>
-void run(float *gbuf, uint32_t nrows_mask, float *sink, long long *cycles_d, int sms) {
-    const int ctas_per_sm = 2;
+void run(float *gbuf, uint32_t nrows_mask, float *sink, long long *cycles_d, int sms, int ctas_per_sm = 2) {
     const int grid = sms * ctas_per_sm;
     cudaEvent_t e0, e1;
     CHECK(cudaEventCreate(&e0)); CHECK(cudaEventCreate(&e1));
@@ -172,6 +171,7 @@ void run(float *gbuf, uint32_t nrows_mask, float *sink, long long *cycles_d, int
     free(h);
     // warp instructions per SM = ctas_per_sm * warps * ITERS * UNROLL
     const double instr_per_sm = (double)ctas_per_sm * (THREADS / 32) * ITERS * UNROLL;
+    if (ctas_per_sm != 2) printf("[%d CTAs = %2d warps/SM] ", ctas_per_sm, ctas_per_sm * THREADS / 32);
     printf("%-58s  %8.3f ms  %9.0f clk/CTA  %7.2f SM-cycles per warp-instr  (%6.1f GB/s row payload @128B/row-instr)\n",
            kNames[TEST], ms, mean, mean / instr_per_sm,
            instr_per_sm * sms * 128.0 / (ms * 1e-3) / 1e9);
@@ -188,7 +188,7 @@ int main() {
     CHECK(cudaMalloc(&gbuf, (size_t)nrows * ROW_BYTES));
     CHECK(cudaMemset(gbuf, 0, (size_t)nrows * ROW_BYTES));
     CHECK(cudaMalloc(&sink, 16));
-    CHECK(cudaMalloc(&cycles, sizeof(long long) * sms * 4));
+    CHECK(cudaMalloc(&cycles, sizeof(long long) * sms * 8));
     run<LDS32_BCAST>(gbuf, nrows - 1, sink, cycles, sms);
     run<LDS32_DISTINCT>(gbuf, nrows - 1, sink, cycles, sms);
     run<LDS64_4ADDR>(gbuf, nrows - 1, sink, cycles, sms);
@@ -215,6 +215,12 @@ int main() {
     run<ATOMS_INT_RET>(gbuf, nrows - 1, sink, cycles, sms);
     run<ATOMS_F32_ROW>(gbuf, nrows - 1, sink, cycles, sms);
     run<ATOMS_F32_ROW_SMALLWIN>(gbuf, nrows - 1, sink, cycles, sms);
+    // does the reduction / load rate depend on how many warps are resident? (1..4 CTAs of 16 warps)
+    for (int c = 1; c <= 4; ++c) run<RED128_4ROWS>(gbuf, nrows - 1, sink, cycles, sms, c);
+    for (int c = 1; c <= 4; ++c) run<RED32_1ROW>(gbuf, nrows - 1, sink, cycles, sms, c);
+    for (int c = 1; c <= 4; ++c) run<LDG128_4ROWS_L1>(gbuf, nrows - 1, sink, cycles, sms, c);
+    for (int c = 1; c <= 4; ++c) run<LDG128_4ROWS_L2>(gbuf, nrows - 1, sink, cycles, sms, c);
+    for (int c = 1; c <= 4; ++c) run<STG128_4ROWS>(gbuf, nrows - 1, sink, cycles, sms, c);
     printf("done\n");
     return 0;
 }
