@@ -13,7 +13,7 @@ if ROOT not in sys.path:
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 GOLDEN_NAMES = sorted(n for n in (os.path.splitext(os.path.basename(p))[0]
                                   for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-                      if not n.startswith("encoder"))       # op-level fixtures only
+                      if not n.startswith(("encoder", "pixel_decoder")))       # op-level fixtures only
 
 # tolerances of BASELINE.json's north_star
 FWD_ABS_TOL = 1e-5      # fp32 forward, max abs error vs the fp64 oracle, value ~ N(0,1)

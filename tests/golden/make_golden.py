@@ -123,8 +123,44 @@ def encoder_golden():
     print(f"encoder_small: memory {tuple(memory.shape)} -> {os.path.getsize(path) / 1024:.1f} KiB")
 
 
+PD_KW = dict(transformer_dropout=0.0, transformer_nheads=2, transformer_dim_feedforward=96,
+             transformer_enc_layers=2, conv_dim=64, mask_dim=32, norm="GN",
+             transformer_in_features=["res3", "res4", "res5"], common_stride=4)
+PD_SHAPES = {"res2": (12, 4), "res3": (20, 8), "res4": (28, 16), "res5": (36, 32)}   # (channels, stride)
+
+
+def pixel_decoder_golden():
+    """A small reference MSDeformAttnPixelDecoder (msdeformattn.py:178-386, with the third-party stubs of
+    tests/ref_stubs) in fp32 (its only mode: inputs are cast with .float()) on CPU for a 64x96 image: weights, the four backbone features and the three
+    outputs of forward_features.  Pins uni-encoder-code_b200/pixel_decoder.py."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ref_import
+    ns = ref_import.load()
+    torch.manual_seed(4321)
+    shapes = {k: ns.ShapeSpec(channels=c, stride=s) for k, (c, s) in PD_SHAPES.items()}
+    dec = ns.MSDeformAttnPixelDecoder(shapes, **PD_KW).eval()      # fp32: forward_features casts its inputs with .float()
+    gen = torch.Generator().manual_seed(77)
+    with torch.no_grad():
+        for layer in dec.transformer.encoder.layers:
+            a = layer.self_attn
+            a.sampling_offsets.weight.copy_(torch.randn(a.sampling_offsets.weight.shape, generator=gen) * 0.05)
+            a.sampling_offsets.bias.add_(torch.rand(a.sampling_offsets.bias.shape, generator=gen) * 0.6 + 0.2)
+            a.attention_weights.weight.copy_(torch.randn(a.attention_weights.weight.shape, generator=gen) * 0.1)
+    feats = {k: torch.randn(2, c, 64 // s, 96 // s, generator=gen) for k, (c, s) in PD_SHAPES.items()}
+    with torch.no_grad():
+        mask_feat, low, multi = dec.forward_features(feats)      # the reference casts inputs to fp32 (.float())
+    out = {"state::" + k: v.detach().numpy() for k, v in dec.state_dict().items()}
+    out.update({"feat::" + k: v.numpy() for k, v in feats.items()})
+    out.update(mask_features=mask_feat.numpy(), lowest=low.numpy(),
+               **{f"multi{i}": m.numpy() for i, m in enumerate(multi)})
+    path = os.path.join(HERE, "pixel_decoder_small.npz")
+    np.savez_compressed(path, **out)
+    print(f"pixel_decoder_small: mask_features {tuple(mask_feat.shape)} -> {os.path.getsize(path) / 1024:.1f} KiB")
+
+
 def main():
     encoder_golden()
+    pixel_decoder_golden()
     core = load_reference()
     syn = load_package().synthetic if os.path.exists(
         os.path.join(ROOT, "uni-encoder-code_b200", "lib", "libmsda_b200.so")) else None

@@ -1,0 +1,68 @@
+"""Mirror of the reference's MSDeformAttnPixelDecoder (uni-encoder-code_b200/pixel_decoder.py) against
+the committed golden of the reference class (tests/golden/make_golden.py::pixel_decoder_golden) and,
+in the build container, against the live reference: parameter names, init, forward_features."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+import ref_import
+from test_modules import oracle_core
+
+PD_KW = dict(transformer_dropout=0.0, transformer_nheads=2, transformer_dim_feedforward=96,
+             transformer_enc_layers=2, conv_dim=64, mask_dim=32, norm="GN",
+             transformer_in_features=["res3", "res4", "res5"], common_stride=4)
+PD_SHAPES = {"res2": (12, 4), "res3": (20, 8), "res4": (28, 16), "res5": (36, 32)}
+
+
+def build(pkg, core=None, device="cpu", fused=False):
+    g = load_golden("pixel_decoder_small")
+    m = pkg.pixel_decoder.MSDeformAttnPixelDecoder(PD_SHAPES, core=core, fused=fused, **PD_KW)
+    state = {k[len("state::"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("state::")}
+    missing, unexpected = m.load_state_dict(state, strict=True)
+    assert not missing and not unexpected
+    feats = {k[len("feat::"):]: torch.from_numpy(v).to(device) for k, v in g.items() if k.startswith("feat::")}
+    return m.to(device).eval(), feats, g
+
+
+def check(outs, g, tol):
+    mask_feat, low, multi = outs
+    assert tuple(mask_feat.shape) == g["mask_features"].shape and len(multi) == 3
+    assert np.abs(mask_feat.detach().cpu().numpy() - g["mask_features"]).max() <= tol
+    assert np.abs(low.detach().cpu().numpy() - g["lowest"]).max() <= tol
+    for i, m in enumerate(multi):
+        assert np.abs(m.detach().cpu().numpy() - g[f"multi{i}"]).max() <= tol
+
+
+def test_mirror_loads_reference_checkpoint_and_matches_forward_features_cpu(pkg, oracle):
+    m, feats, g = build(pkg, core=oracle_core(oracle))
+    with torch.no_grad():
+        check(m.forward_features(feats), g, 2e-5)
+    # the position embedding is input-independent and cached per shape
+    assert len(m.pe_layer._cache) == 3
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference checkout not present")
+def test_mirror_init_equals_live_reference(pkg, oracle):
+    ns = ref_import.load()
+    torch.manual_seed(11)
+    ref = ns.MSDeformAttnPixelDecoder({k: ns.ShapeSpec(channels=c, stride=s) for k, (c, s) in PD_SHAPES.items()}, **PD_KW)
+    torch.manual_seed(11)
+    mine = pkg.pixel_decoder.MSDeformAttnPixelDecoder(PD_SHAPES, core=oracle_core(oracle), **PD_KW)
+    rs, ms = ref.state_dict(), mine.state_dict()
+    assert list(rs) == list(ms)
+    for k in rs:
+        assert torch.equal(rs[k], ms[k]), k
+    x = torch.randn(1, 7, 5, 9)
+    assert torch.equal(ns.PositionEmbeddingSine(32, normalize=True)(x), mine.pe_layer(x))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fused", [False, True])
+def test_mirror_plus_cuda_op_matches_reference_pixel_decoder_golden(pkg, fused):
+    m, feats, g = build(pkg, device="cuda:0", fused=fused)
+    n0 = pkg.launch_count()
+    with torch.no_grad():
+        outs = m.forward_features(feats)
+    assert pkg.launch_count() - n0 == 2          # one MSDA forward per encoder layer
+    check(outs, g, 5e-4)

@@ -6,8 +6,9 @@
 
  1  single MSDA forward, 1024x2048 pyramid, batch 1                      (op level)
  2  MSDA forward+backward, 512x1024 crop, batch 8 per GPU                (op level; bench.py headline)
- 3  6-layer encoder inference, 1024x2048, batch 8 per GPU                (batch-sharded)
- 4  KITTI 384x1248 two-frame input (8 pairs = batch 16 per GPU) encoder forward
+ 3  MSDeformAttnPixelDecoder.forward_features (input proj + 6-layer encoder + FPN), 1024x2048,
+    batch 8 per GPU (batch-sharded), Swin-T feature shapes
+ 4  KITTI 384x1248 two-frame input (8 pairs = batch 16 per GPU), same pixel-decoder forward
  5  encoder training step (fwd+bwd+AdamW) at 512x1024, batch 16 per GPU, DDP all-reduce over NCCL
  q  query-range sharded single-image encoder inference, 1024x2048, batch 1 over all ranks
 
@@ -126,23 +127,31 @@ def main():
                   "queries_per_s": world * q / ms * 1e3, "algorithmic_GBs_per_gpu": q * 8576 / ms / 1e6,
                   "frac_of_measured_hbm": q * 8576 / ms / 1e6 / peak})
         elif cfg in ("3", "4"):
-            levels, batch, name = ((syn.pyramid(1024, 2048), 8, "encoder inference 1024x2048, batch 8 per GPU") if cfg == "3"
-                                   else (syn.pyramid(384, 1248), 16, "KITTI 384x1248 two-frame (8 pairs = batch 16 per GPU) encoder forward"))
-            m = encoder().eval()
-            srcs, pos = features(levels, batch, 10)
+            (Himg, Wimg), batch, name = (((1024, 2048), 8, "pixel-decoder forward_features 1024x2048, batch 8 per GPU") if cfg == "3"
+                                         else ((384, 1248), 16, "KITTI 384x1248 two-frame (8 pairs = batch 16 per GPU) pixel-decoder forward_features"))
+            # Swin-T feature pyramid: (channels, stride) per backbone output (model/modeling/backbone/swin.py:730-741)
+            shapes = {"res2": (96, 4), "res3": (192, 8), "res4": (384, 16), "res5": (768, 32)}
+            torch.manual_seed(0)
+            dec = pkg.pixel_decoder.MSDeformAttnPixelDecoder(
+                shapes, transformer_dropout=0.1, transformer_nheads=8, transformer_dim_feedforward=1024,
+                transformer_enc_layers=6, conv_dim=256, mask_dim=256, norm="GN",
+                transformer_in_features=["res3", "res4", "res5"], common_stride=4, fused=args.fused).to(dev).eval()
+            gen = torch.Generator().manual_seed(10 + rank)
+            feats = {k: torch.randn(batch, c, -(-Himg // st), -(-Wimg // st), generator=gen).to(dev)
+                     for k, (c, st) in shapes.items()}
             with torch.no_grad():
-                ms = timed(lambda: m(srcs, pos), args.steps)
+                ms = timed(lambda: dec.forward_features(feats), args.steps)
                 ev = pkg.ops.enable_timing(True)
                 for _ in range(args.steps):
-                    m(srcs, pos)
+                    dec.forward_features(feats)
                 f_ms, _ = msda_ms(ev, args.steps)
                 pkg.ops.enable_timing(False)
-            S = sum(h * w for h, w in levels)
+            S = sum(h * w for h, w in syn.pyramid(Himg, Wimg))
             q = batch * S
             emit({"config": int(cfg), "what": name, "ms": ms, "msda_ms_6_layers": f_ms, "msda_share": f_ms / ms,
-                  "queries_per_layer_per_gpu": q, "encoder_queries_per_s": world * q / ms * 1e3,
+                  "queries_per_layer_per_gpu": q, "images_per_s": world * batch / ms * 1e3,
                   "msda_algorithmic_GBs": 6 * q * 3200 / f_ms / 1e6, "msda_frac_of_measured_hbm": 6 * q * 3200 / f_ms / 1e6 / peak})
-            del m, srcs, pos
+            del dec, feats
         elif cfg == "5":
             levels, batch = syn.pyramid(512, 1024), 16
             m = encoder().train()

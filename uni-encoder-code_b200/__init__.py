@@ -20,12 +20,12 @@ from .functions import MSDeformAttnFunction, MSDeformAttnFusedFunction
 from .ops import (debug_indices, ms_deform_attn_backward, ms_deform_attn_forward,
                   ms_deform_attn_fused_backward, ms_deform_attn_fused_forward)
 from . import synthetic
-from . import modules, sharding
+from . import modules, pixel_decoder, sharding
 
 __all__ = [
     "ms_deform_attn_forward", "ms_deform_attn_backward", "MSDeformAttnFunction", "debug_indices",
     "ms_deform_attn_fused_forward", "ms_deform_attn_fused_backward", "MSDeformAttnFusedFunction",
-    "install_dropin", "set_option", "get_option", "launch_count", "synthetic", "modules", "sharding",
+    "install_dropin", "set_option", "get_option", "launch_count", "synthetic", "modules", "pixel_decoder", "sharding",
 ]
 
 DROPIN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dropin")
