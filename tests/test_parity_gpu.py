@@ -369,6 +369,44 @@ def test_launches_are_counted(pkg):
     assert pkg.launch_count() - n0 == 2
 
 
+def test_non_finite_and_far_away_locations_are_skipped(pkg, oracle):
+    """NaN / +-Inf / astronomically large sampling locations fail the range test (cuh:293) like any
+    other out-of-range point: they contribute nothing and get zero gradients; everything else is
+    unaffected.  (The oracle is given a finite stand-in far outside for those points.)"""
+    levels = [(8, 12), (16, 24)]
+    inp = pkg.synthetic.make_inputs(levels, 2, heads=4, points=4, mode="model", seed=31)
+    loc = inp["sampling_locations"]
+    gen = torch.Generator().manual_seed(5)
+    pick = torch.rand(loc.shape[:-1], generator=gen) < 0.2
+    bad = torch.tensor([float("nan"), float("inf"), -float("inf"), 3e38, -3e38, 1e9])
+    fill = bad[torch.randint(0, len(bad), loc.shape, generator=gen)]
+    poisoned = torch.where(pick[..., None], fill, loc)
+    standin = torch.where(pick[..., None], torch.full_like(loc, 7.0), loc)
+    d = to_dev(dict(inp, sampling_locations=poisoned))
+    out, gv, gl, gw = run_fwd_bwd(pkg, d)
+    for t in (out, gv, gl, gw):
+        assert torch.isfinite(t).all()
+    assert not gl.cpu()[pick].any() and not gw.cpu()[pick].any()
+    check_against(out, gv, gl, gw, *oracle_refs(oracle, dict(inp, sampling_locations=standin)), tag="non-finite")
+
+
+def test_runs_on_the_tensors_device_not_the_current_one(pkg):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    inp = pkg.synthetic.make_inputs([(6, 10), (12, 20), (24, 40)], 2, mode="model", seed=8)
+    a0 = [inp[k].to("cuda:0") for k in ("value", "spatial_shapes", "level_start_index",
+                                          "sampling_locations", "attention_weights")]
+    a1 = [t.to("cuda:1") for t in a0]
+    with torch.cuda.device(0):
+        o1 = pkg.ms_deform_attn_forward(*a1, 128)           # tensors on cuda:1, current device 0
+        g1 = pkg.ms_deform_attn_backward(*a1, inp["grad_output"].to("cuda:1"), 128)
+        o0 = pkg.ms_deform_attn_forward(*a0, 128)
+    assert o1.device.index == 1 and g1[0].device.index == 1
+    assert torch.equal(o1.cpu(), o0.cpu())
+    with pytest.raises(RuntimeError, match="is on"):
+        pkg.ms_deform_attn_forward(a0[0], a1[1], a0[2], a0[3], a0[4], 128)
+
+
 # ---------------------------------------------------------------- the reference's own CUDA kernels
 def test_matches_reference_cuda_op_on_same_gpu(pkg):
     """When baseline/_ref/ref_msda_cuda.so exists (the reference's extension compiled for sm_100 by
