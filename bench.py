@@ -32,7 +32,12 @@ DEFAULT_WORKLOAD = "cityscapes_512x1024_b8"
 NOMINAL_HBM_GBS = 8000.0          # north_star's "~8 TB/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of
 # this command (profiles/r1_ncu_bench_summary.csv); only valid for the default workload / mode
-NCU_DRAM_TRAFFIC = {("cityscapes_512x1024_b8", "model"): {"forward": 249.0e6, "backward": 528.7e6}}
+NCU_DRAM_TRAFFIC = {("cityscapes_512x1024_b8", "model"): {"forward": 247.4e6, "backward": 535.6e6}}
+# What actually bounds the dominant (backward) kernel on chip, from the same capture and from
+# tools/microbench.cu (profiles/r1_microbench.txt): 120.5 M reduction sectors of 32 B per launch
+# against an L2-side reduction throughput of ~6.4 TB/s (occupancy-independent).
+NCU_RED_BYTES = {("cityscapes_512x1024_b8", "model"): 120499092 * 32}
+L2_REDUCTION_GBS = 6400.0
 FALLBACK_HBM_GBS = 6650.0         # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -301,6 +306,14 @@ def run_b200_arm(args):
             "peak_source": peak_src,
             "algorithmic_bytes_per_launch": bwd_bytes, "ms_per_launch": bwd_mean,
             "frac_of_nominal_8TBs": achieved / NOMINAL_HBM_GBS,
+            "on_chip_limiter": ({
+                "resource": "L2 reduction (red.global.add) throughput",
+                "bytes_per_launch": NCU_RED_BYTES[(args.workload, args.mode)],
+                "achieved_GBs": NCU_RED_BYTES[(args.workload, args.mode)] / (bwd_mean * 1e-3) / 1e9,
+                "measured_peak_GBs": L2_REDUCTION_GBS,
+                "frac": NCU_RED_BYTES[(args.workload, args.mode)] / (bwd_mean * 1e-3) / 1e9 / L2_REDUCTION_GBS,
+                "source": "profiles/r1_ncu_bench_summary.csv, profiles/r1_microbench.txt; DESIGN.md section 4",
+            } if (args.workload, args.mode) in NCU_RED_BYTES else None),
         },
         "kernels": {
             "forward": {"ms": fwd_mean, "algorithmic_GBs": fwd_bytes / (fwd_mean * 1e-3) / 1e9,
