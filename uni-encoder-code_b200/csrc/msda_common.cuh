@@ -150,17 +150,9 @@ __device__ __forceinline__ void warp_queries(const LevelTable &lt, int L, int g,
 // Per-point record shared by the 32-channel kernels: for each of the 4 bilinear
 // corners {offset, weight}, offset in float4 units from the start of image n
 // (pixel, head m, channel 0), weight = bilinear corner weight * attention weight.
-//   ALIAS == false: a corner outside the level gets {kNoCorner, 0}.
-//   ALIAS == true : a corner outside the level of an otherwise valid point gets
-//                   the offset of an in-range corner of the SAME point with weight
-//                   0, so a warp can test one flag per point instead of four; the
-//                   aliased row is one the point reads anyway.  (0 * v == 0 unless v
-//                   is Inf/NaN, in which case the same row already poisons the
-//                   output through its own, non-aliased use or is weighted by an
-//                   exact 0 in the reference too.)  A point that fails the range
-//                   test (cuh:293) gets kNoCorner in all four slots either way.
+// A corner outside the level -- or any corner of a point that fails the range test
+// (cuh:293) -- gets {kNoCorner, 0}: it is neither read nor reduced into.
 // ---------------------------------------------------------------------------
-template <bool ALIAS>
 __device__ __forceinline__ void make_record(const Geom<float> &gm, float aw, uint32_t level_start,
                                             uint32_t W, uint32_t pix_stride, uint32_t head_off,
                                             uint4 &lo, uint4 &hi) {
@@ -169,34 +161,15 @@ __device__ __forceinline__ void make_record(const Geom<float> &gm, float aw, uin
     // a true offset < 2^31 (checked on the host)
     const uint32_t base = (level_start + (uint32_t)gm.h_low * W + (uint32_t)gm.w_low) * pix_stride + head_off;
     const uint32_t row_stride = W * pix_stride;
-    uint32_t off[4] = {base, base + pix_stride, base + row_stride, base + row_stride + pix_stride};
-    float w[4] = {(hh * hw) * aw, (hh * gm.lw) * aw, (gm.lh * hw) * aw, (gm.lh * gm.lw) * aw};
     const int cm = gm.cmask;
-    if (ALIAS) {
-        // which axis of each corner is out of range (only meaningful when cm != 0)
-        const int w_low_bad = !(cm & 0x5), w_high_bad = !(cm & 0xA);   // columns: corners {0,2} / {1,3}
-        const int h_low_bad = !(cm & 0x3), h_high_bad = !(cm & 0xC);   // rows:    corners {0,1} / {2,3}
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (!(cm >> k & 1)) {
-                const int flip = (((k & 1) ? w_high_bad : w_low_bad) ? 1 : 0) |
-                                 (((k & 2) ? h_high_bad : h_low_bad) ? 2 : 0);
-                const int src = k ^ flip;
-                off[k] = cm ? (src == 0 ? off[0] : src == 1 ? off[1] : src == 2 ? off[2] : off[3]) : kNoCorner;
-                w[k] = 0.f;
-            }
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (!(cm >> k & 1)) {
-                off[k] = kNoCorner;
-                w[k] = 0.f;
-            }
-        }
-    }
-    lo = make_uint4(off[0], __float_as_uint(w[0]), off[1], __float_as_uint(w[1]));
-    hi = make_uint4(off[2], __float_as_uint(w[2]), off[3], __float_as_uint(w[3]));
+    lo.x = (cm & 1) ? base : kNoCorner;
+    lo.y = __float_as_uint((cm & 1) ? (hh * hw) * aw : 0.f);
+    lo.z = (cm & 2) ? base + pix_stride : kNoCorner;
+    lo.w = __float_as_uint((cm & 2) ? (hh * gm.lw) * aw : 0.f);
+    hi.x = (cm & 4) ? base + row_stride : kNoCorner;
+    hi.y = __float_as_uint((cm & 4) ? (gm.lh * hw) * aw : 0.f);
+    hi.z = (cm & 8) ? base + row_stride + pix_stride : kNoCorner;
+    hi.w = __float_as_uint((cm & 8) ? (gm.lh * gm.lw) * aw : 0.f);
 }
 
 // address = base + off16 * 16 in ONE instruction (IMAD.WIDE.U32); the compiler otherwise
@@ -232,16 +205,6 @@ __device__ __forceinline__ float4 ldg_keep_f4(const float4 *p) {
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
 }
-__device__ __forceinline__ float2 ldg_keep_f2(const float2 *p) {
-    float2 r;
-    asm("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ float ldg_keep_f1(const float *p) {
-    float r;
-    asm("ld.global.nc.f32 %0, [%1];" : "=f"(r) : "l"(p));
-    return r;
-}
 // streamed once: do not allocate in L1
 __device__ __forceinline__ float4 ldg_stream_f4(const float4 *p) {
     float4 r;
@@ -263,19 +226,9 @@ __device__ __forceinline__ float ldg_stream_f1(const float *p) {
 __device__ __forceinline__ void stg_stream_f1(float *p, float v) {
     asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
-__device__ __forceinline__ void stg_stream_f2(float2 *p, float2 v) {
-    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y)
-                 : "memory");
-}
-// 128-bit vector reduction into global memory (sm_90+): one instruction adds four
-// consecutive floats (SASS: REDG.E.ADD.F32x4).
-__device__ __forceinline__ void red_add_f4(float4 *p, float4 v) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
-                 "f"(v.z), "f"(v.w)
-                 : "memory");
-}
 
-// Predicated forms used by the backward kernel: the validity test lives inside the asm block so
+// 128-bit vector reduction into global memory (sm_90+): one instruction adds four consecutive
+// floats (SASS: REDG.E.ADD.F32x4).  Predicated forms used by the backward kernel: the validity test lives inside the asm block so
 // that no C++ branch surrounds the access -- the loads stay freely schedulable (a batch of them is
 // issued before the first use) and the reductions keep program order without fencing the loads.
 __device__ __forceinline__ float4 ldg_keep_f4_if(const float4 *base, uint32_t off16) {
@@ -397,7 +350,7 @@ __device__ __forceinline__ void phase1_records(const LevelTable &lt, uint2 *rec,
             }
             const Geom<float> gm = decompose(x, y, lv.x, lv.y);
             uint4 lo, hi;   // {off0, w0, off1, w1}, {off2, w2, off3, w3}
-            make_record<false>(gm, aw[r], (uint32_t)lv.z, (uint32_t)lv.y, pix_stride, (uint32_t)m * 8u, lo, hi);
+            make_record(gm, aw[r], (uint32_t)lv.z, (uint32_t)lv.y, pix_stride, (uint32_t)m * 8u, lo, hi);
             rec[0 * PLANE + s] = make_uint2(lo.x, lo.y);
             rec[1 * PLANE + s] = make_uint2(lo.z, lo.w);
             rec[2 * PLANE + s] = make_uint2(hi.x, hi.y);
