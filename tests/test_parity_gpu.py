@@ -315,6 +315,23 @@ def test_error_behaviour_matches_reference(pkg):
     assert torch.equal(o1, o2)
 
 
+def test_empty_inputs_return_zero_filled_tensors(pkg):
+    """No queries / empty batch: like the reference's at::zeros outputs, without a launch."""
+    inp = pkg.synthetic.make_inputs([(4, 6), (8, 12)], 2, heads=2, points=2, num_query=5, mode="uniform")
+    d = to_dev(inp)
+    n0 = pkg.launch_count()
+    no_q = (d["value"], d["spatial_shapes"], d["level_start_index"], d["sampling_locations"][:, :0].contiguous(),
+            d["attention_weights"][:, :0].contiguous())
+    out = pkg.ms_deform_attn_forward(*no_q, 128)
+    assert out.shape == (2, 0, 64)
+    gv, gl, gw = pkg.ms_deform_attn_backward(*no_q, d["grad_output"][:, :0].contiguous(), 128)
+    assert gv.shape == d["value"].shape and not gv.any() and gl.numel() == 0 and gw.numel() == 0
+    no_b = tuple(t[:0].contiguous() if t.dim() > 2 else t for t in
+                 (d["value"], d["spatial_shapes"], d["level_start_index"], d["sampling_locations"], d["attention_weights"]))
+    assert pkg.ms_deform_attn_forward(*no_b, 128).shape == (0, 5, 64)
+    assert pkg.launch_count() == n0
+
+
 def test_dropin_module_and_autograd_function(pkg, oracle):
     """`import MultiScaleDeformableAttention as MSDA` + the reference-style autograd function."""
     pkg.install_dropin()

@@ -87,6 +87,8 @@ def _check_common(named, im2col_step, opname):
             f"level_start_index {tuple(lsi.shape)}, sampling_loc {tuple(loc.shape)}, "
             f"attn_weight {tuple(w.shape)}")
     step = min(N, int(im2col_step))
+    if N == 0:
+        return N, S, M, D, L, Lq, P
     if step <= 0 or N % step != 0:
         raise RuntimeError(f"batch({N}) must divide im2col_step({step})")     # cu:57, :124
     return N, S, M, D, L, Lq, P
@@ -99,6 +101,9 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
              ("level_start_index", level_start_index), ("sampling_loc", sampling_loc),
              ("attn_weight", attn_weight)]
     N, S, M, D, L, Lq, P = _check_common(named, im2col_step, "ms_deform_attn_forward_cuda")
+    if N * Lq * M * D == 0 or S == 0 or L * P == 0:
+        # nothing to sample: the reference returns its zero-initialised output (cu:59)
+        return torch.zeros((N, Lq, M * D), dtype=value.dtype, device=value.device)
     with torch.cuda.device(value.device):
         output = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
         with _timed("forward"):
@@ -119,6 +124,9 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     N, S, M, D, L, Lq, P = _check_common(named, im2col_step, "ms_deform_attn_backward_cuda")
     if grad_output.numel() != N * Lq * M * D:
         raise RuntimeError(f"grad_output has {grad_output.numel()} elements, expected {N * Lq * M * D}")
+    if N * Lq * M * D == 0 or S == 0 or L * P == 0:
+        # nothing to sample: all three gradients stay at the reference's zero fill (cu:126-128)
+        return [torch.zeros_like(value), torch.zeros_like(sampling_loc), torch.zeros_like(attn_weight)]
     with torch.cuda.device(value.device):
         grad_value = torch.zeros_like(value)            # accumulated by reductions (cu:126)
         grad_loc = torch.empty_like(sampling_loc)       # fully overwritten (cf. cu:127)
