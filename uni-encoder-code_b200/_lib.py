@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libmsda_b200.so")
+# MSDA_B200_LIB selects another build of the same ABI (the bounds-checked one of `make checked`)
+LIB_PATH = os.environ.get("MSDA_B200_LIB") or os.path.join(_PKG, "lib", "libmsda_b200.so")
 
 ABI_VERSION = 1
 

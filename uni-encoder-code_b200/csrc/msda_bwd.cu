@@ -93,7 +93,7 @@ msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict_
 
         // ---- phase 1: records (one plane per corner) + per-point coefficients ----
         phase1_records<FUSED, LP, Cfg::kQPW, Cfg::kPlane, true>(lt, rec, aux, loc, attw, pr, n, q0, cnt, m, M,
-                                                                d.Lq, d.L, pix_stride, lane);
+                                                                d.Lq, d.L, pix_stride, (uint32_t)d.S * pix_stride, lane);
         __syncwarp();
 
         // ---- phase 2 ----
@@ -107,24 +107,24 @@ msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict_
             const uint4 *rq = plane + qi * Cfg::kPairs;
             float dpart[LP];
 #pragma unroll
-            for (int b0 = 0; b0 < Cfg::kPairs; b0 += BATCH) {
+            for (int pb = 0; pb < Cfg::kPairs; pb += BATCH) {
                 constexpr int kB = BATCH;
                 uint4 e[kB];
                 float4 va[kB], vc[kB];
 #pragma unroll
                 for (int j = 0; j < kB; ++j)
-                    if (b0 + j < Cfg::kPairs) e[j] = lds_u4(rq + b0 + j);
+                    if (pb + j < Cfg::kPairs) e[j] = lds_u4(rq + pb + j);
 #pragma unroll
                 for (int j = 0; j < kB; ++j) {                  // 2*BATCH independent loads in flight
-                    if (b0 + j < Cfg::kPairs) {
+                    if (pb + j < Cfg::kPairs) {
                         va[j] = ldg_keep_f4_if(vb, e[j].x);
                         vc[j] = ldg_keep_f4_if(vb, e[j].z);
                     }
                 }
 #pragma unroll
                 for (int j = 0; j < kB; ++j) {
-                    if (b0 + j < Cfg::kPairs) {
-                        const int sp = 2 * (b0 + j);
+                    if (pb + j < Cfg::kPairs) {
+                        const int sp = 2 * (pb + j);
                         const float wa = __uint_as_float(e[j].y), wc = __uint_as_float(e[j].w);
                         red_add_f4_if(gvb, e[j].x, make_float4(wa * go.x, wa * go.y, wa * go.z, wa * go.w));
                         red_add_f4_if(gvb, e[j].z, make_float4(wc * go.x, wc * go.y, wc * go.z, wc * go.w));

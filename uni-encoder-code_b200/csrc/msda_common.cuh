@@ -8,6 +8,9 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#ifdef MSDA_CHECK_BOUNDS
+#include <cassert>     // `make checked`: every corner offset is asserted to lie inside its image
+#endif
 
 namespace msda {
 
@@ -155,7 +158,7 @@ __device__ __forceinline__ void warp_queries(const LevelTable &lt, int L, int g,
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void make_record(const Geom<float> &gm, float aw, uint32_t level_start,
                                             uint32_t W, uint32_t pix_stride, uint32_t head_off,
-                                            uint4 &lo, uint4 &hi) {
+                                            uint32_t image_f4, uint4 &lo, uint4 &hi) {
     const float hh = 1.f - gm.lh, hw = 1.f - gm.lw;
     // modular uint32 arithmetic: h_low / w_low may be -1; contributing corners always land on
     // a true offset < 2^31 (checked on the host)
@@ -170,6 +173,16 @@ __device__ __forceinline__ void make_record(const Geom<float> &gm, float aw, uin
     hi.y = __float_as_uint((cm & 4) ? (gm.lh * hw) * aw : 0.f);
     hi.z = (cm & 8) ? base + row_stride + pix_stride : kNoCorner;
     hi.w = __float_as_uint((cm & 8) ? (gm.lh * gm.lw) * aw : 0.f);
+#ifdef MSDA_CHECK_BOUNDS
+    // a contributing corner's row [off, off + 8) float4 must lie inside image n (image_f4 = S*M*8)
+    assert(!(cm & 1) || lo.x + 8u <= image_f4);
+    assert(!(cm & 2) || lo.z + 8u <= image_f4);
+    assert(!(cm & 4) || hi.x + 8u <= image_f4);
+    assert(!(cm & 8) || hi.z + 8u <= image_f4);
+    assert((lo.x == kNoCorner || (lo.x & 7u) == 0u) && (hi.z == kNoCorner || (hi.z & 7u) == 0u));
+#else
+    (void)image_f4;
+#endif
 }
 
 // address = base + off16 * 16 in ONE instruction (IMAD.WIDE.U32); the compiler otherwise
@@ -297,7 +310,7 @@ __device__ __forceinline__ void phase1_records(const LevelTable &lt, uint2 *rec,
                                                const float *__restrict__ loc,
                                                const float *__restrict__ attw, const Producers pr,
                                                long long n, int q0, int cnt, int m, int M, int Lq,
-                                               int L, uint32_t pix_stride, int lane) {
+                                               int L, uint32_t pix_stride, uint32_t image_f4, int lane) {
     constexpr int kRounds = (QPW * LP + 31) / 32;
     float2 xy[kRounds];
     float aw[kRounds];
@@ -350,7 +363,7 @@ __device__ __forceinline__ void phase1_records(const LevelTable &lt, uint2 *rec,
             }
             const Geom<float> gm = decompose(x, y, lv.x, lv.y);
             uint4 lo, hi;   // {off0, w0, off1, w1}, {off2, w2, off3, w3}
-            make_record(gm, aw[r], (uint32_t)lv.z, (uint32_t)lv.y, pix_stride, (uint32_t)m * 8u, lo, hi);
+            make_record(gm, aw[r], (uint32_t)lv.z, (uint32_t)lv.y, pix_stride, (uint32_t)m * 8u, image_f4, lo, hi);
             rec[0 * PLANE + s] = make_uint2(lo.x, lo.y);
             rec[1 * PLANE + s] = make_uint2(lo.z, lo.w);
             rec[2 * PLANE + s] = make_uint2(hi.x, hi.y);

@@ -79,7 +79,7 @@ msda_fwd_d32_kernel(const float *__restrict__ value, const int64_t *__restrict__
 
         // ---- phase 1: one sampling point per lane per round -> records ----
         phase1_records<FUSED, LP, Cfg::kQPW, Cfg::kPlane, false>(lt, rec, nullptr, loc, attw, pr, n, q0, cnt, m,
-                                                                 M, d.Lq, d.L, pix_stride, lane);
+                                                                 M, d.Lq, d.L, pix_stride, (uint32_t)d.S * pix_stride, lane);
         __syncwarp();
 
         // ---- phase 2: gather + weighted reduction, one query at a time ----

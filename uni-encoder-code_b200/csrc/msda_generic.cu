@@ -49,6 +49,13 @@ msda_fwd_generic_kernel(const T *__restrict__ value, const int64_t *__restrict__
                     if (g.valid && c < d.D) {
                         const T hh = 1 - g.lh, hw = 1 - g.lw;
                         const T *p0 = lb + ((long long)g.h_low * W + g.w_low) * pix + c;
+#ifdef MSDA_CHECK_BOUNDS
+                        {
+                            const T *lo = value + n * (long long)d.S * pix, *hi = lo + (long long)d.S * pix;
+                            assert(!(g.cmask & 1) || (p0 >= lo && p0 < hi));
+                            assert(!(g.cmask & 8) || (p0 + (long long)W * pix + pix >= lo && p0 + (long long)W * pix + pix < hi));
+                        }
+#endif
                         const T v1 = (g.cmask & 1) ? p0[0] : (T)0;
                         const T v2 = (g.cmask & 2) ? p0[pix] : (T)0;
                         const T v3 = (g.cmask & 4) ? p0[(long long)W * pix] : (T)0;
@@ -105,6 +112,9 @@ msda_bwd_generic_kernel(const T *__restrict__ grad_out, const T *__restrict__ va
                         for (int k = 0; k < 4; ++k) {
                             if (g.cmask >> k & 1) {
                                 const long long o = p0 + co[k] + c;
+#ifdef MSDA_CHECK_BOUNDS
+                                assert(o >= n * (long long)d.S * pix && o < (n + 1) * (long long)d.S * pix);
+#endif
                                 const T v = value[o];
                                 sh += dh[k] * v;
                                 sw += dw[k] * v;
