@@ -155,6 +155,9 @@ int msda_b200_debug_indices_f32(const int64_t *spatial_shapes, const int64_t *le
  *   "tile_order"   0 = auto (2-D tiles when the queries are laid out like the value pixels),
  *                  1 = groups of consecutive queries
  *   "ctas_per_sm"  0 = occupancy limit, k > 0 caps the persistent grid at k CTAs per SM
+ *   "whatif_drop_reds"  MEASUREMENT ONLY, breaks grad_value: k > 0 drops the grad_value reductions
+ *                  of the first k point pairs of every query (k = 4: the two coarsest of 3 levels x 4
+ *                  points) to time the best case of any pre-L2 aggregation scheme; 0 = off
  */
 int msda_b200_set_option(const char *name, int value);
 int msda_b200_get_option(const char *name, int *value);

@@ -65,6 +65,7 @@ static int option_index(const char *name) {
     if (!strcmp(name, "bwd_variant")) return OPT_BWD_VARIANT;
     if (!strcmp(name, "tile_order")) return OPT_TILE_ORDER;
     if (!strcmp(name, "ctas_per_sm")) return OPT_CTAS_PER_SM;
+    if (!strcmp(name, "whatif_drop_reds")) return OPT_WHATIF_DROP_REDS;
     return -1;
 }
 

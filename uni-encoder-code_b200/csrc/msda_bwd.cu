@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
 msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict__ value,
                     const int64_t *__restrict__ shapes, const int64_t *__restrict__ lstart,
                     const float *__restrict__ loc, const float *__restrict__ attw,
-                    const Producers pr, const Dims d, const int want_spatial,
+                    const Producers pr, const Dims d, const int flags,
                     float *__restrict__ grad_value, float *__restrict__ grad_loc,
                     float *__restrict__ grad_attw) {
     using Cfg = BwdCfg<LP, WARPS, TILE_W, QPW>;
@@ -71,7 +71,11 @@ msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict_
     float4 *aux = reinterpret_cast<float4 *>(smem_raw + Cfg::kRecBytes) + (size_t)warp * Cfg::kRecPerWarp;
 
     fill_level_table(lt, shapes, lstart, d.L, d.P, d.S, d.Lq, Cfg::kGroup, Cfg::kTileH, TILE_W,
-                     want_spatial);
+                     flags & 1);
+    // what-if knob for profiles/ only (WRONG grad_value): drop the reductions of the first
+    // `drop_pairs` record pairs of every query, i.e. of the coarsest levels -- the best case any
+    // scheme that merges those contributions before they reach L2 could hope for
+    const int drop_pairs = flags >> 1;
     __syncthreads();
 
     const int M = d.M;
@@ -126,8 +130,10 @@ msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict_
                     if (pb + j < Cfg::kPairs) {
                         const int sp = 2 * (pb + j);
                         const float wa = __uint_as_float(e[j].y), wc = __uint_as_float(e[j].w);
-                        red_add_f4_if(gvb, e[j].x, make_float4(wa * go.x, wa * go.y, wa * go.z, wa * go.w));
-                        red_add_f4_if(gvb, e[j].z, make_float4(wc * go.x, wc * go.y, wc * go.z, wc * go.w));
+                        if (pb + j >= drop_pairs) {
+                            red_add_f4_if(gvb, e[j].x, make_float4(wa * go.x, wa * go.y, wa * go.z, wa * go.w));
+                            red_add_f4_if(gvb, e[j].z, make_float4(wc * go.x, wc * go.y, wc * go.z, wc * go.w));
+                        }
                         const float da = fmaf(va[j].w, go.w, fmaf(va[j].z, go.z, fmaf(va[j].y, go.y, va[j].x * go.x)));
                         const float dc = fmaf(vc[j].w, go.w, fmaf(vc[j].z, go.z, fmaf(vc[j].y, go.y, vc[j].x * go.x)));
                         dpart[sp] = (e[j].x != kNoCorner) ? da : 0.f;      // a corner outside contributes 0
@@ -246,9 +252,9 @@ static cudaError_t launch_bwd_cfg(const float *grad_out, const float *value, con
     const long long items_ub = (long long)d.N * d.M * d.Lq;
     if (blocks > items_ub) blocks = items_ub;
     if (blocks < 1) blocks = 1;
-    const int want_spatial = option_value(OPT_TILE_ORDER) != 1;
+    const int flags = (option_value(OPT_TILE_ORDER) != 1 ? 1 : 0) | (option_value(OPT_WHATIF_DROP_REDS) << 1);
     kern<<<(unsigned)blocks, WARPS * 32, Cfg::kSmem, stream>>>(grad_out, value, shapes, lstart, loc,
-                                                              attw, pr, d, want_spatial, grad_value,
+                                                              attw, pr, d, flags, grad_value,
                                                               grad_loc, grad_attw);
     note_launch();
     return cudaGetLastError();
