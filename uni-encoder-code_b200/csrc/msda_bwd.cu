@@ -8,9 +8,12 @@
 // thread 0 add them up serially between two __syncthreads.
 //
 // Design (same work decomposition, phase 1 and record layout as msda_fwd.cu):
-//   * the L*P points of a query are consumed in two batches: all value loads of a
-//     batch are issued before the first of them is used, so a warp has 6 x 512 bytes
-//     in flight instead of paying one memory latency per point;
+//   * the L*P points of a query are consumed in batches of BATCH record pairs: the 2*BATCH
+//     value loads of a batch are issued before the first of them is used.  The shipped
+//     BATCH is 1 (64 registers, 32 warps per SM): larger batches spill or halve the
+//     occupancy and measured slower (profiles/r1_sweep.md);
+//   * the corner validity test lives inside the asm of the load / reduction (@p ld / @p red),
+//     so no C++ branch surrounds them;
 //   * lane = corner*8 + chunk.  Per sampling point a lane loads 16 bytes of its
 //     corner's value row, forms the partial dot product with its 4 grad_output
 //     channels (d) and adds weight*grad_output to grad_value with ONE 128-bit
@@ -41,7 +44,7 @@ struct BwdCfg {
     static constexpr int kRounds = (kQPW * LP + 31) / 32;
     static constexpr int kRecPerWarp = kQPW * LP;
     static constexpr int kPlane = kRecPerWarp + 2;   // padded corner-plane stride, see msda_fwd.cu
-    // per warp: 4 corner planes of {offset, weight} + one {lh, lw, aw*W, aw*H} per point
+    // per warp: 4 corner planes of {offset, weight} + one {lh, lw, attention weight, level} per point
     static constexpr size_t kRecBytes = (size_t)WARPS * 4 * kPlane * sizeof(uint2);
     static constexpr size_t kSmem = kRecBytes + (size_t)WARPS * kRecPerWarp * sizeof(float4);
     // sizes along the two reduce-scatters
