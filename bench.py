@@ -273,7 +273,11 @@ def run_b200_arm(args):
     # ---- end to end through the plugin API with host buffers (rank-local, then max over ranks)
     e2e = None
     if not args.no_e2e:
+        old_affinity = bind_near_gpu(local_rank)
         e2e = run_e2e(pkg, host, dev, world, max(4, min(args.steps, 20)), dist if world > 1 else None)
+        e2e["cpus_bound"] = len(os.sched_getaffinity(0))
+        if old_affinity:
+            os.sched_setaffinity(0, old_affinity)
 
     if rank != 0:
         if world > 1:
@@ -376,6 +380,25 @@ def reference_cuda_same_gpu(pkg, d, flush, iters=5):
                         "incl. its own zero-fills; see profiles/r1_vs_reference_cuda.md"}
     except Exception as e:      # a comparison aid must never break the bench line
         return {"unavailable": repr(e)[:200]}
+
+
+def bind_near_gpu(index):
+    """Pin this process to the CPUs NVML reports as local to GPU `index` (intersected with what the
+    container allows), so the pinned host buffers of the e2e leg are first-touched on the GPU's NUMA
+    node.  Returns the previous affinity (restored before the CPU baseline uses every core)."""
+    try:
+        import pynvml
+        before = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(before) // 64) + 1)
+        near = {i * 64 + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        pick = near & before
+        if pick and pick != before:
+            os.sched_setaffinity(0, pick)
+        return before
+    except Exception:
+        return None
 
 
 def run_e2e(pkg, host, dev, world, steps, dist):
