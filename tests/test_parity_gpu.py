@@ -451,3 +451,31 @@ def test_matches_reference_cuda_op_on_same_gpu(pkg):
         g_new = pkg.ms_deform_attn_backward(*a, d["grad_output"], 128)
         for x, y in zip(g_new, g_ref):
             assert rel_err(x.cpu().numpy(), y.cpu().numpy()) <= GRAD_REL_TOL
+
+
+def test_reference_python_stack_runs_unchanged_on_the_shim(pkg, oracle):
+    """Where both a GPU and the reference checkout exist: the reference's own MSDeformAttnFunction
+    (func.py:35-52) and MSDeformAttn module (ms_deform_attn.py), imported unmodified, run on the
+    drop-in `MultiScaleDeformableAttention` module.  (Skipped on the GPU box, which has no checkout,
+    and in the build container, which has no GPU.)"""
+    import ref_import
+    if not ref_import.available():
+        pytest.skip("reference checkout not present")
+    pkg.install_dropin()                       # before the reference imports MultiScaleDeformableAttention
+    ns = ref_import.load()
+    import importlib
+    func = importlib.import_module("refmodeling.pixel_decoder.ops.functions.ms_deform_attn_func")
+    inp = pkg.synthetic.make_inputs([(6, 10), (12, 20), (24, 40)], 2, mode="model", seed=11)
+    d = to_dev(inp)
+    v = d["value"].clone().requires_grad_(True)
+    loc = d["sampling_locations"].clone().requires_grad_(True)
+    w = d["attention_weights"].clone().requires_grad_(True)
+    out = func.MSDeformAttnFunction.apply(v, d["spatial_shapes"], d["level_start_index"], loc, w, 128)
+    out.backward(d["grad_output"])
+    check_against(out.detach(), v.grad, loc.grad, w.grad, *oracle_refs(oracle, inp), tag="reference stack")
+    attn = ns.MSDeformAttn(256, 3, 8, 4).to(DEV)
+    S = v.shape[1]
+    q = torch.randn(2, S, 256, device=DEV)
+    ref_pts = pkg.modules.reference_points_for([(6, 10), (12, 20), (24, 40)], DEV).expand(2, -1, -1, -1)
+    y = attn(q, ref_pts, q, d["spatial_shapes"], d["level_start_index"])
+    assert y.shape == (2, S, 256) and torch.isfinite(y).all()
