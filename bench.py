@@ -453,20 +453,27 @@ def run_e2e(pkg, host, dev, world, steps, dist):
                 r.record_stream(s_out)
             out_done[b].record(s_out)
 
-    for i in range(4):
+    # warm-up: first-touch of the pinned buffers, allocator pools, and the PCIe link leaving its idle
+    # state (the first transfers of a fresh process were measured ~40 % slower)
+    for i in range(16):
         one(i)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(cur)
-    for i in range(steps):
-        one(i)
-    cur.wait_stream(s_out)
-    cur.wait_stream(s_in)
-    e1.record(cur)
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    # the host side (pinned memory, PCIe root) is shared with other tenants of the box: three
+    # repetitions of `steps` steps, the fastest one is reported (all three are listed)
+    trials = []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(cur)
+        for i in range(steps):
+            one(i)
+        cur.wait_stream(s_out)
+        cur.wait_stream(s_in)
+        e1.record(cur)
+        torch.cuda.synchronize()
+        trials.append(e0.elapsed_time(e1))
+    ms = min(trials)
     if dist is not None:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -474,9 +481,10 @@ def run_e2e(pkg, host, dev, world, steps, dist):
     q = host["value"].shape[0] * host["sampling_locations"].shape[1]
     return {"value": world * q * steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h, "ms_per_step": ms / steps, "steps": steps,
+            "trials_ms_per_step": [t / steps for t in trials],
             "api": "MSDeformAttnFunction.apply + autograd.grad; pinned host -> device inputs and "
                    "device -> pinned host results every step, copies overlapped with compute on "
-                   "3 streams (double-buffered)"}
+                   "3 streams (double-buffered); fastest of 3 repetitions of `steps` steps"}
 
 
 def main():
