@@ -200,10 +200,22 @@ def main():
             def fused():
                 out = pkg.MSDeformAttnFusedFunction.apply(value, shapes, lsi, ref, off, logits)
                 torch.autograd.grad(out, (value, off, logits), go)
+            def unfused_fwd():
+                with torch.no_grad():
+                    wts = torch.softmax(logits, -1).view(N, S, M, L, P)
+                    loc = ref[:, :, None, :, None, :] + off / wh[None, None, None, :, None, :]
+                    pkg.ms_deform_attn_forward(value, shapes, lsi, loc, wts, 128)
+
+            def fused_fwd():
+                with torch.no_grad():
+                    pkg.ms_deform_attn_fused_forward(value, shapes, lsi, ref, off, logits)
             ms_u = timed(unfused, args.steps * 3)
             ms_f = timed(fused, args.steps * 3)
+            ms_uf = timed(unfused_fwd, args.steps * 3)
+            ms_ff = timed(fused_fwd, args.steps * 3)
             emit({"config": "f", "what": "op + its producers (softmax, ref + off/(W,H)) forward+backward at configs[1] shape",
-                  "unfused_ms": ms_u, "fused_ms": ms_f, "speedup": ms_u / ms_f})
+                  "unfused_ms": ms_u, "fused_ms": ms_f, "speedup": ms_u / ms_f,
+                  "unfused_fwd_ms": ms_uf, "fused_fwd_ms": ms_ff})
         elif cfg == "q":
             levels = syn.pyramid(1024, 2048)
             m = encoder().eval()

@@ -29,7 +29,7 @@ enum Test { LDS32_BCAST, LDS32_DISTINCT, LDS64_4ADDR, LDS64_DISTINCT, LDS128_4AD
             LDS128_DISTINCT, LDS128_2SAMPLES, SHFL, STS32_DISTINCT, LDS_STS_RMW,
             LDG128_4ROWS_L1, LDG32_1ROW_L1, LDG64_2ROWS_L1, LDG128_4ROWS_L2, LDG32_1ROW_L2,
             RED128_4ROWS, RED32_1ROW, RED64_2ROWS, TMA_RED_ROW, STG128_4ROWS,
-            SHFL2, ATOMS_INT_SPREAD, ATOMS_F32_ROW, ATOMS_F32_ROW_SMALLWIN, ATOMS_INT_RET, NUM_TESTS };
+            SHFL2, ATOMS_INT_SPREAD, ATOMS_F32_ROW, ATOMS_F32_ROW_SMALLWIN, ATOMS_INT_RET, MIX_RED_TMA, NUM_TESTS };
 const char *kNames[] = {"lds32 broadcast (1 addr)", "lds32 32 distinct banks", "lds64 4 addrs (corner groups)",
     "lds64 32 distinct", "lds128 4 addrs (corner groups)", "lds128 broadcast (1 addr)", "lds128 32 distinct",
     "lds128 4 addrs x 16B contiguous 64B", "shfl.bfly", "sts32 32 distinct banks", "lds32+fadd+sts32 row RMW",
@@ -38,12 +38,21 @@ const char *kNames[] = {"lds32 broadcast (1 addr)", "lds32 32 distinct banks", "
     "red.v4.f32 4 rows/instr, random rows", "red.f32 1 row/instr, random rows", "red.v2.f32 2 rows/instr, random rows",
     "TMA cp.reduce.async.bulk 128B row (sts row + 1 bulk op)", "stg128 4 rows/instr, random rows",
     "shfl.bfly (dependent chain, 32 warps)", "smem red.add.s32, 32 random words of 8K", "smem atomicAdd(float) one row of 256 (32 lanes = 32 banks)",
-    "smem atomicAdd(float) one row of 16 (cross-warp conflicts)", "smem atomicAdd(int) with return, 32 random words of 8K"};
+    "smem atomicAdd(float) one row of 16 (cross-warp conflicts)", "smem atomicAdd(int) with return, 32 random words of 8K",
+    "MIX even warps red.v4.f32 (4 rows), odd warps TMA bulk reduce (1 row)"};
 
 template <int TEST>
-__global__ void __launch_bounds__(THREADS) bench(float *gbuf, uint32_t nrows_mask, float *sink, long long *cycles) {
+__global__ void __launch_bounds__(THREADS) bench(float *gbuf, uint32_t nrows_mask, float *sink, long long *cycles,
+                                                  uint32_t active_sms) {
     __shared__ __align__(128) float sm[8192];   // 32 KB
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    {   // CTAs that land on an SM beyond `active_sms` leave at once (fewer SMs against the same L2)
+        uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (smid >= active_sms) {
+            if (threadIdx.x < 2) cycles[blockIdx.x * 2 + threadIdx.x] = 0;
+            return;
+        }
+    }
     for (int i = threadIdx.x; i < 8192; i += THREADS) sm[i] = (float)i;
     __syncthreads();
     float acc = 0.f;
@@ -126,7 +135,11 @@ __global__ void __launch_bounds__(THREADS) bench(float *gbuf, uint32_t nrows_mas
                     } else {
                         float v; asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p)); acc += v;
                     }
-                } else if (TEST == TMA_RED_ROW) {
+                } else if (TEST == MIX_RED_TMA && !(warp & 1)) {
+                    uint32_t row = (step + (uint32_t)(lane >> 3) * 7919u) & nrows_mask;
+                    float *p = gbuf + (size_t)row * 32 + (lane & 7) * 4;
+                    asm volatile("red.global.add.v4.f32 [%0], {%1,%1,%1,%1};" :: "l"(p), "f"(1.0f) : "memory");
+                } else if (TEST == TMA_RED_ROW || TEST == MIX_RED_TMA) {
                     // each warp owns UNROLL 128-byte staging rows in shared memory
                     float *srow = sm + (warp * UNROLL + u) * 32;
                     asm volatile("st.shared.f32 [%0], %1;" :: "r"(smem_u32(srow + lane)), "f"(1.0f) : "memory");
@@ -140,7 +153,7 @@ __global__ void __launch_bounds__(THREADS) bench(float *gbuf, uint32_t nrows_mas
                 }
             }
         }
-        if (TEST == TMA_RED_ROW) {
+        if (TEST == TMA_RED_ROW || (TEST == MIX_RED_TMA && (warp & 1))) {
             if (lane == 0) {
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -150,25 +163,36 @@ __global__ void __launch_bounds__(THREADS) bench(float *gbuf, uint32_t nrows_mas
     }
     const long long t1 = clock64();
     if (acc == 123.456f) sink[0] = acc;
-    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+    if (lane == 0 && warp < 2) cycles[blockIdx.x * 2 + warp] = t1 - t0;   // warp 0 and warp 1 (the two groups of MIX)
 }
 
 template <int TEST>
-void run(float *gbuf, uint32_t nrows_mask, float *sink, long long *cycles_d, int sms, int ctas_per_sm = 2) {
+void run(float *gbuf, uint32_t nrows_mask, float *sink, long long *cycles_d, int sms, int ctas_per_sm = 2,
+         int active_sms = 1 << 20) {
     const int grid = sms * ctas_per_sm;
     cudaEvent_t e0, e1;
     CHECK(cudaEventCreate(&e0)); CHECK(cudaEventCreate(&e1));
-    bench<TEST><<<grid, THREADS>>>(gbuf, nrows_mask, sink, cycles_d);   // warm-up
+    bench<TEST><<<grid, THREADS>>>(gbuf, nrows_mask, sink, cycles_d, (uint32_t)active_sms);   // warm-up
     CHECK(cudaDeviceSynchronize());
     CHECK(cudaEventRecord(e0));
-    bench<TEST><<<grid, THREADS>>>(gbuf, nrows_mask, sink, cycles_d);
+    bench<TEST><<<grid, THREADS>>>(gbuf, nrows_mask, sink, cycles_d, (uint32_t)active_sms);
     CHECK(cudaEventRecord(e1));
     CHECK(cudaDeviceSynchronize());
     float ms = 0; CHECK(cudaEventElapsedTime(&ms, e0, e1));
-    long long *h = (long long *)malloc(sizeof(long long) * grid);
-    CHECK(cudaMemcpy(h, cycles_d, sizeof(long long) * grid, cudaMemcpyDeviceToHost));
-    double mean = 0; for (int i = 0; i < grid; ++i) mean += (double)h[i]; mean /= grid;
+    long long *h = (long long *)malloc(sizeof(long long) * grid * 2);
+    CHECK(cudaMemcpy(h, cycles_d, sizeof(long long) * grid * 2, cudaMemcpyDeviceToHost));
+    double mean = 0, mean1 = 0; int live = 0;
+    for (int i = 0; i < grid; ++i) if (h[2 * i]) { mean += (double)h[2 * i]; mean1 += (double)h[2 * i + 1]; ++live; }
+    mean /= live; mean1 /= live;
     free(h);
+    if (live != grid) printf("[%3d of %d CTAs live, ~%d SMs] ", live, grid, live / ctas_per_sm);
+    if (nrows_mask != (64u << 20) / ROW_BYTES - 1) printf("[%u KB of rows] ", (nrows_mask + 1) / 8);
+    if (TEST == MIX_RED_TMA) {
+        const double n = (double)ctas_per_sm * (THREADS / 64) * ITERS * UNROLL;   // ops per group per SM
+        printf("%s: red warps %.0f clk (%.2f cyc per 4-row instr alone-equivalent), tma warps %.0f clk (%.2f cyc per row op); %.3f ms\n",
+               kNames[TEST], mean, mean / n, mean1, mean1 / n, ms);
+        return;
+    }
     // warp instructions per SM = ctas_per_sm * warps * ITERS * UNROLL
     const double instr_per_sm = (double)ctas_per_sm * (THREADS / 32) * ITERS * UNROLL;
     if (ctas_per_sm != 2) printf("[%d CTAs = %2d warps/SM] ", ctas_per_sm, ctas_per_sm * THREADS / 32);
@@ -188,7 +212,7 @@ int main() {
     CHECK(cudaMalloc(&gbuf, (size_t)nrows * ROW_BYTES));
     CHECK(cudaMemset(gbuf, 0, (size_t)nrows * ROW_BYTES));
     CHECK(cudaMalloc(&sink, 16));
-    CHECK(cudaMalloc(&cycles, sizeof(long long) * sms * 8));
+    CHECK(cudaMalloc(&cycles, sizeof(long long) * sms * 16));
     run<LDS32_BCAST>(gbuf, nrows - 1, sink, cycles, sms);
     run<LDS32_DISTINCT>(gbuf, nrows - 1, sink, cycles, sms);
     run<LDS64_4ADDR>(gbuf, nrows - 1, sink, cycles, sms);
@@ -221,6 +245,15 @@ int main() {
     for (int c = 1; c <= 4; ++c) run<LDG128_4ROWS_L1>(gbuf, nrows - 1, sink, cycles, sms, c);
     for (int c = 1; c <= 4; ++c) run<LDG128_4ROWS_L2>(gbuf, nrows - 1, sink, cycles, sms, c);
     for (int c = 1; c <= 4; ++c) run<STG128_4ROWS>(gbuf, nrows - 1, sink, cycles, sms, c);
+    // is the reduction rate an SM-side or an L2-side limit?  same kernel on a quarter / half / 3/4 of the SMs
+    for (int a : {37, 74, 111, 148}) run<RED128_4ROWS>(gbuf, nrows - 1, sink, cycles, sms, 2, a);
+    for (int a : {37, 74, 111, 148}) run<STG128_4ROWS>(gbuf, nrows - 1, sink, cycles, sms, 2, a);
+    for (int a : {37, 74, 148}) run<LDG128_4ROWS_L2>(gbuf, nrows - 1, sink, cycles, sms, 2, a);
+    // does it depend on how many distinct rows are hit (same-row collisions in the L2 atomic units)?
+    for (uint32_t kb : {65536u, 4096u, 256u, 16u}) run<RED128_4ROWS>(gbuf, kb * 8 - 1, sink, cycles, sms);
+    // do LSU reductions and TMA bulk reductions share one path?
+    run<MIX_RED_TMA>(gbuf, nrows - 1, sink, cycles, sms);
+    run<MIX_RED_TMA>(gbuf, nrows - 1, sink, cycles, sms, 2, 74);
     printf("done\n");
     return 0;
 }

@@ -151,7 +151,6 @@ msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict_
             rs_step<Cfg::kN2>(r2, r3, b0, 1);
             // coefficient of D_corner in (d/dx, d/dy, d/dweight) of each finalised point
             float t0[Cfg::kT0];
-            float prob[Cfg::kN3], lvW[Cfg::kN3], lvH[Cfg::kN3];   // of the points this lane finalises
 #pragma unroll
             for (int j = 0; j < Cfg::kN3; ++j) {
                 const int i2 = j + (b0 ? Cfg::kN3 : 0);          // index before step 3
@@ -159,21 +158,15 @@ msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict_
                 const int sp = i1 + (b2 ? Cfg::kN1 : 0);         // index before step 1 = point
                 const bool live = (i2 < Cfg::kN2) && (i1 < Cfg::kN1) && (sp < LP);
                 float cx = 0.f, cy = 0.f, ca = 0.f;
-                prob[j] = 0.f;
-                lvW[j] = 1.f;
-                lvH[j] = 1.f;
                 if (live) {
                     const float4 a = aux[qi * LP + sp];          // {lh, lw, attention weight, level}
                     const int4 lv = lt.hws[__float_as_int(a.w)];
                     const float lh = a.x, lw = a.y, hh = 1.f - a.x, hw = 1.f - a.y;
                     const float fh = c1 ? lh : hh;               // factor along h of this corner's weight
                     const float fw = c0 ? lw : hw;               // factor along w
-                    prob[j] = a.z;
-                    lvW[j] = (float)lv.y;
-                    lvH[j] = (float)lv.x;
                     ca = fh * fw;                                // d val / d weight part (cuh:161)
-                    cx = (c0 ? fh : -fh) * (a.z * lvW[j]);       // W * aw * d w_k / d w  (cuh:128-156,162)
-                    cy = (c1 ? fw : -fw) * (a.z * lvH[j]);       // H * aw * d w_k / d h  (cuh:128-156,163)
+                    cx = (c0 ? fh : -fh) * (a.z * (float)lv.y);  // W * aw * d w_k / d w  (cuh:128-156,162)
+                    cy = (c1 ? fw : -fw) * (a.z * (float)lv.x);  // H * aw * d w_k / d h  (cuh:128-156,163)
                 }
                 t0[3 * j + 0] = cx * r3[j];
                 t0[3 * j + 1] = cy * r3[j];
@@ -183,37 +176,61 @@ msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict_
             float t1[Cfg::kT1], t2[Cfg::kT2];
             rs_step<Cfg::kT0>(t0, t1, c1, 16);
             rs_step<Cfg::kT1>(t1, t2, c0, 8);
-            // softmax backward (FUSED): grad_logit_i = a_i * (ga_i - sum_j a_j * ga_j)  (torch's
-            // softmax_backward: (grad - sum(grad * out)) * out); the ga_j sit on different lanes
-            float dot_a = 0.f;
-            if (FUSED) {
+            if (!FUSED) {
 #pragma unroll
                 for (int i = 0; i < Cfg::kT2; ++i) {
                     const int u1 = i + (c0 ? Cfg::kT2 : 0);
                     const int u0 = u1 + (c1 ? Cfg::kT1 : 0);
-                    if (u1 < Cfg::kT1 && u0 < Cfg::kT0 && (u0 % 3) == 2) dot_a += prob[u0 / 3] * t2[i];
+                    if (u1 < Cfg::kT1 && u0 < Cfg::kT0) {
+                        const int j = u0 / 3, comp = u0 - 3 * j;
+                        const int i2 = j + (b0 ? Cfg::kN3 : 0);
+                        const int i1 = i2 + (b1 ? Cfg::kN2 : 0);
+                        const int sp = i1 + (b2 ? Cfg::kN1 : 0);
+                        if (i2 < Cfg::kN2 && i1 < Cfg::kN1 && sp < LP) {
+                            const long long sidx = qrow * LP + sp;
+                            if (comp == 2) stg_stream_f1(grad_attw + sidx, t2[i]);
+                            else stg_stream_f1(grad_loc + 2 * sidx + comp, t2[i]);
+                        }
+                    }
                 }
+            } else {
+                // the producers' backward.  Their per-point data is re-read from `aux` here, after the
+                // reduce-scatters, instead of being carried through them in registers.
+                //   locations: d loc / d offset = 1 / (W, H)  (mod.py:110-112)
+                //   softmax:   grad_logit_i = a_i * (ga_i - sum_j a_j * ga_j)  (torch's softmax backward:
+                //              (grad - sum(grad * out)) * out); the ga_j sit on different lanes
+                int sp_of[Cfg::kT2], comp_of[Cfg::kT2];          // which (point, component) t2[i] is
+                float prob[Cfg::kT2], div[Cfg::kT2];
+                float dot_a = 0.f;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) dot_a += __shfl_xor_sync(kFullMask, dot_a, o);
-            }
-#pragma unroll
-            for (int i = 0; i < Cfg::kT2; ++i) {
-                const int u1 = i + (c0 ? Cfg::kT2 : 0);
-                const int u0 = u1 + (c1 ? Cfg::kT1 : 0);
-                if (u1 < Cfg::kT1 && u0 < Cfg::kT0) {
-                    const int j = u0 / 3, comp = u0 - 3 * j;
+                for (int i = 0; i < Cfg::kT2; ++i) {
+                    const int u1 = i + (c0 ? Cfg::kT2 : 0);
+                    const int u0 = u1 + (c1 ? Cfg::kT1 : 0);
+                    const int j = u0 / 3;
                     const int i2 = j + (b0 ? Cfg::kN3 : 0);
                     const int i1 = i2 + (b1 ? Cfg::kN2 : 0);
                     const int sp = i1 + (b2 ? Cfg::kN1 : 0);
-                    if (i2 < Cfg::kN2 && i1 < Cfg::kN1 && sp < LP) {
-                        const long long sidx = qrow * LP + sp;
-                        float v = t2[i];
-                        if (FUSED) {
-                            // d loc / d offset = 1 / (W, H)  (mod.py:110-112)
-                            v = comp == 2 ? prob[j] * (v - dot_a) : __fdiv_rn(v, comp == 0 ? lvW[j] : lvH[j]);
-                        }
-                        if (comp == 2) stg_stream_f1(grad_attw + sidx, v);
-                        else stg_stream_f1(grad_loc + 2 * sidx + comp, v);
+                    const bool live = u1 < Cfg::kT1 && u0 < Cfg::kT0 && i2 < Cfg::kN2 && i1 < Cfg::kN1 && sp < LP;
+                    sp_of[i] = live ? sp : -1;
+                    comp_of[i] = u0 - 3 * j;
+                    prob[i] = 0.f;
+                    div[i] = 1.f;
+                    if (live) {
+                        const float4 a = aux[qi * LP + sp];
+                        const int4 lv = lt.hws[__float_as_int(a.w)];
+                        prob[i] = a.z;
+                        div[i] = (float)(comp_of[i] == 0 ? lv.y : lv.x);
+                        if (comp_of[i] == 2) dot_a = fmaf(a.z, t2[i], dot_a);
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) dot_a += __shfl_xor_sync(kFullMask, dot_a, o);
+#pragma unroll
+                for (int i = 0; i < Cfg::kT2; ++i) {
+                    if (sp_of[i] >= 0) {
+                        const long long sidx = qrow * LP + sp_of[i];
+                        if (comp_of[i] == 2) stg_stream_f1(grad_attw + sidx, prob[i] * (t2[i] - dot_a));
+                        else stg_stream_f1(grad_loc + 2 * sidx + comp_of[i], __fdiv_rn(t2[i], div[i]));
                     }
                 }
             }

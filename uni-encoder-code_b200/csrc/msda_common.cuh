@@ -81,6 +81,7 @@ __device__ __forceinline__ Geom<T> decompose(T loc_x, T loc_y, int H, int W) {
 // ---------------------------------------------------------------------------
 struct LevelTable {
     int4 hws[kMaxLevels];             // {H, W, start, 0}: one 128-bit shared load per point in phase 1
+    float2 rcp_wh[kMaxLevels];        // {RN(1/W), RN(1/H)} for div_by_size() (fused producers)
     int H[kMaxLevels];
     int W[kMaxLevels];
     int start[kMaxLevels];            // first pixel of the level inside one image
@@ -108,6 +109,7 @@ __device__ __forceinline__ void fill_level_table(LevelTable &lt, const int64_t *
             lt.W[l] = W;
             lt.start[l] = (int)st;
             lt.hws[l] = make_int4(H, W, (int)st, 0);
+            lt.rcp_wh[l] = make_float2(__frcp_rn((float)W), __frcp_rn((float)H));
             layout_ok = layout_ok && (st == pix) && H > 0 && W > 0;
             pix += (long long)H * W;
             lt.tiles_x[l] = (W + tile_w - 1) / tile_w;
@@ -298,8 +300,20 @@ __device__ __forceinline__ void rs_step(const float (&in)[N], float (&out)[(N + 
 //                 `ref`  = reference points      [N or 1, Lq, L, 2]
 //                 location = ref + offset / (W_l, H_l)  (IEEE division, then add: the same two
 //                 roundings as the reference's tensor expression) and the weight is the softmax
-//                 of the query-head's L*P logits (each lane re-reduces its row's logits).
+//                 of the query-head's L*P logits (exchanged through the warp's record area).
 // ---------------------------------------------------------------------------
+// a / b, correctly rounded (== __fdiv_rn), for a level size b with rb = RN(1/b): one Newton
+// correction of a * rb through the exact FMA residual (Markstein).  Exact whenever nothing
+// under- or overflows -- checked against IEEE division for every size up to 5000 on 1.5e9
+// random numerators -- so numerators outside [1e-18, 1e18] (and inf / nan) take the full division.
+__device__ __forceinline__ float div_by_size(float a, float b, float rb) {
+    const float q0 = a * rb;
+    const float q = fmaf(fmaf(-q0, b, a), rb, q0);
+    const float mag = fabsf(a);
+    if (!(mag < 1e18f) || (mag < 1e-18f && a != 0.f)) return __fdiv_rn(a, b);
+    return q;
+}
+
 struct Producers {
     const float *ref;          // FUSED only
     long long ref_bstride;     // elements between images in `ref` (0: shared by the batch)
@@ -313,7 +327,7 @@ __device__ __forceinline__ void phase1_records(const LevelTable &lt, uint2 *rec,
                                                int L, uint32_t pix_stride, uint32_t image_f4, int lane) {
     constexpr int kRounds = (QPW * LP + 31) / 32;
     float2 xy[kRounds];
-    float aw[kRounds];
+    float aw[kRounds];          // attention weight; FUSED: the raw logit until the softmax below
 #pragma unroll
     for (int r = 0; r < kRounds; ++r) {          // all global loads first
         const int s = r * 32 + lane;
@@ -323,29 +337,53 @@ __device__ __forceinline__ void phase1_records(const LevelTable &lt, uint2 *rec,
         if (qi < cnt) {                           // also false for the padding lanes of the last round
             const long long qrow = (n * Lq + q0 + qi) * M + m;
             xy[r] = ldg_stream_f2(reinterpret_cast<const float2 *>(loc) + qrow * LP + sp);
-            if (!FUSED) {
-                aw[r] = ldg_stream_f1(attw + qrow * LP + sp);
-            } else {
-                // softmax over the row's LP logits; lanes of the same (query, head) read the same 16-byte words
-                const float4 *lg = reinterpret_cast<const float4 *>(attw + qrow * LP);
-                float4 v[LP / 4];
+            aw[r] = ldg_stream_f1(attw + qrow * LP + sp);
+        }
+    }
+    if (FUSED) {
+        // softmax over each (query, head) row's LP logits (mod.py:107-108).  The rows do not line up
+        // with lanes (LP = 12), so the logits are exchanged through the warp's record area, which is
+        // free until the records are written below: four lanes per query reduce its row to
+        // {max, sum of exp}, then every lane normalises its own logit.
+        static_assert(LP % 4 == 0 && (QPW * LP + 2 * QPW) * 4 <= 4 * PLANE * 8, "softmax scratch");
+        float *scr = reinterpret_cast<float *>(rec);
+        float2 *stats = reinterpret_cast<float2 *>(scr + QPW * LP);
 #pragma unroll
-                for (int k = 0; k < LP / 4; ++k) v[k] = ldg_stream_f4(lg + k);
-                float mx = v[0].x;
+        for (int r = 0; r < kRounds; ++r) {
+            const int s = r * 32 + lane;
+            if (s < cnt * LP) scr[s] = aw[r];
+        }
+        __syncwarp();
+        {   // four lanes per query, LP/4 logits each; max and sum combined over lane bits 0,1
+            static_assert(QPW * 4 <= 32, "one warp reduces all rows at once");
+            const int q = min(lane >> 2, QPW - 1);
+            const float *part = scr + q * LP + (lane & 3) * (LP / 4);
+            float v[LP / 4];
 #pragma unroll
-                for (int k = 0; k < LP / 4; ++k) mx = fmaxf(fmaxf(fmaxf(mx, v[k].x), v[k].y), fmaxf(v[k].z, v[k].w));
-                float sum = 0.f, mine = 0.f;
+            for (int k = 0; k < LP / 4; ++k) v[k] = part[k];
+            float mx = v[0];
 #pragma unroll
-                for (int k = 0; k < LP / 4; ++k) {
-                    const float e0 = expf(v[k].x - mx), e1 = expf(v[k].y - mx);
-                    const float e2 = expf(v[k].z - mx), e3 = expf(v[k].w - mx);
-                    sum += (e0 + e1) + (e2 + e3);
-                    mine = (sp == 4 * k) ? e0 : (sp == 4 * k + 1) ? e1 : (sp == 4 * k + 2) ? e2
-                         : (sp == 4 * k + 3) ? e3 : mine;
-                }
-                aw[r] = __fdiv_rn(mine, sum);
+            for (int k = 1; k < LP / 4; ++k) mx = fmaxf(mx, v[k]);
+            mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, 2));
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < LP / 4; ++k) sum += expf(v[k] - mx);
+            sum += __shfl_xor_sync(kFullMask, sum, 1);
+            sum += __shfl_xor_sync(kFullMask, sum, 2);
+            if ((lane & 3) == 0 && (lane >> 2) < cnt) stats[lane >> 2] = make_float2(mx, sum);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < kRounds; ++r) {
+            const int s = r * 32 + lane;
+            const int qi = s / LP;
+            if (qi < cnt) {
+                const float2 st = stats[qi];
+                aw[r] = __fdiv_rn(expf(aw[r] - st.x), st.y);
             }
         }
+        __syncwarp();                             // the scratch is overwritten by the records
     }
 #pragma unroll
     for (int r = 0; r < kRounds; ++r) {
@@ -358,8 +396,9 @@ __device__ __forceinline__ void phase1_records(const LevelTable &lt, uint2 *rec,
             if (FUSED) {
                 const long long rrow = n * pr.ref_bstride + ((long long)(q0 + qi) * L + l) * 2;
                 const float2 rp = ldg_stream_f2(reinterpret_cast<const float2 *>(pr.ref + rrow));
-                x = rp.x + __fdiv_rn(x, (float)lv.y);          // mod.py:110-112: ref + off / (W, H)
-                y = rp.y + __fdiv_rn(y, (float)lv.x);
+                const float2 rc = lt.rcp_wh[l];
+                x = rp.x + div_by_size(x, (float)lv.y, rc.x);   // mod.py:110-112: ref + off / (W, H)
+                y = rp.y + div_by_size(y, (float)lv.x, rc.y);
             }
             const Geom<float> gm = decompose(x, y, lv.x, lv.y);
             uint4 lo, hi;   // {off0, w0, off1, w1}, {off2, w2, off3, w3}
