@@ -19,6 +19,7 @@ constexpr int THREADS = 512;
 constexpr int ITERS = 256;
 constexpr int UNROLL = 8;
 constexpr int ROW_BYTES = 128;
+constexpr int NS_SLOT = 148 * 16;   // cycles[NS_SLOT..+1]: wall nanoseconds and cycles of CTA 0 (actual SM clock)
 
 __device__ __forceinline__ uint32_t hash32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16; return x;
@@ -69,6 +70,8 @@ __global__ void __launch_bounds__(THREADS) bench(float *gbuf, uint32_t nrows_mas
     if (TEST == LDS128_DISTINCT) lane_base = lane * 4;
     if (TEST == LDS128_2SAMPLES) lane_base = (lane >> 3) * 4;     // 4 contiguous 16-byte slots
     const uint32_t sbase = smem_u32(sm + lane_base);
+    unsigned long long ns0, ns1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
     const long long t0 = clock64();
     for (int it = 0; it < ITERS; ++it) {
 #pragma unroll
@@ -162,8 +165,96 @@ __global__ void __launch_bounds__(THREADS) bench(float *gbuf, uint32_t nrows_mas
         }
     }
     const long long t1 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
     if (acc == 123.456f) sink[0] = acc;
-    if (lane == 0 && warp < 2) cycles[blockIdx.x * 2 + warp] = t1 - t0;   // warp 0 and warp 1 (the two groups of MIX)
+    // the CTA's time is that of its LAST warp (the LSU serves older warps first: warp 0 alone finishes
+    // its loop well before the CTA's reductions are all issued); even / odd warps separately for MIX
+    __shared__ unsigned long long last[2];
+    if (threadIdx.x < 2) last[threadIdx.x] = 0;
+    __syncthreads();
+    if (lane == 0) atomicMax(&last[TEST == MIX_RED_TMA ? (warp & 1) : 0], (unsigned long long)(t1 - t0));
+    __syncthreads();
+    if (threadIdx.x < 2) cycles[blockIdx.x * 2 + threadIdx.x] = (long long)last[threadIdx.x];
+    if (threadIdx.x == 0 && blockIdx.x == 0) { cycles[NS_SLOT] = (long long)(ns1 - ns0); cycles[NS_SLOT + 1] = t1 - t0; }
+}
+
+
+// Do LSU reductions (red.global.add.v4.f32) and TMA bulk reductions (cp.reduce.async.bulk) leave the
+// SM through one path or two?  Every warp issues, per iteration, R4 four-row vector reductions and T
+// one-row bulk reductions from a double-buffered staging ring (the previous iteration's bulk group
+// may still be reading while this one is filled), so both engines are kept busy together.
+template <int R4, int T>
+__global__ void __launch_bounds__(THREADS) mix2(float *gbuf, uint32_t nrows_mask, long long *cycles) {
+    constexpr int TT = T > 0 ? T : 1;
+    __shared__ __align__(128) float stage[THREADS / 32][2][TT][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t h = hash32(blockIdx.x * 977u + warp * 131u + 7u);
+    __syncthreads();
+    unsigned long long ns0, ns1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
+    const long long t0 = clock64();
+    for (int it = 0; it < ITERS * 2; ++it) {
+#pragma unroll
+        for (int u = 0; u < R4; ++u) {
+            h = h * 1664525u + 1013904223u;
+            const uint32_t row = ((h >> 8) + (uint32_t)(lane >> 3) * 7919u) & nrows_mask;
+            float *p = gbuf + (size_t)row * 32 + (lane & 7) * 4;
+            asm volatile("red.global.add.v4.f32 [%0], {%1,%1,%1,%1};" :: "l"(p), "f"(1.0f) : "memory");
+        }
+        if (T > 0) {
+            const int b = it & 1;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffer b is free again
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < TT; ++u)
+                asm volatile("st.shared.f32 [%0], %1;" :: "r"(smem_u32(&stage[warp][b][u][lane])), "f"(1.0f) : "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane < TT) {
+                h = h * 1664525u + 1013904223u;
+                const uint32_t row = ((h >> 8) + (uint32_t)lane * 104729u) & nrows_mask;
+                asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                             :: "l"(gbuf + (size_t)row * 32), "r"(smem_u32(&stage[warp][b][lane][0])), "n"(ROW_BYTES) : "memory");
+            }
+            if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (T > 0) { if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); __syncwarp(); }
+    const long long t1 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+    __shared__ unsigned long long last;
+    if (threadIdx.x == 0) last = 0;
+    __syncthreads();
+    if (lane == 0) atomicMax(&last, (unsigned long long)(t1 - t0));
+    __syncthreads();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = (long long)last;
+    if (threadIdx.x == 0 && blockIdx.x == 0) { cycles[NS_SLOT] = (long long)(ns1 - ns0); cycles[NS_SLOT + 1] = t1 - t0; }
+}
+
+template <int R4, int T>
+void run_mix2(float *gbuf, uint32_t nrows_mask, long long *cycles_d, int sms) {
+    const int grid = sms * 2;
+    const int pad = 98 * 1024 - (THREADS / 32) * 2 * (T > 0 ? T : 1) * 128;   // exactly 2 CTAs per SM
+    CHECK(cudaFuncSetAttribute(mix2<R4, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad));
+    for (int w = 0; w < 20; ++w) mix2<R4, T><<<grid, THREADS, pad>>>(gbuf, nrows_mask, cycles_d);
+    CHECK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1;
+    CHECK(cudaEventCreate(&e0)); CHECK(cudaEventCreate(&e1));
+    CHECK(cudaEventRecord(e0));
+    mix2<R4, T><<<grid, THREADS, pad>>>(gbuf, nrows_mask, cycles_d);
+    CHECK(cudaEventRecord(e1));
+    CHECK(cudaDeviceSynchronize());
+    float ms = 0; CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    long long *h = (long long *)malloc(sizeof(long long) * grid);
+    CHECK(cudaMemcpy(h, cycles_d, sizeof(long long) * grid, cudaMemcpyDeviceToHost));
+    double mean = 0; for (int i = 0; i < grid; ++i) mean += (double)h[i]; mean /= grid;
+    free(h);
+    const double rows_per_sm = 2.0 * (THREADS / 32) * (ITERS * 2) * (4.0 * R4 + T);
+    long long nsclk[2];
+    CHECK(cudaMemcpy(nsclk, cycles_d + NS_SLOT, sizeof(nsclk), cudaMemcpyDeviceToHost));
+    printf("[%4.0f MHz] ", nsclk[0] > 0 ? 1e3 * (double)nsclk[1] / (double)nsclk[0] : 0.0);
+    printf("mix2: per warp-iteration %d x red.v4 (4 rows) + %d x TMA bulk reduce (1 row): %8.3f ms  %9.0f clk/CTA  %5.2f SM-cycles per row  (%6.1f GB/s)\n",
+           R4, T, ms, mean, mean / rows_per_sm, rows_per_sm * sms * 128.0 / (ms * 1e-3) / 1e9);
 }
 
 template <int TEST>
@@ -172,10 +263,15 @@ void run(float *gbuf, uint32_t nrows_mask, float *sink, long long *cycles_d, int
     const int grid = sms * ctas_per_sm;
     cudaEvent_t e0, e1;
     CHECK(cudaEventCreate(&e0)); CHECK(cudaEventCreate(&e1));
-    bench<TEST><<<grid, THREADS>>>(gbuf, nrows_mask, sink, cycles_d, (uint32_t)active_sms);   // warm-up
+    // dynamic shared memory that nothing uses: exactly `ctas_per_sm` CTAs fit on an SM, so the grid is
+    // spread evenly (without it up to 4 CTAs fit and the block scheduler loads the SMs unevenly)
+    const int pad = (200 * 1024) / ctas_per_sm - 33 * 1024;
+    CHECK(cudaFuncSetAttribute(bench<TEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad));
+    for (int w = 0; w < 20; ++w)   // warm-up: the clocks of an idle GPU take a while to reach the boost state
+        bench<TEST><<<grid, THREADS, pad>>>(gbuf, nrows_mask, sink, cycles_d, (uint32_t)active_sms);
     CHECK(cudaDeviceSynchronize());
     CHECK(cudaEventRecord(e0));
-    bench<TEST><<<grid, THREADS>>>(gbuf, nrows_mask, sink, cycles_d, (uint32_t)active_sms);
+    bench<TEST><<<grid, THREADS, pad>>>(gbuf, nrows_mask, sink, cycles_d, (uint32_t)active_sms);
     CHECK(cudaEventRecord(e1));
     CHECK(cudaDeviceSynchronize());
     float ms = 0; CHECK(cudaEventElapsedTime(&ms, e0, e1));
@@ -184,7 +280,22 @@ void run(float *gbuf, uint32_t nrows_mask, float *sink, long long *cycles_d, int
     double mean = 0, mean1 = 0; int live = 0;
     for (int i = 0; i < grid; ++i) if (h[2 * i]) { mean += (double)h[2 * i]; mean1 += (double)h[2 * i + 1]; ++live; }
     mean /= live; mean1 /= live;
+    double cmin = 1e30, cmax = 0;
+    for (int i = 0; i < grid; ++i) if (h[2 * i]) { cmin = h[2 * i] < cmin ? h[2 * i] : cmin; cmax = h[2 * i] > cmax ? h[2 * i] : cmax; }
+    if (TEST == RED128_4ROWS || TEST == STG128_4ROWS || TEST == LDG128_4ROWS_L2)
+        printf("[CTA clk min %.0f max %.0f] ", cmin, cmax);
+    if (TEST == RED128_4ROWS && ctas_per_sm == 2 && live == grid && nrows_mask == (64u << 20) / ROW_BYTES - 1) {
+        // distribution of CTA times in 10 buckets between min and max
+        int hist[10] = {0};
+        for (int i = 0; i < grid; ++i) { int b = (int)((h[2 * i] - cmin) / (cmax - cmin + 1) * 10); hist[b]++; }
+        printf("\n    CTA-time histogram (min..max, 10 buckets):");
+        for (int b = 0; b < 10; ++b) printf(" %d", hist[b]);
+        printf("\n    ");
+    }
     free(h);
+    long long nsclk[2];
+    CHECK(cudaMemcpy(nsclk, cycles_d + NS_SLOT, sizeof(nsclk), cudaMemcpyDeviceToHost));
+    printf("[%4.0f MHz] ", nsclk[0] > 0 ? 1e3 * (double)nsclk[1] / (double)nsclk[0] : 0.0);
     if (live != grid) printf("[%3d of %d CTAs live, ~%d SMs] ", live, grid, live / ctas_per_sm);
     if (nrows_mask != (64u << 20) / ROW_BYTES - 1) printf("[%u KB of rows] ", (nrows_mask + 1) / 8);
     if (TEST == MIX_RED_TMA) {
@@ -212,7 +323,9 @@ int main() {
     CHECK(cudaMalloc(&gbuf, (size_t)nrows * ROW_BYTES));
     CHECK(cudaMemset(gbuf, 0, (size_t)nrows * ROW_BYTES));
     CHECK(cudaMalloc(&sink, 16));
-    CHECK(cudaMalloc(&cycles, sizeof(long long) * sms * 16));
+    CHECK(cudaMalloc(&cycles, sizeof(long long) * (NS_SLOT + 2)));
+    for (int w = 0; w < 2000; ++w) bench<LDG128_4ROWS_L2><<<sms * 2, THREADS>>>(gbuf, nrows - 1, sink, cycles, 1u << 20);   // ~0.6 s
+    CHECK(cudaDeviceSynchronize());
     run<LDS32_BCAST>(gbuf, nrows - 1, sink, cycles, sms);
     run<LDS32_DISTINCT>(gbuf, nrows - 1, sink, cycles, sms);
     run<LDS64_4ADDR>(gbuf, nrows - 1, sink, cycles, sms);
@@ -254,6 +367,12 @@ int main() {
     // do LSU reductions and TMA bulk reductions share one path?
     run<MIX_RED_TMA>(gbuf, nrows - 1, sink, cycles, sms);
     run<MIX_RED_TMA>(gbuf, nrows - 1, sink, cycles, sms, 2, 74);
+    run_mix2<2, 0>(gbuf, nrows - 1, cycles, sms);
+    run_mix2<0, 8>(gbuf, nrows - 1, cycles, sms);
+    run_mix2<2, 2>(gbuf, nrows - 1, cycles, sms);
+    run_mix2<2, 4>(gbuf, nrows - 1, cycles, sms);
+    run_mix2<2, 8>(gbuf, nrows - 1, cycles, sms);
+    run_mix2<1, 8>(gbuf, nrows - 1, cycles, sms);
     printf("done\n");
     return 0;
 }
