@@ -130,6 +130,22 @@ int msda_b200_fused_backward_f32(const float *grad_output, const float *value,
                                  void *stream);
 
 /*
+ * Next component on the path's caller side: the fp32 nn.Linear layers around
+ * the op (ops/modules/ms_deform_attn.py:62-65,97-121 and msdeformattn.py:126-142), which the reference
+ * runs as fp32 GEMMs (torch F.linear; autocast disabled, msdeformattn.py:338).
+ *     y[rows, out_features] = x[rows, in_features] * weight[out_features, in_features]^T + bias
+ * (torch.nn.functional.linear semantics, row-major contiguous fp32; bias may be NULL; relu != 0
+ * applies max(., 0) to the result).  Computed on the sm_100a tensor cores with the error-compensated
+ * 3 x TF32 split (fp32-class accuracy, fp32 accumulation).  `workspace`: device scratch of
+ * 2 * out_features * in_features floats (the split weight; the library never allocates).  Requires
+ * in_features % 32 == 0, out_features % 4 == 0 and 16-byte aligned x / weight / workspace;
+ * MSDA_ERR_UNSUPPORTED otherwise.
+ */
+int msda_b200_linear_f32(const float *x, const float *weight, const float *bias, float *y,
+                         int rows, int out_features, int in_features, int relu, float *workspace,
+                         void *stream);
+
+/*
  * Integer known-answer hook (no counterpart in the reference; it exposes the
  * integer work of cuh:43-58, 279-293 so tests can pin it bit-exactly).
  * For every (n, q, m, l, p), in sampling_loc order:

@@ -1,0 +1,140 @@
+"""GPU tests of msda_b200_linear_f32: the fp32 nn.Linear of the layers around the op
+(ops/modules/ms_deform_attn.py:62-65, msdeformattn.py:126-130) as an error-compensated 3xTF32 GEMM on the
+tensor cores.  Reference = torch.nn.functional.linear in fp64; the bar is "as accurate as an fp32 GEMM":
+the error against fp64 may not exceed a small multiple of the error torch's own fp32 (non-TF32) GEMM makes
+on the same inputs."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+# measured: 1.0-1.6x (K <= 256), 2.9x (K = 1024: the tensor core truncates when it adds into the fp32
+# accumulator, so the error grows with the number of accumulations)
+ERR_FACTOR = 4.0
+
+
+def case(rows, out_f, in_f, seed, bias=True, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.randn(rows, in_f, generator=g) * scale).to(DEV)
+    w = (torch.randn(out_f, in_f, generator=g) / in_f ** 0.5).to(DEV)
+    b = torch.randn(out_f, generator=g).to(DEV) if bias else None
+    return x, w, b
+
+
+@pytest.mark.parametrize("rows,out_f,in_f", [
+    (128, 256, 32), (128, 256, 256), (1, 256, 256), (127, 256, 256), (129, 256, 256), (1000, 192, 256),
+    (777, 96, 256), (513, 1024, 256), (640, 256, 1024), (130, 128, 64), (300, 64, 96), (50, 4, 32),
+    (260, 260, 64), (333, 512, 128)])
+def test_linear_matches_fp64(pkg, rows, out_f, in_f):
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        x, w, b = case(rows, out_f, in_f, seed=rows + out_f)
+        n0 = pkg.launch_count()
+        y = pkg.linear_tf32x3(x, w, b)
+        torch.cuda.synchronize()
+        assert pkg.launch_count() - n0 == 2           # weight split + GEMM
+        ref64 = F.linear(x.double(), w.double(), b.double())
+        err = (y.double() - ref64).abs().max().item()
+        err32 = (F.linear(x, w, b).double() - ref64).abs().max().item()
+        assert y.shape == (rows, out_f) and torch.isfinite(y).all()
+        assert err <= ERR_FACTOR * err32 + 1e-7, (err, err32)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def test_linear_is_far_more_accurate_than_plain_tf32(pkg):
+    x, w, b = case(512, 256, 256, seed=5)
+    ref64 = F.linear(x.double(), w.double(), b.double())
+    err = (pkg.linear_tf32x3(x, w, b).double() - ref64).abs().max().item()
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        err_tf32 = (F.linear(x, w, b).double() - ref64).abs().max().item()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    assert err * 50 < err_tf32, (err, err_tf32)
+
+
+def test_linear_relu_no_bias_leading_dims_and_scales(pkg):
+    x, w, b = case(2 * 77, 192, 256, seed=9)
+    x3 = x.view(2, 77, 256)
+    y = pkg.linear_tf32x3(x3, w, None, relu=True)
+    assert y.shape == (2, 77, 192)
+    ref = F.linear(x3.double(), w.double()).relu()
+    assert (y.double() - ref).abs().max().item() <= 2e-5
+    assert (y >= 0).all()
+    # large / small magnitudes: relative accuracy is what the split preserves
+    for scale in (1e-6, 1e4):
+        xs, ws, bs = case(256, 256, 256, seed=3, bias=False, scale=scale)
+        ys = pkg.linear_tf32x3(xs, ws, None)
+        refs = F.linear(xs.double(), ws.double())
+        assert (ys.double() - refs).abs().max().item() <= 3e-6 * refs.abs().max().item()
+    # exactly representable inputs give the exact result (integers: no rounding anywhere)
+    xi = torch.randint(-8, 9, (200, 64), device=DEV).float()
+    wi = torch.randint(-8, 9, (32, 64), device=DEV).float()
+    assert torch.equal(pkg.linear_tf32x3(xi, wi, None), F.linear(xi.double(), wi.double()).float())
+
+
+def test_linear_non_finite_inputs_propagate(pkg):
+    x, w, b = case(130, 64, 64, seed=2)
+    x[5, 7] = float("inf")
+    x[100, 0] = float("nan")
+    y = pkg.linear_tf32x3(x, w, b)
+    assert not torch.isfinite(y[5]).any() and torch.isnan(y[100]).all()
+    keep = torch.ones(130, dtype=torch.bool, device=DEV)
+    keep[5] = keep[100] = False
+    assert torch.isfinite(y[keep]).all()
+
+
+def test_linear_error_behaviour(pkg):
+    x, w, b = case(64, 64, 64, seed=1)
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        pkg.linear_tf32x3(x.cpu(), w.cpu(), b.cpu())
+    with pytest.raises(RuntimeError, match="contiguous"):
+        pkg.linear_tf32x3(x.t(), w, b)
+    with pytest.raises(RuntimeError, match="float32"):
+        pkg.linear_tf32x3(x.double(), w.double(), b.double())
+    with pytest.raises(RuntimeError, match="in % 32"):
+        pkg.linear_tf32x3(x[:, :48].contiguous(), w[:, :48].contiguous(), b)
+    # the C ABI itself: null pointers and unsupported shapes are reported, nothing is launched
+    lib = pkg._lib.lib
+    assert lib.msda_b200_linear_f32(None, w.data_ptr(), None, x.data_ptr(), 64, 64, 64, 0, x.data_ptr(), None) == -1
+    assert lib.msda_b200_linear_f32(x.data_ptr(), w.data_ptr(), None, x.data_ptr(), 64, 64, 48, 0, x.data_ptr(), None) == -3
+    assert lib.msda_b200_linear_f32(x.data_ptr(), w.data_ptr(), None, x.data_ptr(), 0, 64, 64, 0, x.data_ptr(), None) == -2
+
+
+def test_encoder_layer_with_tensor_core_linears_matches_torch_linears(pkg):
+    """The encoder mirror with linear="tf32x3" (inference) against the same weights with torch's fp32
+    GEMMs; with autograd on it must take the torch path (and be bit-identical to it)."""
+    torch.manual_seed(4)
+    levels = [(8, 16), (16, 32), (32, 64)]
+    kw = dict(d_model=256, nhead=8, num_encoder_layers=2, dim_feedforward=1024, dropout=0.0,
+              num_feature_levels=3, enc_n_points=4)
+    a = pkg.modules.MSDeformAttnTransformerEncoderOnly(**kw).to(DEV).eval()
+    b = pkg.modules.MSDeformAttnTransformerEncoderOnly(linear="tf32x3", **kw).to(DEV).eval()
+    b.load_state_dict(a.state_dict())
+    for m in list(a.modules()) + list(b.modules()):           # away from the zero-initialised producers
+        if isinstance(m, pkg.modules.MSDeformAttn):
+            torch.nn.init.normal_(m.sampling_offsets.weight, std=0.02)
+            torch.nn.init.normal_(m.attention_weights.weight, std=0.05)
+    b.load_state_dict(a.state_dict())
+    srcs = [torch.randn(2, 256, h, w, device=DEV) for h, w in levels]
+    pos = [torch.randn(2, 256, h, w, device=DEV) for h, w in levels]
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            n0 = pkg.launch_count()
+            ya = a(srcs, pos)[0]
+            n1 = pkg.launch_count()
+            yb = b(srcs, pos)[0]
+            n2 = pkg.launch_count()
+        assert n1 - n0 == 2 and n2 - n1 == 2 + 2 * 6 * 2      # + (split + GEMM) x 6 linears x 2 layers
+        assert (ya - yb).abs().max().item() <= 5e-5, (ya - yb).abs().max().item()
+        yc = b(srcs, pos)[0]                                   # autograd on: torch GEMMs
+        assert torch.equal(yc, a(srcs, pos)[0])
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old

@@ -15,9 +15,9 @@ PD_KW = dict(transformer_dropout=0.0, transformer_nheads=2, transformer_dim_feed
 PD_SHAPES = {"res2": (12, 4), "res3": (20, 8), "res4": (28, 16), "res5": (36, 32)}
 
 
-def build(pkg, core=None, device="cpu", fused=False):
+def build(pkg, core=None, device="cpu", fused=False, linear="torch"):
     g = load_golden("pixel_decoder_small")
-    m = pkg.pixel_decoder.MSDeformAttnPixelDecoder(PD_SHAPES, core=core, fused=fused, **PD_KW)
+    m = pkg.pixel_decoder.MSDeformAttnPixelDecoder(PD_SHAPES, core=core, fused=fused, linear=linear, **PD_KW)
     state = {k[len("state::"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("state::")}
     missing, unexpected = m.load_state_dict(state, strict=True)
     assert not missing and not unexpected
@@ -58,9 +58,9 @@ def test_mirror_init_equals_live_reference(pkg, oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("fused", [False, True])
-def test_mirror_plus_cuda_op_matches_reference_pixel_decoder_golden(pkg, fused):
-    m, feats, g = build(pkg, device="cuda:0", fused=fused)
+@pytest.mark.parametrize("fused,linear", [(False, "torch"), (True, "torch"), (False, "tf32x3"), (True, "tf32x3")])
+def test_mirror_plus_cuda_op_matches_reference_pixel_decoder_golden(pkg, fused, linear):
+    m, feats, g = build(pkg, device="cuda:0", fused=fused, linear=linear)
     n0 = pkg.launch_count()
     # cuDNN convolutions default to TF32 on this GPU (1e-3 errors); the golden is true fp32
     tf32 = torch.backends.cudnn.allow_tf32
@@ -70,5 +70,6 @@ def test_mirror_plus_cuda_op_matches_reference_pixel_decoder_golden(pkg, fused):
             outs = m.forward_features(feats)
     finally:
         torch.backends.cudnn.allow_tf32 = tf32
-    assert pkg.launch_count() - n0 == 2          # one MSDA forward per encoder layer
+    # one MSDA forward per encoder layer (+ weight split and GEMM for each of the 6 linears of a layer)
+    assert pkg.launch_count() - n0 == (2 if linear == "torch" else 2 + 2 * 6 * 2)
     check(outs, g, 5e-4)

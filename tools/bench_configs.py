@@ -37,6 +37,8 @@ def main():
     ap.add_argument("--configs", default="1,2,3,4,5")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--fused", action="store_true", help="use the fused-producer kernels inside the encoder mirror")
+    ap.add_argument("--linear", default="torch", choices=["torch", "tf32x3"],
+                    help="nn.Linear implementation inside the encoder mirror in inference (tf32x3: tensor-core GEMM)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "configs.jsonl"))
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -58,7 +60,7 @@ def main():
         return float(t.item())
 
     def emit(rec):
-        rec.update(n_gpus=world, fused_producers=bool(args.fused))
+        rec.update(n_gpus=world, fused_producers=bool(args.fused), linear=args.linear)
         if rank == 0:
             os.makedirs(os.path.dirname(args.out), exist_ok=True)
             with open(args.out, "a") as f:
@@ -95,7 +97,7 @@ def main():
         torch.manual_seed(seed)
         m = pkg.modules.MSDeformAttnTransformerEncoderOnly(
             d_model=256, nhead=8, num_encoder_layers=6, dim_feedforward=1024, dropout=0.1,
-            num_feature_levels=3, enc_n_points=4, fused=args.fused).to(dev)
+            num_feature_levels=3, enc_n_points=4, fused=args.fused, linear=args.linear).to(dev)
         # trained-model-like sampling: small learned offsets instead of the integer-lattice init
         gen = torch.Generator().manual_seed(seed + 1)
         with torch.no_grad():
@@ -135,7 +137,8 @@ def main():
             dec = pkg.pixel_decoder.MSDeformAttnPixelDecoder(
                 shapes, transformer_dropout=0.1, transformer_nheads=8, transformer_dim_feedforward=1024,
                 transformer_enc_layers=6, conv_dim=256, mask_dim=256, norm="GN",
-                transformer_in_features=["res3", "res4", "res5"], common_stride=4, fused=args.fused).to(dev).eval()
+                transformer_in_features=["res3", "res4", "res5"], common_stride=4, fused=args.fused,
+                linear=args.linear).to(dev).eval()
             gen = torch.Generator().manual_seed(10 + rank)
             feats = {k: torch.randn(batch, c, -(-Himg // st), -(-Wimg // st), generator=gen).to(dev)
                      for k, (c, st) in shapes.items()}

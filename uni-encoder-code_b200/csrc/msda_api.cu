@@ -30,6 +30,8 @@ cudaError_t launch_fwd_generic(const T *, const int64_t *, const int64_t *, cons
 template <typename T>
 cudaError_t launch_bwd_generic(const T *, const T *, const int64_t *, const int64_t *, const T *,
                                const T *, const Dims &, T *, T *, T *, cudaStream_t);
+cudaError_t launch_linear_tf32x3(const float *, const float *, const float *, float *, int, int, int, int,
+                                 float *, cudaStream_t, bool *handled);
 cudaError_t launch_debug_indices(const int64_t *, const int64_t *, const float *, const Dims &,
                                  int32_t *, int64_t *, cudaStream_t);
 
@@ -220,6 +222,17 @@ int msda_b200_fused_backward_f32(const float *grad_output, const float *value,
                                          reference_points, ref_batch_stride, sampling_offsets,
                                          attn_logits, d, grad_value, grad_sampling_offsets,
                                          grad_attn_logits, (cudaStream_t)stream, &handled);
+    if (e == cudaSuccess && !handled) return MSDA_ERR_UNSUPPORTED;
+    return (int)e;
+}
+
+int msda_b200_linear_f32(const float *x, const float *weight, const float *bias, float *y, int rows,
+                         int out_features, int in_features, int relu, float *workspace, void *stream) {
+    if (!x || !weight || !y || !workspace) return MSDA_ERR_NULL_POINTER;
+    if (rows <= 0 || out_features <= 0 || in_features <= 0) return MSDA_ERR_BAD_SHAPE;
+    bool handled = false;
+    cudaError_t e = launch_linear_tf32x3(x, weight, bias, y, rows, out_features, in_features, relu,
+                                         workspace, (cudaStream_t)stream, &handled);
     if (e == cudaSuccess && !handled) return MSDA_ERR_UNSUPPORTED;
     return (int)e;
 }

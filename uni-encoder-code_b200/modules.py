@@ -34,6 +34,19 @@ from .functions import MSDeformAttnFunction, MSDeformAttnFusedFunction
 CoreFn = Callable[..., torch.Tensor]
 
 
+def _linear(layer: nn.Linear, x, impl: str, relu: bool = False):
+    """``layer(x)`` (+ ReLU).  impl == "tf32x3": in inference (autograd off) the fp32 GEMM runs on the
+    tensor cores as an error-compensated 3xTF32 product (ops.linear_tf32x3); with autograd
+    on, and for any shape the kernel does not cover, torch's own fp32 GEMM is used as in the reference."""
+    if impl == "tf32x3" and not torch.is_grad_enabled() and x.is_contiguous() \
+            and ops.linear_tf32x3_supported(x, layer.weight):
+        return ops.linear_tf32x3(x, layer.weight, layer.bias, relu=relu)
+    if impl not in ("torch", "tf32x3"):
+        raise ValueError(f"unknown linear implementation {impl!r}")
+    y = layer(x)
+    return F.relu(y) if relu else y
+
+
 def _cuda_core(value, spatial_shapes, level_start_index, sampling_locations, attention_weights,
                im2col_step):
     return MSDeformAttnFunction.apply(value, spatial_shapes, level_start_index, sampling_locations,
@@ -44,11 +57,13 @@ class MSDeformAttn(nn.Module):
     """Multi-scale deformable attention module (ms_deform_attn.py:35-126)."""
 
     def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4, core: Optional[CoreFn] = None,
-                 fused: bool = False):
+                 fused: bool = False, linear: str = "torch"):
         """`fused=True` (not in the reference): softmax and location arithmetic run inside the
-        kernels whenever the shapes allow; results agree to rounding."""
+        kernels whenever the shapes allow; results agree to rounding.
+        `linear="tf32x3"` (not in the reference): see `_linear`."""
         super().__init__()
         self.fused = fused
+        self.linear = linear
         if d_model % n_heads:
             raise ValueError(f"d_model must be divisible by n_heads, but got {d_model} and {n_heads}")
         self.im2col_step = 128                    # ms_deform_attn.py:55
@@ -84,8 +99,8 @@ class MSDeformAttn(nn.Module):
         (ms_deform_attn.py:105-118)."""
         N, Lq, _ = query.shape
         M, L, P = self.n_heads, self.n_levels, self.n_points
-        offsets = self.sampling_offsets(query).view(N, Lq, M, L, P, 2)
-        weights = F.softmax(self.attention_weights(query).view(N, Lq, M, L * P), -1).view(N, Lq, M, L, P)
+        offsets = _linear(self.sampling_offsets, query, self.linear).view(N, Lq, M, L, P, 2)
+        weights = F.softmax(_linear(self.attention_weights, query, self.linear).view(N, Lq, M, L * P), -1).view(N, Lq, M, L, P)
         if reference_points.shape[-1] == 2:
             wh = input_spatial_shapes.flip(-1).to(offsets.dtype)       # (W_l, H_l)
             loc = reference_points[:, :, None, :, None, :] + offsets / wh[None, None, None, :, None, :]
@@ -99,7 +114,7 @@ class MSDeformAttn(nn.Module):
 
     def project_value(self, input_flatten, input_padding_mask=None):
         N, S, _ = input_flatten.shape
-        value = self.value_proj(input_flatten)
+        value = _linear(self.value_proj, input_flatten, self.linear)
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], 0.0)
         return value.view(N, S, self.n_heads, self.d_model // self.n_heads)
@@ -109,8 +124,10 @@ class MSDeformAttn(nn.Module):
         value = self.project_value(input_flatten, input_padding_mask)
         if self.fused and self._core is _cuda_core and not reference_points.requires_grad:
             N, Lq, _ = query.shape
-            offsets = self.sampling_offsets(query).view(N, Lq, self.n_heads, self.n_levels, self.n_points, 2)
-            logits = self.attention_weights(query).view(N, Lq, self.n_heads, self.n_levels * self.n_points)
+            offsets = _linear(self.sampling_offsets, query, self.linear).view(
+                N, Lq, self.n_heads, self.n_levels, self.n_points, 2)
+            logits = _linear(self.attention_weights, query, self.linear).view(
+                N, Lq, self.n_heads, self.n_levels * self.n_points)
             ref = reference_points
             if ref.dim() == 4 and ref.stride(0) == 0:        # expanded over the batch: pass one copy
                 ref = ref[:1]
@@ -118,11 +135,11 @@ class MSDeformAttn(nn.Module):
             if ops.fused_supported(value, ref, offsets, logits):
                 out = MSDeformAttnFusedFunction.apply(value, input_spatial_shapes, input_level_start_index,
                                                       ref, offsets, logits)
-                return self.output_proj(out)
+                return _linear(self.output_proj, out, self.linear)
         loc, weights = self.sampling_inputs(query, reference_points, input_spatial_shapes)
         out = self._core(value, input_spatial_shapes, input_level_start_index, loc.contiguous(),
                          weights.contiguous(), self.im2col_step)
-        return self.output_proj(out)
+        return _linear(self.output_proj, out, self.linear)
 
 
 def _activation(name):
@@ -133,9 +150,10 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
     """msdeformattn.py:102-142 (post-norm: attention, add & norm, FFN, add & norm)."""
 
     def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8,
-                 n_points=4, core: Optional[CoreFn] = None, fused: bool = False):
+                 n_points=4, core: Optional[CoreFn] = None, fused: bool = False, linear: str = "torch"):
         super().__init__()
-        self.self_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points, core=core, fused=fused)
+        self.linear = linear
+        self.self_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points, core=core, fused=fused, linear=linear)
         self.dropout1 = nn.Dropout(dropout)
         self.norm1 = nn.LayerNorm(d_model)
         self.linear1 = nn.Linear(d_model, d_ffn)
@@ -146,7 +164,11 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
         self.norm2 = nn.LayerNorm(d_model)
 
     def forward_ffn(self, src):
-        return self.norm2(src + self.dropout3(self.linear2(self.dropout2(self.activation(self.linear1(src))))))
+        if self.activation is F.relu:              # ReLU rides in the GEMM epilogue of the tf32x3 kernel
+            hidden = _linear(self.linear1, src, self.linear, relu=True)
+        else:
+            hidden = self.activation(_linear(self.linear1, src, self.linear))
+        return self.norm2(src + self.dropout3(_linear(self.linear2, self.dropout2(hidden), self.linear)))
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
         q = src if pos is None else src + pos
@@ -217,12 +239,12 @@ class MSDeformAttnTransformerEncoderOnly(nn.Module):
 
     def __init__(self, d_model=256, nhead=8, num_encoder_layers=6, dim_feedforward=1024, dropout=0.1,
                  activation="relu", num_feature_levels=4, enc_n_points=4, core: Optional[CoreFn] = None,
-                 fused: bool = False):
+                 fused: bool = False, linear: str = "torch"):
         super().__init__()
         self.d_model, self.nhead = d_model, nhead
         layer = MSDeformAttnTransformerEncoderLayer(d_model, dim_feedforward, dropout, activation,
                                                     num_feature_levels, nhead, enc_n_points, core=core,
-                                                    fused=fused)
+                                                    fused=fused, linear=linear)
         self.encoder = MSDeformAttnTransformerEncoder(layer, num_encoder_layers)
         self.level_embed = nn.Parameter(torch.empty(num_feature_levels, d_model))
         self._reset_parameters()

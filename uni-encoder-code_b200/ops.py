@@ -236,3 +236,41 @@ def ms_deform_attn_fused_backward(value, spatial_shapes, level_start_index, refe
                 torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "ms_deform_attn_fused_backward")
     return [grad_value, grad_off, grad_logits]
+
+
+# ----------------------------------------------------------------------------------------------
+# fp32 Linear on the tensor cores: the nn.Linear layers around the op
+# (ops/modules/ms_deform_attn.py:62-65, msdeformattn.py:126-130) as an error-compensated 3xTF32 GEMM.
+# Inference only (no backward); torch.nn.functional.linear semantics.
+# ----------------------------------------------------------------------------------------------
+def linear_tf32x3_supported(x, weight) -> bool:
+    return (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32
+            and weight.dtype == torch.float32 and weight.dim() == 2 and x.size(-1) == weight.size(1)
+            and weight.size(1) % 32 == 0 and weight.size(0) % 4 == 0 and x.numel() > 0)
+
+
+def linear_tf32x3(x, weight, bias=None, relu=False):
+    """``F.linear(x, weight, bias)`` (then ``relu`` if set) for fp32 CUDA tensors; ``x`` [..., in],
+    ``weight`` [out, in] with in % 32 == 0 and out % 4 == 0."""
+    if not x.is_cuda:
+        raise RuntimeError("Not implemented on the CPU")
+    for name, t in (("x", x), ("weight", weight)) + ((("bias", bias),) if bias is not None else ()):
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name} tensor has to be contiguous")
+        if not t.is_cuda or t.device != x.device:
+            raise RuntimeError(f"{name} must be a CUDA tensor on {x.device}")
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"{name} must be float32")
+    if not linear_tf32x3_supported(x, weight) or (bias is not None and bias.shape != (weight.size(0),)):
+        raise RuntimeError("linear_tf32x3 needs x [..., in] and weight [out, in] with in % 32 == 0, out % 4 == 0")
+    out_f, in_f = weight.shape
+    rows = x.numel() // in_f
+    y = torch.empty(x.shape[:-1] + (out_f,), dtype=x.dtype, device=x.device)
+    workspace = torch.empty(2 * out_f * in_f, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib.msda_b200_linear_f32(x.data_ptr(), weight.data_ptr(),
+                                           bias.data_ptr() if bias is not None else None, y.data_ptr(),
+                                           rows, out_f, in_f, 1 if relu else 0, workspace.data_ptr(),
+                                           torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(rc, "linear_tf32x3")
+    return y

@@ -95,7 +95,7 @@ class MSDeformAttnPixelDecoder(nn.Module):
                  transformer_nheads: int, transformer_dim_feedforward: int, transformer_enc_layers: int,
                  conv_dim: int, mask_dim: int, norm: Optional[str] = None,
                  transformer_in_features: Sequence[str], common_stride: int,
-                 core: Optional[CoreFn] = None, fused: bool = False):
+                 core: Optional[CoreFn] = None, fused: bool = False, linear: str = "torch"):
         super().__init__()
         by_stride = sorted(input_shape.items(), key=lambda kv: kv[1][1])
         self.in_features = [k for k, _ in by_stride]
@@ -114,7 +114,7 @@ class MSDeformAttnPixelDecoder(nn.Module):
         self.transformer = MSDeformAttnTransformerEncoderOnly(
             d_model=conv_dim, dropout=transformer_dropout, nhead=transformer_nheads,
             dim_feedforward=transformer_dim_feedforward, num_encoder_layers=transformer_enc_layers,
-            num_feature_levels=self.transformer_num_feature_levels, core=core, fused=fused)
+            num_feature_levels=self.transformer_num_feature_levels, core=core, fused=fused, linear=linear)
         self.pe_layer = PositionEmbeddingSine(conv_dim // 2, normalize=True)
         self.mask_dim = mask_dim
         self.mask_features = nn.Conv2d(conv_dim, mask_dim, kernel_size=1, stride=1, padding=0)
