@@ -146,6 +146,16 @@ int msda_b200_linear_f32(const float *x, const float *weight, const float *bias,
                          void *stream);
 
 /*
+ * y[rows, cols] = LayerNorm(x + residual) * gamma + beta over the last dimension (eps inside the square
+ * root, biased variance: torch.nn.functional.layer_norm semantics) -- the `norm(src + sublayer(src))`
+ * steps of the encoder layer (msdeformattn.py:134-141) in one pass.  residual may be NULL.
+ * cols in {128, 256, 384, 512}, 16-byte aligned pointers; MSDA_ERR_UNSUPPORTED otherwise.
+ */
+int msda_b200_add_layernorm_f32(const float *x, const float *residual, const float *gamma,
+                                const float *beta, float *y, long long rows, int cols, float eps,
+                                void *stream);
+
+/*
  * Integer known-answer hook (no counterpart in the reference; it exposes the
  * integer work of cuh:43-58, 279-293 so tests can pin it bit-exactly).
  * For every (n, q, m, l, p), in sampling_loc order:

@@ -132,9 +132,27 @@ def test_encoder_layer_with_tensor_core_linears_matches_torch_linears(pkg):
             n1 = pkg.launch_count()
             yb = b(srcs, pos)[0]
             n2 = pkg.launch_count()
-        assert n1 - n0 == 2 and n2 - n1 == 2 + 2 * 6 * 2      # + (split + GEMM) x 6 linears x 2 layers
+        assert n1 - n0 == 2 and n2 - n1 == 2 + (2 * 6 + 2) * 2   # + ((split + GEMM) x 6 linears + 2 add-norms) x 2 layers
         assert (ya - yb).abs().max().item() <= 5e-5, (ya - yb).abs().max().item()
         yc = b(srcs, pos)[0]                                   # autograd on: torch GEMMs
         assert torch.equal(yc, a(srcs, pos)[0])
     finally:
         torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.parametrize("rows,cols,with_res", [(1000, 256, True), (37, 256, False), (513, 128, True),
+                                                (64, 512, True), (9, 384, True)])
+def test_add_layernorm_matches_torch(pkg, rows, cols, with_res):
+    g = torch.Generator().manual_seed(rows)
+    x = (torch.randn(rows, cols, generator=g) * 3 + 1).to(DEV)
+    r = torch.randn(rows, cols, generator=g).to(DEV) if with_res else None
+    w = torch.randn(cols, generator=g).to(DEV)
+    b = torch.randn(cols, generator=g).to(DEV)
+    y = pkg.add_layernorm(x, r, w, b, 1e-5)
+    v = x.double() + (r.double() if with_res else 0)
+    ref = F.layer_norm(v, (cols,), w.double(), b.double(), 1e-5)
+    ref32 = F.layer_norm(x + r if with_res else x, (cols,), w, b, 1e-5)
+    err, err32 = (y.double() - ref).abs().max().item(), (ref32.double() - ref).abs().max().item()
+    assert err <= 2 * err32 + 1e-6, (err, err32)
+    with pytest.raises(RuntimeError, match="add_layernorm needs"):
+        pkg.add_layernorm(x[:, :100].contiguous(), None, w[:100].contiguous(), b[:100].contiguous())

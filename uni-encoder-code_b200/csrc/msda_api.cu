@@ -32,6 +32,8 @@ cudaError_t launch_bwd_generic(const T *, const T *, const int64_t *, const int6
                                const T *, const Dims &, T *, T *, T *, cudaStream_t);
 cudaError_t launch_linear_tf32x3(const float *, const float *, const float *, float *, int, int, int, int,
                                  float *, cudaStream_t, bool *handled);
+cudaError_t launch_add_layernorm(const float *, const float *, const float *, const float *, float *, long long,
+                                 int, float, cudaStream_t, bool *handled);
 cudaError_t launch_debug_indices(const int64_t *, const int64_t *, const float *, const Dims &,
                                  int32_t *, int64_t *, cudaStream_t);
 
@@ -233,6 +235,16 @@ int msda_b200_linear_f32(const float *x, const float *weight, const float *bias,
     bool handled = false;
     cudaError_t e = launch_linear_tf32x3(x, weight, bias, y, rows, out_features, in_features, relu,
                                          workspace, (cudaStream_t)stream, &handled);
+    if (e == cudaSuccess && !handled) return MSDA_ERR_UNSUPPORTED;
+    return (int)e;
+}
+
+int msda_b200_add_layernorm_f32(const float *x, const float *residual, const float *gamma, const float *beta,
+                                float *y, long long rows, int cols, float eps, void *stream) {
+    if (!x || !gamma || !beta || !y) return MSDA_ERR_NULL_POINTER;
+    if (rows <= 0 || cols <= 0) return MSDA_ERR_BAD_SHAPE;
+    bool handled = false;
+    cudaError_t e = launch_add_layernorm(x, residual, gamma, beta, y, rows, cols, eps, (cudaStream_t)stream, &handled);
     if (e == cudaSuccess && !handled) return MSDA_ERR_UNSUPPORTED;
     return (int)e;
 }

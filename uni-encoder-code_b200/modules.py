@@ -35,7 +35,8 @@ CoreFn = Callable[..., torch.Tensor]
 
 
 def _linear(layer: nn.Linear, x, impl: str, relu: bool = False):
-    """``layer(x)`` (+ ReLU).  impl == "tf32x3": in inference (autograd off) the fp32 GEMM runs on the
+    """``layer(x)`` (+ ReLU).  impl == "tf32x3" selects the inference kernels of SURVEY 8f.3 (this GEMM and the
+    fused residual + LayerNorm of `_add_norm`): in inference (autograd off) the fp32 GEMM runs on the
     tensor cores as an error-compensated 3xTF32 product (ops.linear_tf32x3); with autograd
     on, and for any shape the kernel does not cover, torch's own fp32 GEMM is used as in the reference."""
     if impl == "tf32x3" and not torch.is_grad_enabled() and x.is_contiguous() \
@@ -45,6 +46,14 @@ def _linear(layer: nn.Linear, x, impl: str, relu: bool = False):
         raise ValueError(f"unknown linear implementation {impl!r}")
     y = layer(x)
     return F.relu(y) if relu else y
+
+
+def _add_norm(norm: nn.LayerNorm, x, sublayer_out, impl: str):
+    """``norm(x + sublayer_out)``; impl == "tf32x3" (inference): one fused pass (ops.add_layernorm)."""
+    if impl == "tf32x3" and not torch.is_grad_enabled() and norm.elementwise_affine \
+            and ops.add_layernorm_supported(x, sublayer_out, norm.weight):
+        return ops.add_layernorm(x, sublayer_out, norm.weight, norm.bias, norm.eps)
+    return norm(x + sublayer_out)
 
 
 def _cuda_core(value, spatial_shapes, level_start_index, sampling_locations, attention_weights,
@@ -168,12 +177,13 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
             hidden = _linear(self.linear1, src, self.linear, relu=True)
         else:
             hidden = self.activation(_linear(self.linear1, src, self.linear))
-        return self.norm2(src + self.dropout3(_linear(self.linear2, self.dropout2(hidden), self.linear)))
+        return _add_norm(self.norm2, src, self.dropout3(_linear(self.linear2, self.dropout2(hidden), self.linear)),
+                         self.linear)
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
         q = src if pos is None else src + pos
         attn = self.self_attn(q, reference_points, src, spatial_shapes, level_start_index, padding_mask)
-        return self.forward_ffn(self.norm1(src + self.dropout1(attn)))
+        return self.forward_ffn(_add_norm(self.norm1, src, self.dropout1(attn), self.linear))
 
 
 _REF_CACHE = {}

@@ -274,3 +274,30 @@ def linear_tf32x3(x, weight, bias=None, relu=False):
                                            torch.cuda.current_stream(x.device).cuda_stream)
     _lib.check(rc, "linear_tf32x3")
     return y
+
+
+def add_layernorm_supported(x, residual, weight) -> bool:
+    return (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+            and x.size(-1) in (128, 256, 384, 512) and x.numel() > 0 and weight is not None
+            and weight.dtype == torch.float32 and weight.numel() == x.size(-1)
+            and (residual is None or (residual.shape == x.shape and residual.is_contiguous()
+                                      and residual.dtype == torch.float32 and residual.device == x.device)))
+
+
+def add_layernorm(x, residual, weight, bias, eps=1e-5):
+    """``F.layer_norm(x + residual, (C,), weight, bias, eps)`` in one pass (fp32 CUDA, C in {128,...,512});
+    ``residual`` may be None.  Inference only (no backward)."""
+    if not x.is_cuda:
+        raise RuntimeError("Not implemented on the CPU")
+    if not add_layernorm_supported(x, residual, weight) or bias is None or bias.shape != weight.shape:
+        raise RuntimeError("add_layernorm needs contiguous fp32 CUDA tensors with a last dimension of "
+                           "128, 256, 384 or 512 and affine parameters")
+    y = torch.empty_like(x)
+    cols = x.size(-1)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib.msda_b200_add_layernorm_f32(
+            x.data_ptr(), residual.data_ptr() if residual is not None else None, weight.data_ptr(),
+            bias.data_ptr(), y.data_ptr(), x.numel() // cols, cols, float(eps),
+            torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(rc, "add_layernorm")
+    return y
