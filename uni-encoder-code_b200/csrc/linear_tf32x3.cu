@@ -14,17 +14,18 @@
 // SECOND accumulator (2^-11 of the magnitude, hence 2^-11 of the truncation error) that is added in the
 // epilogue: one third of the accumulations into the main one.
 //
-// Structure (one CTA per 128 x BN output tile, 10 warps):
+// Structure (persistent: one CTA per SM walks 128 x BN output tiles, BN = 128 or 96; 10 warps):
 //   pre-pass  W is split once per call into Whi / Wlo (workspace, 2 x N x K floats);
 //   warp 0   one thread: TMA loads of the fp32 X tile (128 x 32) and the Whi / Wlo tiles (BN x 32) of
 //            each k-block into a STAGES-deep ring (128-byte swizzle: a tile row is one swizzle span);
-//   warps 2-9 split the landed X tile element-wise into hi (in place) and lo (second buffer, same
+//   warps 2-5 split the landed X tile element-wise into hi (in place) and lo (second buffer, same
 //            offsets -- the swizzle is irrelevant to an element-wise pass), fence to the async proxy
 //            and hand the stage to
-//   warp 1   one thread: 3 x 4 tcgen05.mma.kind::tf32 (128 x BN x 8) per k-block into the two TMEM
-//            accumulators, tcgen05.commit to release the stage;
-//   warps 2-9 epilogue: tcgen05.ld both accumulators (lane = row), add them and the bias, ReLU,
-//            transpose 32 x 32 blocks through shared memory and store whole 128-byte row segments.
+//   warp 1   one thread: 3 x 4 tcgen05.mma.kind::tf32 (128 x BN x 8) per k-block into one of TWO
+//            {main, small} accumulator sets in TMEM, tcgen05.commit to release the stage;
+//   warps 6-9 epilogue of tile i while tile i+1 is being computed: tcgen05.ld both accumulators
+//            (lane = row), add them and the bias, ReLU, transpose 32 x 32 blocks through shared memory
+//            and store whole 128-byte row segments.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -38,8 +39,6 @@ namespace {
 constexpr int kBM = 128;          // rows of X per CTA (= TMEM lanes)
 constexpr int kBK = 32;           // fp32 elements per k-block: 128 bytes = one swizzle span
 constexpr int kUmmaK = 8;         // tf32 MMA depth
-constexpr int kSplitWarps = 8;
-constexpr int kThreads = 64 + 32 * kSplitWarps;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -101,36 +100,55 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // two full-rate integer instructions (the cvt runs on the quarter-rate conversion pipe)
 __device__ __forceinline__ uint32_t to_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 
-template <int BN, int STAGES>
+constexpr int kSplitWarps = 4;    // warps 2-5
+constexpr int kEpiWarps = 4;      // warps 6-9: one per TMEM lane quarter
+constexpr int kThreads = 64 + 32 * (kSplitWarps + kEpiWarps);
+
+template <int BN, int STAGES, int NBUF, int NACC>
 struct LinCfg {
     static constexpr int kXBytes = kBM * kBK * 4, kWBytes = BN * kBK * 4;
     static constexpr int kStageBytes = 2 * kXBytes + 2 * kWBytes;  // X hi, X lo, W hi, W lo
     static constexpr int kTxBytes = kXBytes + 2 * kWBytes;         // what TMA delivers per stage
-    static constexpr int kTileBytes = STAGES * kStageBytes;
-    static constexpr int kSmem = kTileBytes + 1024 /* alignment slack */ + 256 /* barriers */;
-    static constexpr int kTmemCols = 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
-    static_assert(kTileBytes >= kSplitWarps * 32 * 33 * 4, "epilogue scratch lives in the ring");
+    static constexpr int kRingBytes = STAGES * kStageBytes;
+    static constexpr int kEpiBytes = kEpiWarps * 32 * 33 * 4;      // 32 x 32 transpose tile (padded) per epilogue warp
+    static constexpr int kSmem = kRingBytes + kEpiBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+    // NBUF accumulator sets (2: tile i is drained while tile i+1 is computed) of NACC accumulators of BN
+    // columns: NACC == 2: {main, small}; NACC == 4: {main, main', small, small'} -- a tcgen05.mma that
+    // accumulates into the result of the previous one waits ~240 cycles for it, so the products of a
+    // k-step are spread over independent accumulators (the epilogue adds them up)
+    static constexpr int kSetCols = NACC * BN;
+    static constexpr int kTmemCols = NBUF * kSetCols <= 128 ? 128 : NBUF * kSetCols <= 256 ? 256 : 512;
+    static_assert(NBUF * kSetCols <= 512 && BN % 32 == 0 && kStageBytes % 1024 == 0 && (NACC == 2 || NACC == 4), "tile shape");
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NBUF, int NACC>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wh,
-                     const __grid_constant__ CUtensorMap map_wl, const float *__restrict__ bias, float *__restrict__ y, int M, int N, int K, int relu) {
-    using Cfg = LinCfg<BN, STAGES>;
+                     const __grid_constant__ CUtensorMap map_wl, const float *__restrict__ bias,
+                     float *__restrict__ y, int M, int N, int K, int relu, int whatif) {
+    using Cfg = LinCfg<BN, STAGES, NBUF, NACC>;
     extern __shared__ uint8_t smem_dyn[];
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;         // 128-byte swizzle: 1024-byte aligned tiles
     uint8_t *base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
-    const uint32_t bars = base + Cfg::kTileBytes;
-    // barriers: full[s] (TMA landed), ready[s] (split done), empty[s] (MMAs done), acc (accumulator complete)
+    const uint32_t bars = base + Cfg::kRingBytes + Cfg::kEpiBytes;
+    // ring barriers: full[s] (TMA landed), ready[s] (split done), empty[s] (MMAs done);
+    // accumulator barriers: acc_full[b] (tile complete), acc_empty[b] (tile drained)
     auto full = [&](int s) { return bars + 8u * s; };
     auto ready = [&](int s) { return bars + 8u * (STAGES + s); };
     auto empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
-    const uint32_t acc_bar = bars + 8u * 3 * STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(base_ptr + Cfg::kTileBytes + 8 * (3 * STAGES + 1));
+    auto acc_full = [&](int b) { return bars + 8u * (3 * STAGES + b); };
+    auto acc_empty = [&](int b) { return bars + 8u * (3 * STAGES + 2 + b); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(base_ptr + Cfg::kRingBytes + Cfg::kEpiBytes + 8 * (3 * STAGES + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
+    // timing experiments for profiles/ (results WRONG; msda_b200_set_option("whatif_linear", bits)):
+    // 1 no MMAs, 2 no split work, 4 no output stores, 8 no W loads, 16 no X loads
+    const bool dbg_no_mma = whatif & 1, dbg_no_split = whatif & 2, dbg_no_store = whatif & 4, dbg_no_w = whatif & 8,
+               dbg_no_x = whatif & 16;
     const int kblocks = K / kBK;
+    const int k_rot = (int)(blockIdx.x % (unsigned)kblocks);
+    const int n_tiles = (N + BN - 1) / BN;
+    const long long tiles = (long long)((M + kBM - 1) / kBM) * n_tiles;   // n fastest: the N-tiles of a row block run together
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -138,7 +156,10 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             mbar_init(ready(s), 32 * kSplitWarps);
             mbar_init(empty(s), 1);
         }
-        mbar_init(acc_bar, 1);
+        for (int b = 0; b < NBUF; ++b) {
+            mbar_init(acc_full(b), 1);
+            mbar_init(acc_empty(b), 32 * kEpiWarps);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -149,92 +170,140 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_acc = *tmem_slot;
+    const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
+        // ---- TMA producer ----
         if (lane == 0) {
-            for (int kb = 0; kb < kblocks; ++kb) {
-                const int s = kb % STAGES;
-                mbar_wait(empty(s), ((kb / STAGES) & 1) ^ 1);
-                const uint32_t st = base + s * Cfg::kStageBytes;
-                mbar_arrive_expect_tx(full(s), Cfg::kTxBytes);
-                tma_load_2d(st, &map_x, full(s), kb * kBK, m0);
-                tma_load_2d(st + 2 * Cfg::kXBytes, &map_wh, full(s), kb * kBK, n0);
-                tma_load_2d(st + 2 * Cfg::kXBytes + Cfg::kWBytes, &map_wl, full(s), kb * kBK, n0);
+            uint32_t g = 0;                                               // k-blocks issued so far (ring position)
+            for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+                const int m0 = (int)(t / n_tiles) * kBM, n0 = (int)(t % n_tiles) * BN;
+                for (int kb = 0; kb < kblocks; ++kb, ++g) {
+                    // every CTA starts its k loop at a different k-block: at any moment the SMs read different
+                    // lines of W (which all of them share) instead of queueing on the same L2 lines
+                    const int kk = (kb + k_rot) % kblocks;
+                    const int s = g % STAGES;
+                    mbar_wait(empty(s), ((g / STAGES) & 1) ^ 1);
+                    const uint32_t st = base + s * Cfg::kStageBytes;
+                    mbar_arrive_expect_tx(full(s), (dbg_no_x ? 0 : Cfg::kXBytes) + (dbg_no_w ? 0 : 2 * Cfg::kWBytes));
+                    if (!dbg_no_x) tma_load_2d(st, &map_x, full(s), kk * kBK, m0);
+                    if (!dbg_no_w) tma_load_2d(st + 2 * Cfg::kXBytes, &map_wh, full(s), kk * kBK, n0);
+                    if (!dbg_no_w) tma_load_2d(st + 2 * Cfg::kXBytes + Cfg::kWBytes, &map_wl, full(s), kk * kBK, n0);
+                }
             }
         }
     } else if (warp == 1) {
+        // ---- MMA issuer ----
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc(kBM, BN);
-            for (int kb = 0; kb < kblocks; ++kb) {
-                const int s = kb % STAGES;
-                mbar_wait(ready(s), (kb / STAGES) & 1);
+            uint32_t g = 0, it = 0;
+            for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+                const uint32_t buf = it % NBUF;
+                const uint32_t acc_set = tmem_base + buf * Cfg::kSetCols;
+                mbar_wait(acc_empty(buf), ((it / NBUF) & 1) ^ 1);        // the epilogue has drained this set
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t xh = base + s * Cfg::kStageBytes, xl = xh + Cfg::kXBytes;
-                const uint32_t wh = xl + Cfg::kXBytes, wl = wh + Cfg::kWBytes;
+                for (int kb = 0; kb < kblocks; ++kb, ++g) {
+                    const int s = g % STAGES;
+                    mbar_wait(ready(s), (g / STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t xh = base + s * Cfg::kStageBytes, xl = xh + Cfg::kXBytes;
+                    const uint32_t wh = xl + Cfg::kXBytes, wl = wh + Cfg::kWBytes;
 #pragma unroll
-                for (int k = 0; k < kBK / kUmmaK; ++k) {
-                    const uint32_t ko = k * kUmmaK * 4;                    // 32 bytes inside the swizzle span
-                    umma_tf32(tmem_acc + BN, umma_desc(xl + ko), umma_desc(wh + ko), idesc, (kb | k) != 0);
-                    umma_tf32(tmem_acc + BN, umma_desc(xh + ko), umma_desc(wl + ko), idesc, 1);
-                    umma_tf32(tmem_acc, umma_desc(xh + ko), umma_desc(wh + ko), idesc, (kb | k) != 0);
+                    for (int k = 0; k < kBK / kUmmaK; ++k) {
+                        const uint32_t ko = k * kUmmaK * 4;                // 32 bytes inside the swizzle span
+                        if (dbg_no_mma) continue;
+                        if (NACC == 2) {           // {main, small}
+                            umma_tf32(acc_set + BN, umma_desc(xl + ko), umma_desc(wh + ko), idesc, (kb | k) != 0);
+                            umma_tf32(acc_set + BN, umma_desc(xh + ko), umma_desc(wl + ko), idesc, 1);
+                            umma_tf32(acc_set, umma_desc(xh + ko), umma_desc(wh + ko), idesc, (kb | k) != 0);
+                        } else {                   // {main (even k-steps), main (odd), small: xl*wh, small: xh*wl}
+                            umma_tf32(acc_set + 2 * BN, umma_desc(xl + ko), umma_desc(wh + ko), idesc, (kb | k) != 0);
+                            umma_tf32(acc_set + 3 * BN, umma_desc(xh + ko), umma_desc(wl + ko), idesc, (kb | k) != 0);
+                            umma_tf32(acc_set + (k & 1) * BN, umma_desc(xh + ko), umma_desc(wh + ko), idesc, (kb | (k >> 1)) != 0);
+                        }
+                    }
+                    umma_commit(empty(s));                                // stage reusable once these MMAs are done
                 }
-                umma_commit(empty(s));                                    // stage reusable once these MMAs are done
+                umma_commit(acc_full(buf));
             }
-            umma_commit(acc_bar);
+        }
+    } else if (warp < 2 + kSplitWarps) {
+        // ---- split warps: x -> (tf32(x), tf32(x - tf32(x))) ----
+        const int t0 = threadIdx.x - 64;
+        uint32_t g = 0;
+        for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+            for (int kb = 0; kb < kblocks; ++kb, ++g) {
+                const int s = g % STAGES;
+                mbar_wait(full(s), (g / STAGES) & 1);
+                float4 *hi = reinterpret_cast<float4 *>(base_ptr + s * Cfg::kStageBytes);
+                float4 *lo = reinterpret_cast<float4 *>(base_ptr + s * Cfg::kStageBytes + Cfg::kXBytes);
+#pragma unroll
+                for (int c = t0; c < (dbg_no_split ? 0 : Cfg::kXBytes / 16); c += 32 * kSplitWarps) {
+                    const float4 v = hi[c];
+                    uint4 h, l;
+                    h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+                    l.x = to_tf32(v.x - __uint_as_float(h.x));
+                    l.y = to_tf32(v.y - __uint_as_float(h.y));
+                    l.z = to_tf32(v.z - __uint_as_float(h.z));
+                    l.w = to_tf32(v.w - __uint_as_float(h.w));
+                    *reinterpret_cast<uint4 *>(hi + c) = h;
+                    *reinterpret_cast<uint4 *>(lo + c) = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor core reads
+                mbar_arrive(ready(s));
+            }
         }
     } else {
-        // ---- split warps: x -> (tf32(x), tf32(x - tf32(x))) ----
-        const int t = threadIdx.x - 64;                                   // 0..255
-        for (int kb = 0; kb < kblocks; ++kb) {
-            const int s = kb % STAGES;
-            mbar_wait(full(s), (kb / STAGES) & 1);
-            float4 *hi = reinterpret_cast<float4 *>(base_ptr + s * Cfg::kStageBytes);
-            float4 *lo = reinterpret_cast<float4 *>(base_ptr + s * Cfg::kStageBytes + Cfg::kXBytes);
+        // ---- epilogue warps: TMEM lane = row; warp w may touch lanes 32*(w%4) .. +31 ----
+        const int q = warp & 3;
+        float *tile = reinterpret_cast<float *>(base_ptr + Cfg::kRingBytes) + (warp - 2 - kSplitWarps) * 32 * 33;
+        uint32_t it = 0;
+        for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+            const int m0 = (int)(t / n_tiles) * kBM, n0 = (int)(t % n_tiles) * BN;
+            const uint32_t buf = it % NBUF;
+            const uint32_t acc = tmem_base + buf * Cfg::kSetCols + ((uint32_t)(q * 32) << 16);
+            mbar_wait(acc_full(buf), (it / NBUF) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32], u[32];
+                tmem_ld32(acc + (uint32_t)(c * 32), v);
+                tmem_ld32(acc + (uint32_t)(BN + c * 32), u);
+                if (NACC == 4) {
+                    // small + small' first (same magnitude), then main + main', then the two sums
+                    uint32_t p[32], r[32];
+                    tmem_ld32(acc + (uint32_t)(2 * BN + c * 32), p);
+                    tmem_ld32(acc + (uint32_t)(3 * BN + c * 32), r);
 #pragma unroll
-            for (int c = t; c < Cfg::kXBytes / 16; c += 32 * kSplitWarps) {
-                const float4 v = hi[c];
-                uint4 h, l;
-                h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-                l.x = to_tf32(v.x - __uint_as_float(h.x));
-                l.y = to_tf32(v.y - __uint_as_float(h.y));
-                l.z = to_tf32(v.z - __uint_as_float(h.z));
-                l.w = to_tf32(v.w - __uint_as_float(h.w));
-                *reinterpret_cast<uint4 *>(hi + c) = h;
-                *reinterpret_cast<uint4 *>(lo + c) = l;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor core reads
-            mbar_arrive(ready(s));
-        }
-        // ---- epilogue: TMEM lane = row; warp w may touch lanes 32*(w%4) .. +31 ----
-        mbar_wait(acc_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int q = warp & 3;                                           // TMEM lane quarter of this warp
-        const int part = (warp - 2) >> 2;                                 // which of the 32-column blocks: c % 2 == part
-        float *tile = reinterpret_cast<float *>(base_ptr) + (warp - 2) * 32 * 33;   // the ring is idle now
-        for (int c = part; c < BN / 32; c += kSplitWarps / 4) {
-            uint32_t v[32], u[32];
-            tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-            tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c * 32), u);
-            const int col = n0 + c * 32;
-            const float b = (bias != nullptr && col + lane < N) ? bias[col + lane] : 0.f;
+                    for (int j = 0; j < 32; ++j) {
+                        v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+                        u[j] = __float_as_uint(__uint_as_float(p[j]) + __uint_as_float(r[j]));
+                    }
+                }
+                if (c == BN / 32 - 1) {                                   // everything is in registers: hand the set back
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(acc_empty(buf));
+                }
+                const int col = n0 + c * 32;
+                const float b = (bias != nullptr && col + lane < N) ? bias[col + lane] : 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(v[j]) + __uint_as_float(u[j]);
-            __syncwarp();
+                for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(v[j]) + __uint_as_float(u[j]);
+                __syncwarp();
 #pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
-                const int row = m0 + q * 32 + r;
-                float o = tile[r * 33 + lane] + b;
-                if (relu) o = fmaxf(o, 0.f);
-                if (row < M && col + lane < N) y[(long long)row * N + col + lane] = o;
+                for (int r = 0; r < 32; ++r) {
+                    const int row = m0 + q * 32 + r;
+                    float o = tile[r * 33 + lane] + b;
+                    if (relu) o = fmaxf(o, 0.f);
+                    if (row < M && col + lane < N && !dbg_no_store) y[(long long)row * N + col + lane] = o;
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(Cfg::kTmemCols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
 }
 
 // W -> (tf32(W), tf32(W - tf32(W))), once per call
@@ -282,11 +351,11 @@ bool make_map(CUtensorMap *map, const float *ptr, int rows, int cols, int box_ro
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NBUF, int NACC>
 cudaError_t launch_linear(const float *x, const float *w, const float *bias, float *y, int M, int N, int K,
                           int relu, float *workspace, cudaStream_t stream) {
-    using Cfg = LinCfg<BN, STAGES>;
-    auto kern = linear_tf32x3_kernel<BN, STAGES>;
+    using Cfg = LinCfg<BN, STAGES, NBUF, NACC>;
+    auto kern = linear_tf32x3_kernel<BN, STAGES, NBUF, NACC>;
     static bool attr_set[64] = {false};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
@@ -303,8 +372,10 @@ cudaError_t launch_linear(const float *x, const float *w, const float *bias, flo
     split_weight_kernel<<<(unsigned)((n4 + 255) / 256 < 592 ? (n4 + 255) / 256 : 592), 256, 0, stream>>>(
         reinterpret_cast<const float4 *>(w), reinterpret_cast<float4 *>(whi), reinterpret_cast<float4 *>(wlo), n4);
     note_launch();
-    dim3 grid((M + kBM - 1) / kBM, (N + BN - 1) / BN);
-    kern<<<grid, kThreads, Cfg::kSmem, stream>>>(mx, mwh, mwl, bias, y, M, N, K, relu);
+    long long tiles = (long long)((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
+    const long long grid = tiles < sm_count() ? tiles : sm_count();     // persistent: one CTA per SM
+    kern<<<(unsigned)grid, kThreads, Cfg::kSmem, stream>>>(mx, mwh, mwl, bias, y, M, N, K, relu,
+                                                           option_value(OPT_WHATIF_LINEAR));
     note_launch();
     return cudaGetLastError();
 }
@@ -320,10 +391,16 @@ cudaError_t launch_linear_tf32x3(const float *x, const float *w, const float *bi
         *handled = false;
         return cudaSuccess;
     }
-    if (N % 256 == 0 || N > 192) return launch_linear<256, 2>(x, w, bias, y, M, N, K, relu, workspace, stream);
-    if (N > 128) return launch_linear<192, 2>(x, w, bias, y, M, N, K, relu, workspace, stream);
-    if (N > 96) return launch_linear<128, 3>(x, w, bias, y, M, N, K, relu, workspace, stream);
-    return launch_linear<96, 4>(x, w, bias, y, M, N, K, relu, workspace, stream);
+    // tile width: 128 columns, or 96 when that wastes fewer (N = 96, 192, 288 ...)
+    const int waste128 = (N + 127) / 128 * 128 - N, waste96 = (N + 95) / 96 * 96 - N;
+    const int variant = option_value(OPT_LINEAR_VARIANT);   // experiments: 1 = 256-wide tiles, one accumulator set
+    if (variant == 1 && N % 256 == 0) return launch_linear<256, 2, 1, 2>(x, w, bias, y, M, N, K, relu, workspace, stream);
+    if (variant == 2) {                                  // four accumulators, one set
+        if (waste96 < waste128) return launch_linear<96, 3, 1, 4>(x, w, bias, y, M, N, K, relu, workspace, stream);
+        return launch_linear<128, 3, 1, 4>(x, w, bias, y, M, N, K, relu, workspace, stream);
+    }
+    if (waste96 < waste128) return launch_linear<96, 3, 2, 2>(x, w, bias, y, M, N, K, relu, workspace, stream);
+    return launch_linear<128, 3, 2, 2>(x, w, bias, y, M, N, K, relu, workspace, stream);
 }
 
 }  // namespace msda

@@ -70,6 +70,8 @@ static int option_index(const char *name) {
     if (!strcmp(name, "tile_order")) return OPT_TILE_ORDER;
     if (!strcmp(name, "ctas_per_sm")) return OPT_CTAS_PER_SM;
     if (!strcmp(name, "whatif_drop_reds")) return OPT_WHATIF_DROP_REDS;
+    if (!strcmp(name, "linear_variant")) return OPT_LINEAR_VARIANT;
+    if (!strcmp(name, "whatif_linear")) return OPT_WHATIF_LINEAR;
     return -1;
 }
 

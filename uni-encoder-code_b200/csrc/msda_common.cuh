@@ -428,6 +428,6 @@ void note_launch();                   // increments the library launch counter
 int sm_count();                       // SMs of the current device (cached)
 int option_value(int which);          // tuning knobs, see msda_api.cu
 enum { OPT_FWD_VARIANT = 0, OPT_BWD_VARIANT = 1, OPT_TILE_ORDER = 2, OPT_CTAS_PER_SM = 3,
-       OPT_WHATIF_DROP_REDS = 4, OPT_COUNT = 5 };
+       OPT_WHATIF_DROP_REDS = 4, OPT_LINEAR_VARIANT = 5, OPT_WHATIF_LINEAR = 6, OPT_COUNT = 7 };
 
 }  // namespace msda
