@@ -6,6 +6,7 @@
 // disabled, msdeformattn.py:338; TF32 matmuls are off by default in torch).  A plain TF32 GEMM would
 // change the results (10-bit mantissa), so this kernel uses the error-compensated split
 //     x = x_hi + x_lo,   x_hi = tf32(x),   x_lo = tf32(x - x_hi)
+// (for X, x_hi = the upper 19 bits, which is what the tensor core reads from the raw fp32 tile)
 //     X * W^T  ~=  Xhi*Whi^T + Xlo*Whi^T + Xhi*Wlo^T          (the dropped Xlo*Wlo^T term is ~2^-22)
 // with fp32 accumulation in tensor memory: fp32-class accuracy at tensor-core speed.
 //
@@ -18,9 +19,8 @@
 //   pre-pass  W is split once per call into Whi / Wlo (workspace, 2 x N x K floats);
 //   warp 0   one thread: TMA loads of the fp32 X tile (128 x 32) and the Whi / Wlo tiles (BN x 32) of
 //            each k-block into a STAGES-deep ring (128-byte swizzle: a tile row is one swizzle span);
-//   warps 2-5 split the landed X tile element-wise into hi (in place) and lo (second buffer, same
-//            offsets -- the swizzle is irrelevant to an element-wise pass), fence to the async proxy
-//            and hand the stage to
+//   warps 2-5 compute x_lo of the landed X tile element-wise into a second buffer (same offsets -- the
+//            swizzle is irrelevant to an element-wise pass), fence to the async proxy and hand it to
 //   warp 1   one thread: 3 x 4 tcgen05.mma.kind::tf32 (128 x BN x 8) per k-block into one of TWO
 //            {main, small} accumulator sets in TMEM, tcgen05.commit to release the stage;
 //   warps 6-9 epilogue of tile i while tile i+1 is being computed: tcgen05.ld both accumulators
@@ -195,7 +195,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     } else if (warp == 1) {
         // ---- MMA issuer ----
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(kBM, BN);
+            constexpr uint32_t idesc = umma_idesc(kBM, BN), idesc2 = umma_idesc(kBM, 2 * BN > 256 ? BN : 2 * BN);
             uint32_t g = 0, it = 0;
             for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
                 const uint32_t buf = it % NBUF;
@@ -204,23 +204,35 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int kb = 0; kb < kblocks; ++kb, ++g) {
                     const int s = g % STAGES;
-                    mbar_wait(ready(s), (g / STAGES) & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t xh = base + s * Cfg::kStageBytes, xl = xh + Cfg::kXBytes;
                     const uint32_t wh = xl + Cfg::kXBytes, wl = wh + Cfg::kWBytes;
+                    // the tensor core reads the upper 19 bits of an fp32 word as tf32, so the X tile as TMA
+                    // delivered it IS x_hi = trunc(x): the two products that need only x_hi start at once ...
+                    mbar_wait(full(s), (g / STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                     for (int k = 0; k < kBK / kUmmaK; ++k) {
-                        const uint32_t ko = k * kUmmaK * 4;                // 32 bytes inside the swizzle span
                         if (dbg_no_mma) continue;
-                        if (NACC == 2) {           // {main, small}
-                            umma_tf32(acc_set + BN, umma_desc(xl + ko), umma_desc(wh + ko), idesc, (kb | k) != 0);
-                            umma_tf32(acc_set + BN, umma_desc(xh + ko), umma_desc(wl + ko), idesc, 1);
-                            umma_tf32(acc_set, umma_desc(xh + ko), umma_desc(wh + ko), idesc, (kb | k) != 0);
+                        const uint32_t ko = k * kUmmaK * 4;                // 32 bytes inside the swizzle span
+                        if (NACC == 2) {
+                            // {main, small} are adjacent in TMEM and W_hi, W_lo adjacent in the stage: ONE MMA of
+                            // width 2*BN computes x_hi * [W_hi; W_lo]^T into both (x_hi is read once)
+                            umma_tf32(acc_set, umma_desc(xh + ko), umma_desc(wh + ko), idesc2, (kb | k) != 0);
+                            if (2 * BN > 256) umma_tf32(acc_set + BN, umma_desc(xh + ko), umma_desc(wl + ko), idesc, (kb | k) != 0);
                         } else {                   // {main (even k-steps), main (odd), small: xl*wh, small: xh*wl}
-                            umma_tf32(acc_set + 2 * BN, umma_desc(xl + ko), umma_desc(wh + ko), idesc, (kb | k) != 0);
-                            umma_tf32(acc_set + 3 * BN, umma_desc(xh + ko), umma_desc(wl + ko), idesc, (kb | k) != 0);
                             umma_tf32(acc_set + (k & 1) * BN, umma_desc(xh + ko), umma_desc(wh + ko), idesc, (kb | (k >> 1)) != 0);
+                            umma_tf32(acc_set + 3 * BN, umma_desc(xh + ko), umma_desc(wl + ko), idesc, (kb | k) != 0);
                         }
+                    }
+                    // ... and x_lo * w_hi follows when the split warps have produced x_lo
+                    mbar_wait(ready(s), (g / STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                    for (int k = 0; k < kBK / kUmmaK; ++k) {
+                        if (dbg_no_mma) continue;
+                        const uint32_t ko = k * kUmmaK * 4;
+                        if (NACC == 2) umma_tf32(acc_set + BN, umma_desc(xl + ko), umma_desc(wh + ko), idesc, 1);
+                        else umma_tf32(acc_set + 2 * BN, umma_desc(xl + ko), umma_desc(wh + ko), idesc, (kb | k) != 0);
                     }
                     umma_commit(empty(s));                                // stage reusable once these MMAs are done
                 }
@@ -228,7 +240,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             }
         }
     } else if (warp < 2 + kSplitWarps) {
-        // ---- split warps: x -> (tf32(x), tf32(x - tf32(x))) ----
+        // ---- split warps: x_lo = tf32(x - trunc19(x)) ----
         const int t0 = threadIdx.x - 64;
         uint32_t g = 0;
         for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
@@ -240,13 +252,11 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 #pragma unroll
                 for (int c = t0; c < (dbg_no_split ? 0 : Cfg::kXBytes / 16); c += 32 * kSplitWarps) {
                     const float4 v = hi[c];
-                    uint4 h, l;
-                    h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-                    l.x = to_tf32(v.x - __uint_as_float(h.x));
-                    l.y = to_tf32(v.y - __uint_as_float(h.y));
-                    l.z = to_tf32(v.z - __uint_as_float(h.z));
-                    l.w = to_tf32(v.w - __uint_as_float(h.w));
-                    *reinterpret_cast<uint4 *>(hi + c) = h;
+                    uint4 l;                  // x_lo = tf32(x - trunc(x)); the X tile itself is left as it is
+                    l.x = to_tf32(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u));
+                    l.y = to_tf32(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u));
+                    l.z = to_tf32(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u));
+                    l.w = to_tf32(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
                     *reinterpret_cast<uint4 *>(lo + c) = l;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor core reads
