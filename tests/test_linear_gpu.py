@@ -10,9 +10,10 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-# measured: 1.0-1.6x (K <= 256), 2.9x (K = 1024: the tensor core truncates when it adds into the fp32
-# accumulator, so the error grows with the number of accumulations)
-ERR_FACTOR = 4.0
+# measured: 1.0-1.6x.  The tensor core truncates when it adds into the fp32 accumulator, so the error grows
+# with the number of accumulations per accumulator: in_features >= 512 use four accumulators (1.3x at 1024;
+# with two it was 2.9x)
+ERR_FACTOR = 3.0
 
 
 def case(rows, out_f, in_f, seed, bias=True, scale=1.0):

@@ -108,7 +108,6 @@ template <int BN, int STAGES, int NBUF, int NACC>
 struct LinCfg {
     static constexpr int kXBytes = kBM * kBK * 4, kWBytes = BN * kBK * 4;
     static constexpr int kStageBytes = 2 * kXBytes + 2 * kWBytes;  // X hi, X lo, W hi, W lo
-    static constexpr int kTxBytes = kXBytes + 2 * kWBytes;         // what TMA delivers per stage
     static constexpr int kRingBytes = STAGES * kStageBytes;
     static constexpr int kEpiBytes = kEpiWarps * 32 * 33 * 4;      // 32 x 32 transpose tile (padded) per epilogue warp
     static constexpr int kSmem = kRingBytes + kEpiBytes + 1024 /* alignment slack */ + 256 /* barriers */;
@@ -405,7 +404,10 @@ cudaError_t launch_linear_tf32x3(const float *x, const float *w, const float *bi
     const int waste128 = (N + 127) / 128 * 128 - N, waste96 = (N + 95) / 96 * 96 - N;
     const int variant = option_value(OPT_LINEAR_VARIANT);   // experiments: 1 = 256-wide tiles, one accumulator set
     if (variant == 1 && N % 256 == 0) return launch_linear<256, 2, 1, 2>(x, w, bias, y, M, N, K, relu, workspace, stream);
-    if (variant == 2) {                                  // four accumulators, one set
+    // long reductions: the truncating accumulation makes the error grow with the number of MMAs per
+    // accumulator, so from in_features = 512 on the products are spread over four accumulators (one set:
+    // the epilogue is not overlapped, ~15 % slower) -- error at the level of an fp32 SIMT GEMM again
+    if (variant == 2 || (variant == 0 && K >= 512)) {
         if (waste96 < waste128) return launch_linear<96, 3, 1, 4>(x, w, bias, y, M, N, K, relu, workspace, stream);
         return launch_linear<128, 3, 1, 4>(x, w, bias, y, M, N, K, relu, workspace, stream);
     }
