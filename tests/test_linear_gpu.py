@@ -135,8 +135,31 @@ def test_encoder_layer_with_tensor_core_linears_matches_torch_linears(pkg):
             n2 = pkg.launch_count()
         assert n1 - n0 == 2 and n2 - n1 == 2 + (2 * 6 + 2) * 2   # + ((split + GEMM) x 6 linears + 2 add-norms) x 2 layers
         assert (ya - yb).abs().max().item() <= 5e-5, (ya - yb).abs().max().item()
-        yc = b(srcs, pos)[0]                                   # autograd on: torch GEMMs
-        assert torch.equal(yc, a(srcs, pos)[0])
+        # autograd on: forward and grad_x GEMMs on the tensor cores, everything else torch
+        srcs_a = [t.clone().requires_grad_(True) for t in srcs]
+        srcs_b = [t.clone().requires_grad_(True) for t in srcs]
+        cot = torch.randn_like(ya)
+        (a(srcs_a, pos)[0] * cot).sum().backward()
+        n3 = pkg.launch_count()
+        yc = b(srcs_b, pos)[0]
+        (yc * cot).sum().backward()
+        # per layer: MSDA fwd + bwd, 6 x (split + GEMM) forward, 6 x (split + GEMM) for grad_x
+        assert pkg.launch_count() - n3 == 2 * (2 + 12 + 12)
+        assert (yc - ya).abs().max().item() <= 5e-5
+        # gradients pass through floor() of the sampling locations: a 1e-6 difference in a location next to
+        # a cell edge moves the point into the neighbouring cell, where the location gradient differs by
+        # O(1).  torch against torch with 1e-6 input noise differs by 4e-4 .. 5e-3 in relative L2 here
+        # (tools/dbg_train_linear.py), so that is the yardstick; everything downstream of the last MSDA
+        # call (last layer's FFN) has no such term and must agree to rounding
+        def rel(u, v):
+            return (u - v).norm().item() / max(v.norm().item(), 1e-12)
+        for ga, gb in zip(srcs_a, srcs_b):
+            assert rel(gb.grad, ga.grad) <= 1e-2
+        last = f"encoder.layers.{kw['num_encoder_layers'] - 1}."
+        for (na, pa), (nb, pb) in zip(a.named_parameters(), b.named_parameters()):
+            if pa.grad is not None:
+                exact = na.startswith(last) and ("linear2" in na or "norm2" in na)
+                assert rel(pb.grad, pa.grad) <= (2e-5 if exact else 1e-2), na
     finally:
         torch.backends.cuda.matmul.allow_tf32 = old
 
@@ -157,3 +180,14 @@ def test_add_layernorm_matches_torch(pkg, rows, cols, with_res):
     assert err <= 2 * err32 + 1e-6, (err, err32)
     with pytest.raises(RuntimeError, match="add_layernorm needs"):
         pkg.add_layernorm(x[:, :100].contiguous(), None, w[:100].contiguous(), b[:100].contiguous())
+
+
+def test_linear_autograd_function_matches_torch(pkg):
+    x, w, b = case(500, 256, 128, seed=12)
+    x1, w1, b1 = (t.clone().requires_grad_(True) for t in (x, w, b))
+    x2, w2, b2 = (t.clone().requires_grad_(True) for t in (x, w, b))
+    cot = torch.randn(500, 256, device=DEV)
+    (pkg.LinearTF32x3Function.apply(x1, w1, b1) * cot).sum().backward()
+    (F.linear(x2.double(), w2.double(), b2.double()) * cot.double()).sum().backward()
+    for mine, ref in ((x1, x2), (w1, w2), (b1, b2)):
+        assert (mine.grad.double() - ref.grad.double()).abs().max().item() <= 1e-5 * max(1.0, ref.grad.abs().max().item())

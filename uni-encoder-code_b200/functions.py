@@ -57,3 +57,36 @@ class MSDeformAttnFusedFunction(Function):
         grad_value, grad_off, grad_logits = ops.ms_deform_attn_fused_backward(
             value, shapes, lsi, ref, off, logits, grad_output)
         return grad_value, None, None, None, grad_off, grad_logits
+
+
+class LinearTF32x3Function(Function):
+    """``apply(x, weight, bias)`` = ``F.linear`` with the forward GEMM and the input-gradient GEMM
+    (``grad_x = grad_y @ weight``) on the tensor cores (ops.linear_tf32x3); the weight gradient
+    (``grad_y^T @ x``, reduction over the rows) and the bias gradient use torch's fp32 kernels.
+    Needs in_features and out_features divisible by 32."""
+
+    @staticmethod
+    def supported(x, weight) -> bool:
+        return (ops.linear_tf32x3_supported(x, weight) and x.is_contiguous()
+                and weight.size(0) % 32 == 0 and weight.size(1) % 32 == 0)
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return ops.linear_tf32x3(x, weight.contiguous(), bias)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_y):
+        x, weight = ctx.saved_tensors
+        grad_y = grad_y.contiguous()
+        grad_x = grad_w = grad_b = None
+        if ctx.needs_input_grad[0]:
+            grad_x = ops.linear_tf32x3(grad_y, weight.t().contiguous(), None)
+        g2 = grad_y.reshape(-1, grad_y.size(-1))
+        if ctx.needs_input_grad[1]:
+            grad_w = g2.t() @ x.reshape(-1, x.size(-1))
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            grad_b = g2.sum(0)
+        return grad_x, grad_w, grad_b

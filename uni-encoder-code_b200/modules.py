@@ -29,7 +29,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
-from .functions import MSDeformAttnFunction, MSDeformAttnFusedFunction
+from .functions import LinearTF32x3Function, MSDeformAttnFunction, MSDeformAttnFusedFunction
 
 CoreFn = Callable[..., torch.Tensor]
 
@@ -38,10 +38,14 @@ def _linear(layer: nn.Linear, x, impl: str, relu: bool = False):
     """``layer(x)`` (+ ReLU).  impl == "tf32x3" selects the inference kernels of SURVEY 8f.3 (this GEMM and the
     fused residual + LayerNorm of `_add_norm`): in inference (autograd off) the fp32 GEMM runs on the
     tensor cores as an error-compensated 3xTF32 product (ops.linear_tf32x3); with autograd
-    on, and for any shape the kernel does not cover, torch's own fp32 GEMM is used as in the reference."""
+    on, the forward and the input-gradient GEMMs do (LinearTF32x3Function; the weight gradient stays a
+    torch GEMM); for any shape the kernel does not cover torch's own fp32 GEMM is used as in the reference."""
     if impl == "tf32x3" and not torch.is_grad_enabled() and x.is_contiguous() \
             and ops.linear_tf32x3_supported(x, layer.weight):
         return ops.linear_tf32x3(x, layer.weight, layer.bias, relu=relu)
+    if impl == "tf32x3" and torch.is_grad_enabled() and LinearTF32x3Function.supported(x, layer.weight):
+        y = LinearTF32x3Function.apply(x, layer.weight, layer.bias)      # forward and grad_x on the tensor cores
+        return F.relu(y) if relu else y
     if impl not in ("torch", "tf32x3"):
         raise ValueError(f"unknown linear implementation {impl!r}")
     y = layer(x)
