@@ -137,7 +137,10 @@ int msda_b200_fused_backward_f32(const float *grad_output, const float *value,
  * (torch.nn.functional.linear semantics, row-major contiguous fp32; bias may be NULL; relu != 0
  * applies max(., 0) to the result).  Computed on the sm_100a tensor cores with the error-compensated
  * 3 x TF32 split (fp32-class accuracy, fp32 accumulation).  `workspace`: device scratch of
- * 2 * out_features * in_features floats (the split weight; the library never allocates).  Requires
+ * 2 * out_features * in_features floats (the split weight; the library never allocates), or NULL: the
+ * weight is then split inside the kernel (for a one-shot "weight", e.g. the transposed activations of a
+ * weight-gradient GEMM).  When the output has few tiles and in_features is very large the reduction is
+ * spread over several CTAs per tile (split-K: y is zero-filled and accumulated with reductions).  Requires
  * in_features % 32 == 0, out_features % 4 == 0 and 16-byte aligned x / weight / workspace;
  * MSDA_ERR_UNSUPPORTED otherwise.
  */

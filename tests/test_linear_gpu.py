@@ -149,7 +149,7 @@ def test_encoder_layer_with_tensor_core_linears_matches_torch_linears(pkg):
         # gradients pass through floor() of the sampling locations: a 1e-6 difference in a location next to
         # a cell edge moves the point into the neighbouring cell, where the location gradient differs by
         # O(1).  torch against torch with 1e-6 input noise differs by 4e-4 .. 5e-3 in relative L2 here
-        # (tools/dbg_train_linear.py), so that is the yardstick; everything downstream of the last MSDA
+        # (measured), so that is the yardstick; everything downstream of the last MSDA
         # call (last layer's FFN) has no such term and must agree to rounding
         def rel(u, v):
             return (u - v).norm().item() / max(v.norm().item(), 1e-12)
@@ -191,3 +191,19 @@ def test_linear_autograd_function_matches_torch(pkg):
     (F.linear(x2.double(), w2.double(), b2.double()) * cot.double()).sum().backward()
     for mine, ref in ((x1, x2), (w1, w2), (b1, b2)):
         assert (mine.grad.double() - ref.grad.double()).abs().max().item() <= 1e-5 * max(1.0, ref.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("rows,out_f,in_f", [(4096, 256, 256), (8192, 96, 256), (2080, 1024, 256), (6400, 256, 1024),
+                                            (64, 128, 64)])
+def test_linear_weight_gradient_gemm_split_k_in_kernel_split(pkg, rows, out_f, in_f):
+    """grad_w = grad_y^T @ x through the same kernel: transposed operands, 'weight' split in the kernel,
+    reduction over the rows spread over several CTAs per output tile (reductions into a zeroed output)."""
+    g = torch.Generator().manual_seed(rows + in_f)
+    gy = torch.randn(rows, out_f, generator=g).to(DEV)
+    x = torch.randn(rows, in_f, generator=g).to(DEV)
+    gw = pkg.linear_tf32x3(gy.t().contiguous(), x.t().contiguous(), None, split_weight_in_kernel=True)
+    ref = gy.double().t() @ x.double()
+    err = (gw.double() - ref).abs().max().item()
+    err32 = ((gy.t() @ x).double() - ref).abs().max().item()
+    assert gw.shape == (out_f, in_f)
+    assert err <= ERR_FACTOR * err32 + 1e-6, (err, err32)

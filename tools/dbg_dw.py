@@ -1,0 +1,21 @@
+import os, sys, json, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from __graft_entry__ import load_package
+pkg = load_package(); dev = "cuda:0"
+def t(fn, n=10):
+    for _ in range(3): fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+M = 172032
+for out_f, in_f in ((256, 256), (192, 256), (96, 256), (1024, 256), (256, 1024)):
+    gy = torch.randn(M, out_f, device=dev); x = torch.randn(M, in_f, device=dev)
+    gyt, xt = gy.t().contiguous(), x.t().contiguous()
+    r = {"out": out_f, "in": in_f,
+         "torch_dw_ms": t(lambda: gy.t() @ x),
+         "transpose_gy_ms": t(lambda: gy.t().contiguous()), "transpose_x_ms": t(lambda: x.t().contiguous()),
+         "kernel_dw_ms": t(lambda: pkg.linear_tf32x3(gyt, xt, None, split_weight_in_kernel=True))}
+    print(json.dumps(r), flush=True)

@@ -120,11 +120,18 @@ struct LinCfg {
     static_assert(NBUF * kSetCols <= 512 && BN % 32 == 0 && kStageBytes % 1024 == 0 && (NACC == 2 || NACC == 4), "tile shape");
 };
 
-template <int BN, int STAGES, int NBUF, int NACC>
+// WSPLIT: W arrives as plain fp32 (map_wh) and is split inside the kernel like X -- for a one-shot "weight"
+//         such as the transposed activations of a weight-gradient GEMM, where a pre-pass would cost a full
+//         extra read and two writes of it.
+// k_chunks > 1 (split-K): an output tile is computed by k_chunks CTAs-worth of work, each over kb_per_chunk
+//         k-blocks, and added into y (zeroed by the launcher) with red.global.add -- for GEMMs with few
+//         output tiles and a very long reduction (weight gradients: reduction over the rows).
+template <int BN, int STAGES, int NBUF, int NACC, bool WSPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wh,
                      const __grid_constant__ CUtensorMap map_wl, const float *__restrict__ bias,
-                     float *__restrict__ y, int M, int N, int K, int relu, int whatif) {
+                     float *__restrict__ y, int M, int N, int K, int relu, int whatif, int k_chunks,
+                     int kb_per_chunk) {
     using Cfg = LinCfg<BN, STAGES, NBUF, NACC>;
     extern __shared__ uint8_t smem_dyn[];
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;         // 128-byte swizzle: 1024-byte aligned tiles
@@ -144,10 +151,22 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     // 1 no MMAs, 2 no split work, 4 no output stores, 8 no W loads, 16 no X loads
     const bool dbg_no_mma = whatif & 1, dbg_no_split = whatif & 2, dbg_no_store = whatif & 4, dbg_no_w = whatif & 8,
                dbg_no_x = whatif & 16;
-    const int kblocks = K / kBK;
-    const int k_rot = (int)(blockIdx.x % (unsigned)kblocks);
+    const int kblocks_all = K / kBK;
     const int n_tiles = (N + BN - 1) / BN;
-    const long long tiles = (long long)((M + kBM - 1) / kBM) * n_tiles;   // n fastest: the N-tiles of a row block run together
+    // work items: (row block, column block, k chunk), chunk fastest
+    const long long tiles = (long long)((M + kBM - 1) / kBM) * n_tiles * k_chunks;
+    // item -> (m0, n0, first k-block, number of k-blocks, rotation of the k order)
+    auto decode = [&](long long t, int &m0, int &n0, int &kb0, int &nkb, int &rot) {
+        const int chunk = (int)(t % k_chunks);
+        const long long o = t / k_chunks;
+        m0 = (int)(o / n_tiles) * kBM;
+        n0 = (int)(o % n_tiles) * BN;
+        kb0 = chunk * kb_per_chunk;
+        nkb = min(kb_per_chunk, kblocks_all - kb0);
+        // every CTA starts its k loop at a different k-block: at any moment the SMs read different lines
+        // of W (which all of them share) instead of queueing on the same L2 lines
+        rot = (int)(blockIdx.x % (unsigned)nkb);
+    };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -176,18 +195,17 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         if (lane == 0) {
             uint32_t g = 0;                                               // k-blocks issued so far (ring position)
             for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-                const int m0 = (int)(t / n_tiles) * kBM, n0 = (int)(t % n_tiles) * BN;
-                for (int kb = 0; kb < kblocks; ++kb, ++g) {
-                    // every CTA starts its k loop at a different k-block: at any moment the SMs read different
-                    // lines of W (which all of them share) instead of queueing on the same L2 lines
-                    const int kk = (kb + k_rot) % kblocks;
+                int m0, n0, kb0, nkb, rot;
+                decode(t, m0, n0, kb0, nkb, rot);
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int kk = kb0 + (kb + rot) % nkb;
                     const int s = g % STAGES;
                     mbar_wait(empty(s), ((g / STAGES) & 1) ^ 1);
                     const uint32_t st = base + s * Cfg::kStageBytes;
-                    mbar_arrive_expect_tx(full(s), (dbg_no_x ? 0 : Cfg::kXBytes) + (dbg_no_w ? 0 : 2 * Cfg::kWBytes));
+                    mbar_arrive_expect_tx(full(s), (dbg_no_x ? 0 : Cfg::kXBytes) + (dbg_no_w ? 0 : (WSPLIT ? 1 : 2) * Cfg::kWBytes));
                     if (!dbg_no_x) tma_load_2d(st, &map_x, full(s), kk * kBK, m0);
                     if (!dbg_no_w) tma_load_2d(st + 2 * Cfg::kXBytes, &map_wh, full(s), kk * kBK, n0);
-                    if (!dbg_no_w) tma_load_2d(st + 2 * Cfg::kXBytes + Cfg::kWBytes, &map_wl, full(s), kk * kBK, n0);
+                    if (!dbg_no_w && !WSPLIT) tma_load_2d(st + 2 * Cfg::kXBytes + Cfg::kWBytes, &map_wl, full(s), kk * kBK, n0);
                 }
             }
         }
@@ -201,7 +219,9 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 const uint32_t acc_set = tmem_base + buf * Cfg::kSetCols;
                 mbar_wait(acc_empty(buf), ((it / NBUF) & 1) ^ 1);        // the epilogue has drained this set
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                for (int kb = 0; kb < kblocks; ++kb, ++g) {
+                int m0_, n0_, kb0_, nkb, rot_;
+                decode(t, m0_, n0_, kb0_, nkb, rot_);
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
                     const int s = g % STAGES;
                     const uint32_t xh = base + s * Cfg::kStageBytes, xl = xh + Cfg::kXBytes;
                     const uint32_t wh = xl + Cfg::kXBytes, wl = wh + Cfg::kWBytes;
@@ -216,11 +236,15 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                         if (NACC == 2) {
                             // {main, small} are adjacent in TMEM and W_hi, W_lo adjacent in the stage: ONE MMA of
                             // width 2*BN computes x_hi * [W_hi; W_lo]^T into both (x_hi is read once)
-                            umma_tf32(acc_set, umma_desc(xh + ko), umma_desc(wh + ko), idesc2, (kb | k) != 0);
-                            if (2 * BN > 256) umma_tf32(acc_set + BN, umma_desc(xh + ko), umma_desc(wl + ko), idesc, (kb | k) != 0);
+                            if (WSPLIT) {          // W_lo is not there yet: main product only
+                                umma_tf32(acc_set, umma_desc(xh + ko), umma_desc(wh + ko), idesc, (kb | k) != 0);
+                            } else {
+                                umma_tf32(acc_set, umma_desc(xh + ko), umma_desc(wh + ko), idesc2, (kb | k) != 0);
+                                if (2 * BN > 256) umma_tf32(acc_set + BN, umma_desc(xh + ko), umma_desc(wl + ko), idesc, (kb | k) != 0);
+                            }
                         } else {                   // {main (even k-steps), main (odd), small: xl*wh, small: xh*wl}
                             umma_tf32(acc_set + (k & 1) * BN, umma_desc(xh + ko), umma_desc(wh + ko), idesc, (kb | (k >> 1)) != 0);
-                            umma_tf32(acc_set + 3 * BN, umma_desc(xh + ko), umma_desc(wl + ko), idesc, (kb | k) != 0);
+                            if (!WSPLIT) umma_tf32(acc_set + 3 * BN, umma_desc(xh + ko), umma_desc(wl + ko), idesc, (kb | k) != 0);
                         }
                     }
                     // ... and x_lo * w_hi follows when the split warps have produced x_lo
@@ -230,8 +254,13 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     for (int k = 0; k < kBK / kUmmaK; ++k) {
                         if (dbg_no_mma) continue;
                         const uint32_t ko = k * kUmmaK * 4;
-                        if (NACC == 2) umma_tf32(acc_set + BN, umma_desc(xl + ko), umma_desc(wh + ko), idesc, 1);
-                        else umma_tf32(acc_set + 2 * BN, umma_desc(xl + ko), umma_desc(wh + ko), idesc, (kb | k) != 0);
+                        if (NACC == 2) {
+                            if (WSPLIT) umma_tf32(acc_set + BN, umma_desc(xh + ko), umma_desc(wl + ko), idesc, (kb | k) != 0);
+                            umma_tf32(acc_set + BN, umma_desc(xl + ko), umma_desc(wh + ko), idesc, 1);
+                        } else {
+                            if (WSPLIT) umma_tf32(acc_set + 3 * BN, umma_desc(xh + ko), umma_desc(wl + ko), idesc, (kb | k) != 0);
+                            umma_tf32(acc_set + 2 * BN, umma_desc(xl + ko), umma_desc(wh + ko), idesc, (kb | k) != 0);
+                        }
                     }
                     umma_commit(empty(s));                                // stage reusable once these MMAs are done
                 }
@@ -243,20 +272,26 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         const int t0 = threadIdx.x - 64;
         uint32_t g = 0;
         for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-            for (int kb = 0; kb < kblocks; ++kb, ++g) {
+            int m0_, n0_, kb0_, nkb, rot_;
+            decode(t, m0_, n0_, kb0_, nkb, rot_);
+            for (int kb = 0; kb < nkb; ++kb, ++g) {
                 const int s = g % STAGES;
                 mbar_wait(full(s), (g / STAGES) & 1);
-                float4 *hi = reinterpret_cast<float4 *>(base_ptr + s * Cfg::kStageBytes);
-                float4 *lo = reinterpret_cast<float4 *>(base_ptr + s * Cfg::kStageBytes + Cfg::kXBytes);
+                // the stage is [X | X_lo | W_hi | W_lo]; lo = tf32(v - trunc19(v)) goes kXBytes (X) or kWBytes (W) further
+                float4 *stage4 = reinterpret_cast<float4 *>(base_ptr + s * Cfg::kStageBytes);
+                constexpr int kX4 = Cfg::kXBytes / 16, kW4 = Cfg::kWBytes / 16;
 #pragma unroll
-                for (int c = t0; c < (dbg_no_split ? 0 : Cfg::kXBytes / 16); c += 32 * kSplitWarps) {
-                    const float4 v = hi[c];
-                    uint4 l;                  // x_lo = tf32(x - trunc(x)); the X tile itself is left as it is
+                for (int c = t0; c < (dbg_no_split ? 0 : kX4 + (WSPLIT ? kW4 : 0)); c += 32 * kSplitWarps) {
+                    const bool is_w = WSPLIT && c >= kX4;
+                    const int src = is_w ? c + kX4 : c;                   // W_hi starts 2 * kX4 into the stage
+                    const int dst = src + (is_w ? kW4 : kX4);
+                    const float4 v = stage4[src];
+                    uint4 l;
                     l.x = to_tf32(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u));
                     l.y = to_tf32(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u));
                     l.z = to_tf32(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u));
                     l.w = to_tf32(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
-                    *reinterpret_cast<uint4 *>(lo + c) = l;
+                    *reinterpret_cast<uint4 *>(stage4 + dst) = l;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor core reads
                 mbar_arrive(ready(s));
@@ -268,7 +303,8 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         float *tile = reinterpret_cast<float *>(base_ptr + Cfg::kRingBytes) + (warp - 2 - kSplitWarps) * 32 * 33;
         uint32_t it = 0;
         for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
-            const int m0 = (int)(t / n_tiles) * kBM, n0 = (int)(t % n_tiles) * BN;
+            int m0, n0, kb0, nkb_, rot_;
+            decode(t, m0, n0, kb0, nkb_, rot_);
             const uint32_t buf = it % NBUF;
             const uint32_t acc = tmem_base + buf * Cfg::kSetCols + ((uint32_t)(q * 32) << 16);
             mbar_wait(acc_full(buf), (it / NBUF) & 1);
@@ -294,7 +330,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     mbar_arrive(acc_empty(buf));
                 }
                 const int col = n0 + c * 32;
-                const float b = (bias != nullptr && col + lane < N) ? bias[col + lane] : 0.f;
+                const float b = (bias != nullptr && col + lane < N && kb0 == 0) ? bias[col + lane] : 0.f;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(v[j]) + __uint_as_float(u[j]);
                 __syncwarp();
@@ -303,7 +339,10 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     const int row = m0 + q * 32 + r;
                     float o = tile[r * 33 + lane] + b;
                     if (relu) o = fmaxf(o, 0.f);
-                    if (row < M && col + lane < N && !dbg_no_store) y[(long long)row * N + col + lane] = o;
+                    if (row < M && col + lane < N && !dbg_no_store) {
+                        if (k_chunks > 1) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(y + (long long)row * N + col + lane), "f"(o) : "memory");
+                        else y[(long long)row * N + col + lane] = o;
+                    }
                 }
                 __syncwarp();
             }
@@ -360,11 +399,11 @@ bool make_map(CUtensorMap *map, const float *ptr, int rows, int cols, int box_ro
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, int STAGES, int NBUF, int NACC>
+template <int BN, int STAGES, int NBUF, int NACC, bool WSPLIT>
 cudaError_t launch_linear(const float *x, const float *w, const float *bias, float *y, int M, int N, int K,
                           int relu, float *workspace, cudaStream_t stream) {
     using Cfg = LinCfg<BN, STAGES, NBUF, NACC>;
-    auto kern = linear_tf32x3_kernel<BN, STAGES, NBUF, NACC>;
+    auto kern = linear_tf32x3_kernel<BN, STAGES, NBUF, NACC, WSPLIT>;
     static bool attr_set[64] = {false};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
@@ -373,18 +412,38 @@ cudaError_t launch_linear(const float *x, const float *w, const float *bias, flo
         if (e != cudaSuccess) return e;
         attr_set[dev] = true;
     }
-    float *whi = workspace, *wlo = workspace + (size_t)N * K;
     CUtensorMap mx, mwh, mwl;
-    if (!make_map(&mx, x, M, K, kBM) || !make_map(&mwh, whi, N, K, BN) || !make_map(&mwl, wlo, N, K, BN))
-        return cudaErrorInvalidValue;
-    const long long n4 = (long long)N * K / 4;
-    split_weight_kernel<<<(unsigned)((n4 + 255) / 256 < 592 ? (n4 + 255) / 256 : 592), 256, 0, stream>>>(
-        reinterpret_cast<const float4 *>(w), reinterpret_cast<float4 *>(whi), reinterpret_cast<float4 *>(wlo), n4);
-    note_launch();
-    long long tiles = (long long)((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
+    if (WSPLIT) {
+        if (!make_map(&mx, x, M, K, kBM) || !make_map(&mwh, w, N, K, BN)) return cudaErrorInvalidValue;
+        mwl = mwh;
+    } else {
+        float *whi = workspace, *wlo = workspace + (size_t)N * K;
+        if (!make_map(&mx, x, M, K, kBM) || !make_map(&mwh, whi, N, K, BN) || !make_map(&mwl, wlo, N, K, BN))
+            return cudaErrorInvalidValue;
+        const long long n4 = (long long)N * K / 4;
+        split_weight_kernel<<<(unsigned)((n4 + 255) / 256 < 592 ? (n4 + 255) / 256 : 592), 256, 0, stream>>>(
+            reinterpret_cast<const float4 *>(w), reinterpret_cast<float4 *>(whi), reinterpret_cast<float4 *>(wlo), n4);
+        note_launch();
+    }
+    // split-K when the output has too few tiles to occupy the GPU and the reduction is long
+    const long long out_tiles = (long long)((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
+    const int kblocks = K / kBK;
+    int k_chunks = 1;
+    if (out_tiles * 2 <= sm_count() && kblocks >= 64 && !relu) {
+        const long long want = (2LL * sm_count() + out_tiles - 1) / out_tiles;    // ~2 work items per SM
+        k_chunks = (int)(want < kblocks / 16 ? want : kblocks / 16);
+        if (k_chunks < 1) k_chunks = 1;
+    }
+    const int kb_per_chunk = (kblocks + k_chunks - 1) / k_chunks;
+    k_chunks = (kblocks + kb_per_chunk - 1) / kb_per_chunk;
+    if (k_chunks > 1) {
+        cudaError_t e = cudaMemsetAsync(y, 0, (size_t)M * N * sizeof(float), stream);
+        if (e != cudaSuccess) return e;
+    }
+    const long long tiles = out_tiles * k_chunks;
     const long long grid = tiles < sm_count() ? tiles : sm_count();     // persistent: one CTA per SM
     kern<<<(unsigned)grid, kThreads, Cfg::kSmem, stream>>>(mx, mwh, mwl, bias, y, M, N, K, relu,
-                                                           option_value(OPT_WHATIF_LINEAR));
+                                                           option_value(OPT_WHATIF_LINEAR), k_chunks, kb_per_chunk);
     note_launch();
     return cudaGetLastError();
 }
@@ -396,23 +455,30 @@ cudaError_t launch_linear_tf32x3(const float *x, const float *w, const float *bi
                                  int relu, float *workspace, cudaStream_t stream, bool *handled) {
     *handled = true;
     if (M <= 0 || N <= 0 || K <= 0 || K % kBK != 0 || N % 4 != 0 ||
-        (reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(workspace)) % 16 != 0) {
+        (reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(workspace)) % 16 != 0 ||
+        ((long long)K * 4) % 16 != 0) {
         *handled = false;
         return cudaSuccess;
     }
     // tile width: 128 columns, or 96 when that wastes fewer (N = 96, 192, 288 ...)
     const int waste128 = (N + 127) / 128 * 128 - N, waste96 = (N + 95) / 96 * 96 - N;
+    const bool narrow = waste96 < waste128;
     const int variant = option_value(OPT_LINEAR_VARIANT);   // experiments: 1 = 256-wide tiles, one accumulator set
-    if (variant == 1 && N % 256 == 0) return launch_linear<256, 2, 1, 2>(x, w, bias, y, M, N, K, relu, workspace, stream);
+    if (workspace == nullptr) {
+        // one-shot weight: split inside the kernel; long reductions (the use case) -> four accumulators
+        if (narrow) return launch_linear<96, 3, 1, 4, true>(x, w, bias, y, M, N, K, relu, workspace, stream);
+        return launch_linear<128, 3, 1, 4, true>(x, w, bias, y, M, N, K, relu, workspace, stream);
+    }
+    if (variant == 1 && N % 256 == 0) return launch_linear<256, 2, 1, 2, false>(x, w, bias, y, M, N, K, relu, workspace, stream);
     // long reductions: the truncating accumulation makes the error grow with the number of MMAs per
     // accumulator, so from in_features = 512 on the products are spread over four accumulators (one set:
     // the epilogue is not overlapped, ~15 % slower) -- error at the level of an fp32 SIMT GEMM again
     if (variant == 2 || (variant == 0 && K >= 512)) {
-        if (waste96 < waste128) return launch_linear<96, 3, 1, 4>(x, w, bias, y, M, N, K, relu, workspace, stream);
-        return launch_linear<128, 3, 1, 4>(x, w, bias, y, M, N, K, relu, workspace, stream);
+        if (narrow) return launch_linear<96, 3, 1, 4, false>(x, w, bias, y, M, N, K, relu, workspace, stream);
+        return launch_linear<128, 3, 1, 4, false>(x, w, bias, y, M, N, K, relu, workspace, stream);
     }
-    if (waste96 < waste128) return launch_linear<96, 3, 2, 2>(x, w, bias, y, M, N, K, relu, workspace, stream);
-    return launch_linear<128, 3, 2, 2>(x, w, bias, y, M, N, K, relu, workspace, stream);
+    if (narrow) return launch_linear<96, 3, 2, 2, false>(x, w, bias, y, M, N, K, relu, workspace, stream);
+    return launch_linear<128, 3, 2, 2, false>(x, w, bias, y, M, N, K, relu, workspace, stream);
 }
 
 }  // namespace msda

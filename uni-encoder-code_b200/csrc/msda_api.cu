@@ -232,7 +232,7 @@ int msda_b200_fused_backward_f32(const float *grad_output, const float *value,
 
 int msda_b200_linear_f32(const float *x, const float *weight, const float *bias, float *y, int rows,
                          int out_features, int in_features, int relu, float *workspace, void *stream) {
-    if (!x || !weight || !y || !workspace) return MSDA_ERR_NULL_POINTER;
+    if (!x || !weight || !y) return MSDA_ERR_NULL_POINTER;
     if (rows <= 0 || out_features <= 0 || in_features <= 0) return MSDA_ERR_BAD_SHAPE;
     bool handled = false;
     cudaError_t e = launch_linear_tf32x3(x, weight, bias, y, rows, out_features, in_features, relu,

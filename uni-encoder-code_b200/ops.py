@@ -249,9 +249,10 @@ def linear_tf32x3_supported(x, weight) -> bool:
             and weight.size(1) % 32 == 0 and weight.size(0) % 4 == 0 and x.numel() > 0)
 
 
-def linear_tf32x3(x, weight, bias=None, relu=False):
+def linear_tf32x3(x, weight, bias=None, relu=False, split_weight_in_kernel=False):
     """``F.linear(x, weight, bias)`` (then ``relu`` if set) for fp32 CUDA tensors; ``x`` [..., in],
-    ``weight`` [out, in] with in % 32 == 0 and out % 4 == 0."""
+    ``weight`` [out, in] with in % 32 == 0 and out % 4 == 0.  ``split_weight_in_kernel``: no pre-pass over
+    (and no workspace for) the weight -- for a one-shot "weight" such as transposed activations."""
     if not x.is_cuda:
         raise RuntimeError("Not implemented on the CPU")
     for name, t in (("x", x), ("weight", weight)) + ((("bias", bias),) if bias is not None else ()):
@@ -266,11 +267,13 @@ def linear_tf32x3(x, weight, bias=None, relu=False):
     out_f, in_f = weight.shape
     rows = x.numel() // in_f
     y = torch.empty(x.shape[:-1] + (out_f,), dtype=x.dtype, device=x.device)
-    workspace = torch.empty(2 * out_f * in_f, dtype=torch.float32, device=x.device)
+    workspace = None if split_weight_in_kernel else \
+        torch.empty(2 * out_f * in_f, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         rc = _lib.lib.msda_b200_linear_f32(x.data_ptr(), weight.data_ptr(),
                                            bias.data_ptr() if bias is not None else None, y.data_ptr(),
-                                           rows, out_f, in_f, 1 if relu else 0, workspace.data_ptr(),
+                                           rows, out_f, in_f, 1 if relu else 0,
+                                           workspace.data_ptr() if workspace is not None else None,
                                            torch.cuda.current_stream(x.device).cuda_stream)
     _lib.check(rc, "linear_tf32x3")
     return y
