@@ -158,6 +158,9 @@ int msda_b200_add_layernorm_f32(const float *x, const float *residual, const flo
                                 const float *beta, float *y, long long rows, int cols, float eps,
                                 void *stream);
 
+/* y[cols, rows] = x[rows, cols]^T, fp32 (operand preparation for weight-gradient GEMMs). */
+int msda_b200_transpose_f32(const float *x, float *y, long long rows, int cols, void *stream);
+
 /*
  * Integer known-answer hook (no counterpart in the reference; it exposes the
  * integer work of cuh:43-58, 279-293 so tests can pin it bit-exactly).

@@ -143,8 +143,9 @@ def test_encoder_layer_with_tensor_core_linears_matches_torch_linears(pkg):
         n3 = pkg.launch_count()
         yc = b(srcs_b, pos)[0]
         (yc * cot).sum().backward()
-        # per layer: MSDA fwd + bwd, 6 x (split + GEMM) forward, 6 x (split + GEMM) for grad_x
-        assert pkg.launch_count() - n3 == 2 * (2 + 12 + 12)
+        # per layer: MSDA fwd + bwd, 6 x (split + GEMM) forward, 6 x (split + GEMM) for grad_x,
+        # 6 x (2 transposes + GEMM) for grad_w
+        assert pkg.launch_count() - n3 == 2 * (2 + 12 + 12 + 18)
         assert (yc - ya).abs().max().item() <= 5e-5
         # gradients pass through floor() of the sampling locations: a 1e-6 difference in a location next to
         # a cell edge moves the point into the neighbouring cell, where the location gradient differs by
@@ -201,9 +202,19 @@ def test_linear_weight_gradient_gemm_split_k_in_kernel_split(pkg, rows, out_f, i
     g = torch.Generator().manual_seed(rows + in_f)
     gy = torch.randn(rows, out_f, generator=g).to(DEV)
     x = torch.randn(rows, in_f, generator=g).to(DEV)
-    gw = pkg.linear_tf32x3(gy.t().contiguous(), x.t().contiguous(), None, split_weight_in_kernel=True)
+    gyt, xt = pkg.ops.transpose2d(gy), pkg.ops.transpose2d(x)
+    assert torch.equal(gyt, gy.t().contiguous()) and torch.equal(xt, x.t().contiguous())
+    gw = pkg.linear_tf32x3(gyt, xt, None, split_weight_in_kernel=True)
     ref = gy.double().t() @ x.double()
     err = (gw.double() - ref).abs().max().item()
     err32 = ((gy.t() @ x).double() - ref).abs().max().item()
     assert gw.shape == (out_f, in_f)
     assert err <= ERR_FACTOR * err32 + 1e-6, (err, err32)
+
+
+def test_transpose2d_ragged_shapes(pkg):
+    for rows, cols in ((1, 1), (33, 7), (100, 257), (1000, 96)):
+        x = torch.randn(rows, cols, device=DEV)
+        assert torch.equal(pkg.ops.transpose2d(x), x.t().contiguous())
+    with pytest.raises(RuntimeError, match="transpose2d needs"):
+        pkg.ops.transpose2d(torch.randn(4, 4, device=DEV).t())

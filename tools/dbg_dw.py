@@ -17,5 +17,7 @@ for out_f, in_f in ((256, 256), (192, 256), (96, 256), (1024, 256), (256, 1024))
     r = {"out": out_f, "in": in_f,
          "torch_dw_ms": t(lambda: gy.t() @ x),
          "transpose_gy_ms": t(lambda: gy.t().contiguous()), "transpose_x_ms": t(lambda: x.t().contiguous()),
+         "my_transpose_gy_ms": t(lambda: pkg.ops.transpose2d(gy)), "my_transpose_x_ms": t(lambda: pkg.ops.transpose2d(x)),
+         "transpose_ok": bool(torch.equal(pkg.ops.transpose2d(x), xt)),
          "kernel_dw_ms": t(lambda: pkg.linear_tf32x3(gyt, xt, None, split_weight_in_kernel=True))}
     print(json.dumps(r), flush=True)

@@ -34,6 +34,7 @@ cudaError_t launch_linear_tf32x3(const float *, const float *, const float *, fl
                                  float *, cudaStream_t, bool *handled);
 cudaError_t launch_add_layernorm(const float *, const float *, const float *, const float *, float *, long long,
                                  int, float, cudaStream_t, bool *handled);
+cudaError_t launch_transpose(const float *, float *, long long, int, cudaStream_t);
 cudaError_t launch_debug_indices(const int64_t *, const int64_t *, const float *, const Dims &,
                                  int32_t *, int64_t *, cudaStream_t);
 
@@ -249,6 +250,12 @@ int msda_b200_add_layernorm_f32(const float *x, const float *residual, const flo
     cudaError_t e = launch_add_layernorm(x, residual, gamma, beta, y, rows, cols, eps, (cudaStream_t)stream, &handled);
     if (e == cudaSuccess && !handled) return MSDA_ERR_UNSUPPORTED;
     return (int)e;
+}
+
+int msda_b200_transpose_f32(const float *x, float *y, long long rows, int cols, void *stream) {
+    if (!x || !y) return MSDA_ERR_NULL_POINTER;
+    if (rows <= 0 || cols <= 0 || (cols + 31) / 32 > 65535) return MSDA_ERR_BAD_SHAPE;
+    return (int)launch_transpose(x, y, rows, cols, (cudaStream_t)stream);
 }
 
 int msda_b200_debug_indices_f32(const int64_t *spatial_shapes, const int64_t *level_start,

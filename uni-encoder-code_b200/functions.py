@@ -60,13 +60,12 @@ class MSDeformAttnFusedFunction(Function):
 
 
 class LinearTF32x3Function(Function):
-    """``apply(x, weight, bias)`` = ``F.linear`` with the forward GEMM and the input-gradient GEMM
-    (``grad_x = grad_y @ weight``) on the tensor cores (ops.linear_tf32x3); the weight gradient
-    (``grad_y^T @ x``, reduction over the rows) and the bias gradient use torch's fp32 kernels.
-    (The kernel can do the weight gradient too -- split-K with the "weight" operand split in the
-    kernel, tests/test_linear_gpu.py -- but it needs both operands transposed, and the two transposes cost
-    more than the tensor cores save: 0.19 + 2 x 0.20 ms against 0.53 ms for torch at 172 032 x 256 x 256.)
-    Needs in_features and out_features divisible by 32."""
+    """``apply(x, weight, bias)`` = ``F.linear`` with all three GEMMs on the tensor cores
+    (ops.linear_tf32x3): forward, input gradient (``grad_y @ weight``) and weight gradient
+    (``grad_y^T @ x``: both operands transposed by ops.transpose2d, then a split-K GEMM over the rows with
+    the "weight" operand split inside the kernel; 0.34 ms against 0.53 ms for torch's fp32 GEMM at
+    172 032 x 256 x 256).  The bias gradient is a torch column sum.  Needs in_features and out_features
+    divisible by 32; a row count that is not a multiple of 32 sends the weight gradient to torch."""
 
     @staticmethod
     def supported(x, weight) -> bool:
@@ -89,7 +88,12 @@ class LinearTF32x3Function(Function):
             grad_x = ops.linear_tf32x3(grad_y, weight.t().contiguous(), None)
         g2 = grad_y.reshape(-1, grad_y.size(-1))
         if ctx.needs_input_grad[1]:
-            grad_w = g2.t() @ x.reshape(-1, x.size(-1))
+            x2 = x.reshape(-1, x.size(-1))
+            if g2.size(0) % 32 == 0:
+                grad_w = ops.linear_tf32x3(ops.transpose2d(g2), ops.transpose2d(x2), None,
+                                           split_weight_in_kernel=True)
+            else:
+                grad_w = g2.t() @ x2
         if ctx.has_bias and ctx.needs_input_grad[2]:
             grad_b = g2.sum(0)
         return grad_x, grad_w, grad_b

@@ -304,3 +304,15 @@ def add_layernorm(x, residual, weight, bias, eps=1e-5):
             torch.cuda.current_stream(x.device).cuda_stream)
     _lib.check(rc, "add_layernorm")
     return y
+
+
+def transpose2d(x):
+    """``x.t().contiguous()`` for a contiguous fp32 CUDA matrix (operand preparation for the weight-gradient GEMM)."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous() and x.numel() > 0):
+        raise RuntimeError("transpose2d needs a contiguous 2-d fp32 CUDA tensor")
+    y = torch.empty(x.size(1), x.size(0), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib.msda_b200_transpose_f32(x.data_ptr(), y.data_ptr(), x.size(0), x.size(1),
+                                              torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(rc, "transpose2d")
+    return y
