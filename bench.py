@@ -32,10 +32,10 @@ DEFAULT_WORKLOAD = "cityscapes_512x1024_b8"
 NOMINAL_HBM_GBS = 8000.0          # north_star's "~8 TB/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of
 # this command (profiles/r1_ncu_bench_summary.csv); only valid for the default workload / mode
-NCU_DRAM_TRAFFIC = {("cityscapes_512x1024_b8", "model"): {"forward": 247.4e6, "backward": 535.6e6}}
+NCU_DRAM_TRAFFIC = {("cityscapes_512x1024_b8", "model"): {"forward": 246.6e6, "backward": 527.4e6}}
 # What actually bounds the dominant (backward) kernel on chip, from the same capture and from
 # tools/microbench.cu (profiles/r1_microbench.txt): 120.5 M reduction sectors of 32 B per launch
-# against an L2-side reduction throughput of ~6.4 TB/s (occupancy-independent).
+# against a reduction-path throughput of ~6.4 TB/s chip-wide (independent of occupancy, instruction width and engine).
 NCU_RED_BYTES = {("cityscapes_512x1024_b8", "model"): 120499092 * 32}
 L2_REDUCTION_GBS = 6400.0
 FALLBACK_HBM_GBS = 6650.0         # /opt/skills/guides/B200_PROFILING.md fallback
