@@ -218,3 +218,36 @@ def test_transpose2d_ragged_shapes(pkg):
         assert torch.equal(pkg.ops.transpose2d(x), x.t().contiguous())
     with pytest.raises(RuntimeError, match="transpose2d needs"):
         pkg.ops.transpose2d(torch.randn(4, 4, device=DEV).t())
+
+
+def test_linear_full_size_is_exact_on_integer_inputs(pkg):
+    """BASELINE configs[2] row count (1024x2048 pyramid, batch 8 = 344 064 rows): thousands of tiles per
+    persistent CTA, every barrier phase flips many times.  Small-integer inputs make every product and sum
+    exactly representable, so the result must equal the fp64 one bit for bit, for every tile."""
+    g = torch.Generator().manual_seed(7)
+    rows = 344064
+    for out_f, in_f in ((256, 256), (96, 256), (256, 1024)):
+        x = torch.randint(-4, 5, (rows, in_f), generator=g).float().to(DEV)
+        w = torch.randint(-4, 5, (out_f, in_f), generator=g).float().to(DEV)
+        b = torch.randint(-9, 10, (out_f,), generator=g).float().to(DEV)
+        y = pkg.linear_tf32x3(x, w, b)
+        ref = (x.double() @ w.double().t() + b.double()).float()
+        assert torch.equal(y, ref), (out_f, in_f, (y - ref).abs().max().item())
+        del x, w, y, ref
+    # weight-gradient shape at the training row count: split-K, reductions into the zeroed output
+    rows = 172032
+    gy = torch.randint(-2, 3, (rows, 192), generator=g).float().to(DEV)
+    x = torch.randint(-2, 3, (rows, 256), generator=g).float().to(DEV)
+    gw = pkg.linear_tf32x3(pkg.ops.transpose2d(gy), pkg.ops.transpose2d(x), None, split_weight_in_kernel=True)
+    assert torch.equal(gw, (gy.double().t() @ x.double()).float())
+
+
+def test_add_layernorm_full_size(pkg):
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(344064, 256, generator=g).to(DEV)
+    r = torch.randn(344064, 256, generator=g).to(DEV)
+    w = torch.randn(256, generator=g).to(DEV)
+    b = torch.randn(256, generator=g).to(DEV)
+    y = pkg.add_layernorm(x, r, w, b, 1e-5)
+    ref = F.layer_norm(x + r, (256,), w, b, 1e-5)
+    assert (y - ref).abs().max().item() <= 5e-6
