@@ -190,9 +190,10 @@ int msda_b200_debug_indices_f32(const int64_t *spatial_shapes, const int64_t *le
  *   "whatif_drop_reds"  MEASUREMENT ONLY, breaks grad_value: k > 0 drops the grad_value reductions
  *                  of the first k point pairs of every query (k = 4: the two coarsest of 3 levels x 4
  *                  points) to time the best case of any pre-L2 aggregation scheme; 0 = off
- *   "linear_variant"  msda_b200_linear_f32: 0 = auto (128/96-column tiles; two {main, small} accumulator
- *                  sets for in_features < 512, four accumulators in one set from 512 on), 1 = 256-column
- *                  tiles with one {main, small} set, 2 = four accumulators in one set, 3 = two sets always
+ *   "linear_variant"  msda_b200_linear_f32: 0 = auto (128/96-column tiles; A operand in tensor memory
+ *                  for in_features < 512, four accumulators in one set with both operands in shared
+ *                  memory from 512 on), 2 = four accumulators in one set, 3 = two {main, small} sets
+ *                  with both operands in shared memory, 4 = A operand in tensor memory always
  *   "whatif_linear"  MEASUREMENT ONLY, breaks msda_b200_linear_f32: bit mask 1 no MMAs, 2 no split
  *                  work, 4 no output stores, 8 no W loads, 16 no X loads; 0 = off
  */

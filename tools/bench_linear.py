@@ -33,12 +33,15 @@ for shape in [(128, 256, 32), (128, 256, 256), (300, 256, 256), (1000, 192, 256)
 run(1000, 256, 256, relu=1)
 pkg.set_option("linear_variant", 2)
 run(1000, 256, 256); run(640, 256, 1024); run(777, 96, 256)
+pkg.set_option("linear_variant", 4)
+print("variant 4 (A in TMEM):")
+run(128, 256, 32); run(1000, 256, 256); run(640, 256, 1024); run(777, 96, 256); run(513, 1024, 256)
 pkg.set_option("linear_variant", 0)
 run(1000, 256, 256, bias=False)
 # timing at the pixel-decoder shape
 M = 344064
 import itertools
-for variant, (N, K) in itertools.product((0, 2, 3), ((256, 256), (192, 256), (96, 256), (1024, 256), (256, 1024))):
+for variant, (N, K) in itertools.product((0, 3), ((256, 256), (192, 256), (96, 256), (1024, 256), (256, 1024))):
     pkg.set_option("linear_variant", variant)
     x = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev) / K ** 0.5; b = torch.randn(N, device=dev)
     y = torch.empty(M, N, device=dev)

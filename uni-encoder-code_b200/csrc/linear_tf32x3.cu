@@ -101,7 +101,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 __device__ __forceinline__ uint32_t to_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 
 constexpr int kSplitWarps = 4;    // warps 2-5
-constexpr int kEpiWarps = 4;      // warps 6-9: one per TMEM lane quarter
+constexpr int kEpiWarps = 8;      // warps 6-13: two per TMEM lane quarter, alternating 32-column blocks
 constexpr int kThreads = 64 + 32 * (kSplitWarps + kEpiWarps);
 
 template <int BN, int STAGES, int NBUF, int NACC>
@@ -309,40 +309,261 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             const uint32_t acc = tmem_base + buf * Cfg::kSetCols + ((uint32_t)(q * 32) << 16);
             mbar_wait(acc_full(buf), (it / NBUF) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t v[32], u[32];
-                tmem_ld32(acc + (uint32_t)(c * 32), v);
-                tmem_ld32(acc + (uint32_t)(BN + c * 32), u);
-                if (NACC == 4) {
-                    // small + small' first (same magnitude), then main + main', then the two sums
-                    uint32_t p[32], r[32];
-                    tmem_ld32(acc + (uint32_t)(2 * BN + c * 32), p);
-                    tmem_ld32(acc + (uint32_t)(3 * BN + c * 32), r);
+            // this warp's 32-column blocks: c = part, part + kEpiWarps/4, ...  All of them are read from TMEM and
+            // their accumulators added up before anything else, so the set goes back to the MMA warp after a few
+            // hundred cycles; the transposes and stores then overlap with the MMAs of the next tile
+            constexpr int kStep = kEpiWarps / 4, kMaxBlk = (BN / 32 + kStep - 1) / kStep;
+            const int part = (warp - 2 - kSplitWarps) >> 2;
+            float sum[kMaxBlk][32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
-                        u[j] = __float_as_uint(__uint_as_float(p[j]) + __uint_as_float(r[j]));
+            for (int i = 0; i < kMaxBlk; ++i) {
+                const int c = part + i * kStep;
+                if (c < BN / 32) {
+                    uint32_t v[32], u[32];
+                    tmem_ld32(acc + (uint32_t)(c * 32), v);
+                    tmem_ld32(acc + (uint32_t)(BN + c * 32), u);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sum[i][j] = __uint_as_float(v[j]) + __uint_as_float(u[j]);
+                    if (NACC == 4) {                                      // (main + main') + (small + small')
+                        tmem_ld32(acc + (uint32_t)(2 * BN + c * 32), v);
+                        tmem_ld32(acc + (uint32_t)(3 * BN + c * 32), u);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) sum[i][j] += __uint_as_float(v[j]) + __uint_as_float(u[j]);
                     }
                 }
-                if (c == BN / 32 - 1) {                                   // everything is in registers: hand the set back
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    mbar_arrive(acc_empty(buf));
-                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(acc_empty(buf));
+#pragma unroll
+            for (int i = 0; i < kMaxBlk; ++i) {
+                const int c = part + i * kStep;
+                if (c >= BN / 32) continue;
                 const int col = n0 + c * 32;
                 const float b = (bias != nullptr && col + lane < N && kb0 == 0) ? bias[col + lane] : 0.f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(v[j]) + __uint_as_float(u[j]);
+                for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = sum[i][j];
+                __syncwarp();
+                if (k_chunks == 1) {               // (kept apart from the split-K loop: an asm with a memory clobber in
+#pragma unroll 8                                   //  the body stops the compiler from batching the shared loads)
+                    for (int r = 0; r < 32; ++r) {
+                        const int row = m0 + q * 32 + r;
+                        float o = tile[r * 33 + lane] + b;
+                        if (relu) o = fmaxf(o, 0.f);
+                        if (row < M && col + lane < N && !dbg_no_store) y[(long long)row * N + col + lane] = o;
+                    }
+                } else {
+#pragma unroll 8
+                    for (int r = 0; r < 32; ++r) {
+                        const int row = m0 + q * 32 + r;
+                        const float o = tile[r * 33 + lane] + b;
+                        if (row < M && col + lane < N)
+                            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(y + (long long)row * N + col + lane), "f"(o));
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// Kernel with the A operand in tensor memory (the default for in_features < 512; linear_variant 4 forces it).  With both operands in shared memory a
+// 128 x 128 x 8 tf32 MMA reads 8 KB for 64 cycles of math and the shared-memory data pipe is the limit
+// (profiles/r1_linear.md).  Here the split warps write x_hi (the raw words) and x_lo of their 32 rows into a
+// 4-slot ring in TMEM with tcgen05.st (lane = row, 32 columns = the 32 k of a k-block) and the MMAs take A
+// from there ([tmem] operand form): operand reads from shared memory are halved and x_lo is never stored
+// to shared memory.  TMEM: {main, small} accumulators (2 * BN columns, one set: the epilogue is not
+// overlapped with the next tile's MMAs) + 4 x 64 columns of A.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+          "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+          "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+
+template <int BN>
+struct LinCfgT {
+    static constexpr int kStages = 4;
+    static constexpr int kXBytes = kBM * kBK * 4, kWBytes = BN * kBK * 4;
+    static constexpr int kStageBytes = kXBytes + 2 * kWBytes;      // X (raw), W hi, W lo
+    static constexpr int kRingBytes = kStages * kStageBytes;
+    static constexpr int kEpiBytes = kEpiWarps * 32 * 33 * 4;
+    static constexpr int kSmem = kRingBytes + kEpiBytes + 1024 + 256;
+    static constexpr int kACol = 2 * BN;                           // first TMEM column of the A ring
+    static constexpr int kTmemCols = 512;
+    static_assert(2 * BN + kStages * 64 <= 512 && kStageBytes % 1024 == 0, "tile shape");
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+linear_tf32x3_atmem_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wh,
+                           const __grid_constant__ CUtensorMap map_wl, const float *__restrict__ bias,
+                           float *__restrict__ y, int M, int N, int K, int relu) {
+    using Cfg = LinCfgT<BN>;
+    constexpr int STAGES = Cfg::kStages;
+    extern __shared__ uint8_t smem_dyn[];
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    uint8_t *base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
+    const uint32_t bars = base + Cfg::kRingBytes + Cfg::kEpiBytes;
+    auto full = [&](int s) { return bars + 8u * s; };
+    auto ready = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+    const uint32_t acc_full = bars + 8u * 3 * STAGES, acc_empty = acc_full + 8u;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(base_ptr + Cfg::kRingBytes + Cfg::kEpiBytes + 8 * (3 * STAGES + 2));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kblocks = K / kBK;
+    const int k_rot = (int)(blockIdx.x % (unsigned)kblocks);
+    const int n_tiles = (N + BN - 1) / BN;
+    const long long tiles = (long long)((M + kBM - 1) / kBM) * n_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full(s), 1);
+            mbar_init(ready(s), 32 * kSplitWarps);
+            mbar_init(empty(s), 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 32 * kEpiWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"(Cfg::kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+                const int m0 = (int)(t / n_tiles) * kBM, n0 = (int)(t % n_tiles) * BN;
+                for (int kb = 0; kb < kblocks; ++kb, ++g) {
+                    const int kk = (kb + k_rot) % kblocks;
+                    const int s = g % STAGES;
+                    mbar_wait(empty(s), ((g / STAGES) & 1) ^ 1);
+                    const uint32_t st = base + s * Cfg::kStageBytes;
+                    mbar_arrive_expect_tx(full(s), Cfg::kStageBytes);
+                    tma_load_2d(st, &map_x, full(s), kk * kBK, m0);
+                    tma_load_2d(st + Cfg::kXBytes, &map_wh, full(s), kk * kBK, n0);
+                    tma_load_2d(st + Cfg::kXBytes + Cfg::kWBytes, &map_wl, full(s), kk * kBK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(kBM, BN), idesc2 = umma_idesc(kBM, 2 * BN);
+            uint32_t g = 0, it = 0;
+            for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+                mbar_wait(acc_empty, (it & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int kb = 0; kb < kblocks; ++kb, ++g) {
+                    const int s = g % STAGES;
+                    mbar_wait(ready(s), (g / STAGES) & 1);                 // A slot written (implies the W tiles landed)
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t wh = base + s * Cfg::kStageBytes + Cfg::kXBytes;
+                    const uint32_t a_hi = tmem_base + Cfg::kACol + s * 64, a_lo = a_hi + 32;
+#pragma unroll
+                    for (int k = 0; k < kBK / kUmmaK; ++k) {
+                        const uint32_t ko = k * kUmmaK * 4;
+                        // x_hi * [W_hi; W_lo]^T -> {main, small};  x_lo * W_hi^T -> small
+                        umma_tf32_ts(tmem_base, a_hi + k * kUmmaK, umma_desc(wh + ko), idesc2, (kb | k) != 0);
+                        umma_tf32_ts(tmem_base + BN, a_lo + k * kUmmaK, umma_desc(wh + ko), idesc, 1);
+                    }
+                    umma_commit(empty(s));                                // smem stage AND TMEM A slot reusable
+                }
+                umma_commit(acc_full);
+            }
+        }
+    } else if (warp < 2 + kSplitWarps) {
+        // ---- A warps: rows 32*(warp%4) .. +31 of the X tile -> TMEM (x_hi = raw words, x_lo) ----
+        const int q = warp & 3, row = q * 32 + lane;
+        uint32_t g = 0;
+        for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+            for (int kb = 0; kb < kblocks; ++kb, ++g) {
+                const int s = g % STAGES;
+                mbar_wait(full(s), (g / STAGES) & 1);
+                const uint8_t *xrow = base_ptr + s * Cfg::kStageBytes + row * 128;
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {                              // 128-byte swizzle: chunk j sits at j ^ (row % 8)
+                    const uint4 v = *reinterpret_cast<const uint4 *>(xrow + ((j ^ (row & 7)) << 4));
+                    hi[4 * j + 0] = v.x; hi[4 * j + 1] = v.y; hi[4 * j + 2] = v.z; hi[4 * j + 3] = v.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    lo[j] = to_tf32(__uint_as_float(hi[j]) - __uint_as_float(hi[j] & 0xffffe000u));
+                const uint32_t a_hi = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::kACol + s * 64;
+                tmem_st32(a_hi, hi);
+                tmem_st32(a_hi + 32, lo);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(ready(s));
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        float *tile = reinterpret_cast<float *>(base_ptr + Cfg::kRingBytes) + (warp - 2 - kSplitWarps) * 32 * 33;
+        uint32_t it = 0;
+        for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+            const int m0 = (int)(t / n_tiles) * kBM, n0 = (int)(t % n_tiles) * BN;
+            const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16);
+            mbar_wait(acc_full, it & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // this warp's 32-column blocks: c = part, part + kEpiWarps/4, ...  All of them are read from TMEM
+            // (and main + small added) before anything else, so the accumulators go back to the MMA warp after
+            // a few hundred cycles; the transposes and stores then overlap with the next tile's MMAs
+            constexpr int kStep = kEpiWarps / 4, kMaxBlk = (BN / 32 + kStep - 1) / kStep;
+            const int part = (warp - 2 - kSplitWarps) >> 2;
+            float sum[kMaxBlk][32];
+#pragma unroll
+            for (int i = 0; i < kMaxBlk; ++i) {
+                const int c = part + i * kStep;
+                if (c < BN / 32) {
+                    uint32_t v[32], u[32];
+                    tmem_ld32(acc + (uint32_t)(c * 32), v);
+                    tmem_ld32(acc + (uint32_t)(BN + c * 32), u);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sum[i][j] = __uint_as_float(v[j]) + __uint_as_float(u[j]);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(acc_empty);
+#pragma unroll
+            for (int i = 0; i < kMaxBlk; ++i) {
+                const int c = part + i * kStep;
+                if (c >= BN / 32) continue;
+                const int col = n0 + c * 32;
+                const float b = (bias != nullptr && col + lane < N) ? bias[col + lane] : 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = sum[i][j];
                 __syncwarp();
 #pragma unroll 8
                 for (int r = 0; r < 32; ++r) {
-                    const int row = m0 + q * 32 + r;
+                    const int rr = m0 + q * 32 + r;
                     float o = tile[r * 33 + lane] + b;
                     if (relu) o = fmaxf(o, 0.f);
-                    if (row < M && col + lane < N && !dbg_no_store) {
-                        if (k_chunks > 1) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(y + (long long)row * N + col + lane), "f"(o) : "memory");
-                        else y[(long long)row * N + col + lane] = o;
-                    }
+                    if (rr < M && col + lane < N) y[(long long)rr * N + col + lane] = o;
                 }
                 __syncwarp();
             }
@@ -448,6 +669,34 @@ cudaError_t launch_linear(const float *x, const float *w, const float *bias, flo
     return cudaGetLastError();
 }
 
+template <int BN>
+cudaError_t launch_linear_atmem(const float *x, const float *w, const float *bias, float *y, int M, int N, int K,
+                                int relu, float *workspace, cudaStream_t stream) {
+    using Cfg = LinCfgT<BN>;
+    auto kern = linear_tf32x3_atmem_kernel<BN>;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (!attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+        if (e != cudaSuccess) return e;
+        attr_set[dev] = true;
+    }
+    float *whi = workspace, *wlo = workspace + (size_t)N * K;
+    CUtensorMap mx, mwh, mwl;
+    if (!make_map(&mx, x, M, K, kBM) || !make_map(&mwh, whi, N, K, BN) || !make_map(&mwl, wlo, N, K, BN))
+        return cudaErrorInvalidValue;
+    const long long n4 = (long long)N * K / 4;
+    split_weight_kernel<<<(unsigned)((n4 + 255) / 256 < 592 ? (n4 + 255) / 256 : 592), 256, 0, stream>>>(
+        reinterpret_cast<const float4 *>(w), reinterpret_cast<float4 *>(whi), reinterpret_cast<float4 *>(wlo), n4);
+    note_launch();
+    const long long tiles = (long long)((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
+    const long long grid = tiles < sm_count() ? tiles : sm_count();
+    kern<<<(unsigned)grid, kThreads, Cfg::kSmem, stream>>>(mx, mwh, mwl, bias, y, M, N, K, relu);
+    note_launch();
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 // y[M, N] = x[M, K] * w[N, K]^T + bias[N]; K % 32 == 0, 16-byte aligned rows; workspace: 2*N*K floats
@@ -463,13 +712,17 @@ cudaError_t launch_linear_tf32x3(const float *x, const float *w, const float *bi
     // tile width: 128 columns, or 96 when that wastes fewer (N = 96, 192, 288 ...)
     const int waste128 = (N + 127) / 128 * 128 - N, waste96 = (N + 95) / 96 * 96 - N;
     const bool narrow = waste96 < waste128;
-    const int variant = option_value(OPT_LINEAR_VARIANT);   // experiments: 1 = 256-wide tiles, one accumulator set
+    const int variant = option_value(OPT_LINEAR_VARIANT);
     if (workspace == nullptr) {
         // one-shot weight: split inside the kernel; long reductions (the use case) -> four accumulators
         if (narrow) return launch_linear<96, 3, 1, 4, true>(x, w, bias, y, M, N, K, relu, workspace, stream);
         return launch_linear<128, 3, 1, 4, true>(x, w, bias, y, M, N, K, relu, workspace, stream);
     }
-    if (variant == 1 && N % 256 == 0) return launch_linear<256, 2, 1, 2, false>(x, w, bias, y, M, N, K, relu, workspace, stream);
+    // default for in_features < 512: A operand in tensor memory (fastest; {main, small} accumulators)
+    if (variant == 4 || (variant == 0 && K < 512)) {
+        if (narrow) return launch_linear_atmem<96>(x, w, bias, y, M, N, K, relu, workspace, stream);
+        return launch_linear_atmem<128>(x, w, bias, y, M, N, K, relu, workspace, stream);
+    }
     // long reductions: the truncating accumulation makes the error grow with the number of MMAs per
     // accumulator, so from in_features = 512 on the products are spread over four accumulators (one set:
     // the epilogue is not overlapped, ~15 % slower) -- error at the level of an fp32 SIMT GEMM again
