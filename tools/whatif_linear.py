@@ -1,11 +1,13 @@
 #!/usr/bin/env python
-"""Timing experiments on the 3xTF32 GEMM (results WRONG on purpose for the knob runs)."""
+"""Timing experiments on the 3xTF32 GEMM with both operands in shared memory (linear_variant 3 / the
+four-accumulator kernel for in = 1024); results WRONG on purpose for the knob runs."""
 import os, sys, json
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from __graft_entry__ import load_package
 pkg = load_package(); lib = pkg._lib.lib; dev = "cuda:0"
+pkg.set_option("linear_variant", 3)
 M = 344064
 for N, K in ((256, 256), (256, 1024)):
     x = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev) / K ** 0.5; b = torch.randn(N, device=dev)
@@ -27,3 +29,4 @@ for N, K in ((256, 256), (256, 1024)):
                           "kcycles_per_tile": round(ms * 1e-3 * 1.92e9 / tiles_per_sm / 1e3, 2),
                           "cycles_per_kblock": round(ms * 1e-3 * 1.92e9 / tiles_per_sm / (K / 32))}), flush=True)
 pkg.set_option("whatif_linear", 0)
+pkg.set_option("linear_variant", 0)
