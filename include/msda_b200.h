@@ -158,6 +158,17 @@ int msda_b200_add_layernorm_f32(const float *x, const float *residual, const flo
                                 const float *beta, float *y, long long rows, int cols, float eps,
                                 void *stream);
 
+/*
+ * Weight and bias gradient of the same Linear (torch autograd semantics), 3 x TF32 on the tensor cores
+ * without transposing the operands in memory:
+ *     grad_weight[out_features, in_features] = grad_y[rows, out_features]^T * x[rows, in_features]
+ *     grad_bias[out_features] = column sums of grad_y                      (grad_bias may be NULL)
+ * Both outputs are overwritten (zero-filled, then accumulated with reductions: the row range is split over
+ * the SMs).  out_features % 4 == 0, in_features % 4 == 0, 16-byte aligned operands; else MSDA_ERR_UNSUPPORTED.
+ */
+int msda_b200_linear_wgrad_f32(const float *grad_y, const float *x, float *grad_weight, float *grad_bias,
+                               long long rows, int out_features, int in_features, void *stream);
+
 /* y[cols, rows] = x[rows, cols]^T, fp32 (operand preparation for weight-gradient GEMMs). */
 int msda_b200_transpose_f32(const float *x, float *y, long long rows, int cols, void *stream);
 

@@ -144,8 +144,8 @@ def test_encoder_layer_with_tensor_core_linears_matches_torch_linears(pkg):
         yc = b(srcs_b, pos)[0]
         (yc * cot).sum().backward()
         # per layer: MSDA fwd + bwd, 6 x (split + GEMM) forward, 6 x (split + GEMM) for grad_x,
-        # 6 x (2 transposes + GEMM) for grad_w
-        assert pkg.launch_count() - n3 == 2 * (2 + 12 + 12 + 18)
+        # 6 weight / bias gradient kernels
+        assert pkg.launch_count() - n3 == 2 * (2 + 12 + 12 + 6)
         assert (yc - ya).abs().max().item() <= 5e-5
         # gradients pass through floor() of the sampling locations: a 1e-6 difference in a location next to
         # a cell edge moves the point into the neighbouring cell, where the location gradient differs by
@@ -240,6 +240,8 @@ def test_linear_full_size_is_exact_on_integer_inputs(pkg):
     x = torch.randint(-2, 3, (rows, 256), generator=g).float().to(DEV)
     gw = pkg.linear_tf32x3(pkg.ops.transpose2d(gy), pkg.ops.transpose2d(x), None, split_weight_in_kernel=True)
     assert torch.equal(gw, (gy.double().t() @ x.double()).float())
+    gw2, gb2 = pkg.ops.linear_wgrad(gy, x)
+    assert torch.equal(gw2, gw) and torch.equal(gb2, gy.double().sum(0).float())
 
 
 def test_add_layernorm_full_size(pkg):
@@ -251,3 +253,29 @@ def test_add_layernorm_full_size(pkg):
     y = pkg.add_layernorm(x, r, w, b, 1e-5)
     ref = F.layer_norm(x + r, (256,), w, b, 1e-5)
     assert (y - ref).abs().max().item() <= 5e-6
+
+
+@pytest.mark.parametrize("rows,out_f,in_f", [(4096, 256, 256), (8200, 96, 256), (2085, 1024, 256), (6400, 256, 1024),
+                                            (33, 128, 64), (1000, 100, 36), (5, 4, 4)])
+def test_linear_wgrad_kernel(pkg, rows, out_f, in_f):
+    """grad_W = grad_y^T @ x and grad_b = column sums, reduction over the rows, operands not transposed in
+    memory (A through tensor memory, B re-laid out in shared memory), against fp64 and torch's fp32 kernels."""
+    g = torch.Generator().manual_seed(rows + in_f)
+    gy = torch.randn(rows, out_f, generator=g).to(DEV)
+    x = torch.randn(rows, in_f, generator=g).to(DEV)
+    gw, gb = pkg.ops.linear_wgrad(gy, x)
+    ref = gy.double().t() @ x.double()
+    err, err32 = (gw.double() - ref).abs().max().item(), ((gy.t() @ x).double() - ref).abs().max().item()
+    assert gw.shape == (out_f, in_f) and err <= ERR_FACTOR * err32 + 2e-6 * ref.abs().max().item(), (err, err32)
+    refb = gy.double().sum(0)
+    assert (gb.double() - refb).abs().max().item() <= 4 * (gy.sum(0).double() - refb).abs().max().item() + 1e-4
+    gw2, none = pkg.ops.linear_wgrad(gy, x, with_bias=False)
+    assert none is None and (gw2 - gw).abs().max().item() <= 2e-3 * max(1.0, gw.abs().max().item())
+    # exact on small integers, at every tile / chunk boundary
+    gyi = torch.randint(-2, 3, (rows, out_f), generator=g).float().to(DEV)
+    xi = torch.randint(-2, 3, (rows, in_f), generator=g).float().to(DEV)
+    gwi, gbi = pkg.ops.linear_wgrad(gyi, xi)
+    assert torch.equal(gwi, (gyi.double().t() @ xi.double()).float())
+    assert torch.equal(gbi, gyi.double().sum(0).float())
+    with pytest.raises(RuntimeError, match="linear_wgrad needs"):
+        pkg.ops.linear_wgrad(gy[:, :out_f - 1].contiguous(), x)

@@ -34,6 +34,8 @@ cudaError_t launch_linear_tf32x3(const float *, const float *, const float *, fl
                                  float *, cudaStream_t, bool *handled);
 cudaError_t launch_add_layernorm(const float *, const float *, const float *, const float *, float *, long long,
                                  int, float, cudaStream_t, bool *handled);
+cudaError_t launch_linear_wgrad(const float *, const float *, float *, float *, long long, int, int, cudaStream_t,
+                                bool *handled);
 cudaError_t launch_transpose(const float *, float *, long long, int, cudaStream_t);
 cudaError_t launch_debug_indices(const int64_t *, const int64_t *, const float *, const Dims &,
                                  int32_t *, int64_t *, cudaStream_t);
@@ -101,7 +103,7 @@ long long msda_b200_launch_count(void) { return g_launches.load(std::memory_orde
 
 int msda_b200_set_option(const char *name, int value) {
     const int i = option_index(name);
-    if (i < 0 || value < 0 || value > 64) return MSDA_ERR_BAD_OPTION;
+    if (i < 0 || value < 0 || value > 4096) return MSDA_ERR_BAD_OPTION;
     g_options[i].store(value, std::memory_order_relaxed);
     return MSDA_OK;
 }
@@ -248,6 +250,17 @@ int msda_b200_add_layernorm_f32(const float *x, const float *residual, const flo
     if (rows <= 0 || cols <= 0) return MSDA_ERR_BAD_SHAPE;
     bool handled = false;
     cudaError_t e = launch_add_layernorm(x, residual, gamma, beta, y, rows, cols, eps, (cudaStream_t)stream, &handled);
+    if (e == cudaSuccess && !handled) return MSDA_ERR_UNSUPPORTED;
+    return (int)e;
+}
+
+int msda_b200_linear_wgrad_f32(const float *grad_y, const float *x, float *grad_weight, float *grad_bias,
+                               long long rows, int out_features, int in_features, void *stream) {
+    if (!grad_y || !x || !grad_weight) return MSDA_ERR_NULL_POINTER;
+    if (rows <= 0 || out_features <= 0 || in_features <= 0) return MSDA_ERR_BAD_SHAPE;
+    bool handled = false;
+    cudaError_t e = launch_linear_wgrad(grad_y, x, grad_weight, grad_bias, rows, out_features, in_features,
+                                        (cudaStream_t)stream, &handled);
     if (e == cudaSuccess && !handled) return MSDA_ERR_UNSUPPORTED;
     return (int)e;
 }

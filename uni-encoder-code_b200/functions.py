@@ -60,12 +60,11 @@ class MSDeformAttnFusedFunction(Function):
 
 
 class LinearTF32x3Function(Function):
-    """``apply(x, weight, bias)`` = ``F.linear`` with all three GEMMs on the tensor cores
-    (ops.linear_tf32x3): forward, input gradient (``grad_y @ weight``) and weight gradient
-    (``grad_y^T @ x``: both operands transposed by ops.transpose2d, then a split-K GEMM over the rows with
-    the "weight" operand split inside the kernel; 0.34 ms against 0.53 ms for torch's fp32 GEMM at
-    172 032 x 256 x 256).  The bias gradient is a torch column sum.  Needs in_features and out_features
-    divisible by 32; a row count that is not a multiple of 32 sends the weight gradient to torch."""
+    """``apply(x, weight, bias)`` = ``F.linear`` with all three GEMMs on the tensor cores: forward and
+    input gradient (``grad_y @ weight``) through ops.linear_tf32x3, weight and bias gradient
+    (``grad_y^T @ x``, column sums of ``grad_y``) through ops.linear_wgrad, which reduces over the rows
+    without transposing the operands in memory (0.15 ms against 0.53 + 0.12 ms for torch's fp32 GEMM and
+    column sum at 172 032 x 256 x 256).  Needs in_features and out_features divisible by 32."""
 
     @staticmethod
     def supported(x, weight) -> bool:
@@ -87,13 +86,13 @@ class LinearTF32x3Function(Function):
         if ctx.needs_input_grad[0]:
             grad_x = ops.linear_tf32x3(grad_y, weight.t().contiguous(), None)
         g2 = grad_y.reshape(-1, grad_y.size(-1))
+        want_b = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
             x2 = x.reshape(-1, x.size(-1))
-            if g2.size(0) % 32 == 0:
-                grad_w = ops.linear_tf32x3(ops.transpose2d(g2), ops.transpose2d(x2), None,
-                                           split_weight_in_kernel=True)
+            if ops.linear_wgrad_supported(g2, x2):
+                grad_w, grad_b = ops.linear_wgrad(g2, x2, with_bias=want_b)
             else:
                 grad_w = g2.t() @ x2
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+        if want_b and grad_b is None:
             grad_b = g2.sum(0)
         return grad_x, grad_w, grad_b

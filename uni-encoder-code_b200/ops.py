@@ -316,3 +316,29 @@ def transpose2d(x):
                                               torch.cuda.current_stream(x.device).cuda_stream)
     _lib.check(rc, "transpose2d")
     return y
+
+
+def linear_wgrad_supported(grad_y, x) -> bool:
+    return (isinstance(grad_y, torch.Tensor) and grad_y.is_cuda and grad_y.dtype == torch.float32 and x.dtype == torch.float32
+            and grad_y.dim() == 2 and x.dim() == 2 and grad_y.size(0) == x.size(0) and grad_y.numel() > 0 and x.numel() > 0
+            and grad_y.is_contiguous() and x.is_contiguous() and grad_y.size(1) % 4 == 0 and x.size(1) % 4 == 0
+            and x.device == grad_y.device)
+
+
+def linear_wgrad(grad_y, x, with_bias=True):
+    """(grad_weight [out, in], grad_bias [out] or None) of ``F.linear`` from ``grad_y`` [rows, out] and ``x``
+    [rows, in] (contiguous fp32 CUDA): grad_y^T @ x and the column sums of grad_y in one kernel."""
+    if not grad_y.is_cuda:
+        raise RuntimeError("Not implemented on the CPU")
+    if not linear_wgrad_supported(grad_y, x):
+        raise RuntimeError("linear_wgrad needs contiguous fp32 CUDA matrices grad_y [rows, out], x [rows, in] with "
+                           "out % 4 == 0 and in % 4 == 0")
+    gw = torch.empty(grad_y.size(1), x.size(1), dtype=torch.float32, device=x.device)
+    gb = torch.empty(grad_y.size(1), dtype=torch.float32, device=x.device) if with_bias else None
+    with torch.cuda.device(x.device):
+        rc = _lib.lib.msda_b200_linear_wgrad_f32(grad_y.data_ptr(), x.data_ptr(), gw.data_ptr(),
+                                                 gb.data_ptr() if gb is not None else None, grad_y.size(0),
+                                                 grad_y.size(1), x.size(1),
+                                                 torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(rc, "linear_wgrad")
+    return gw, gb
