@@ -14,4 +14,5 @@ for n in 1 2 4 8; do
 done
 rm -f gpurun_out/configs_n$NG.jsonl
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29700 tools/bench_configs.py --configs 2,3,5,q --out gpurun_out/configs_n$NG.jsonl > gpurun_out/configs_n$NG.log 2>&1; echo "configs exit $?"
-tail -4 gpurun_out/configs_n$NG.log | cut -c1-400
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29701 tools/bench_configs.py --configs 3,5,q --linear tf32x3 --fused --out gpurun_out/configs_n$NG.jsonl >> gpurun_out/configs_n$NG.log 2>&1; echo "configs (tf32x3, fused) exit $?"
+cut -c1-300 gpurun_out/configs_n$NG.jsonl
