@@ -74,3 +74,29 @@ def test_mirror_plus_cuda_op_matches_reference_pixel_decoder_golden(pkg, fused, 
     # conv_dim 64 is not a width the fused residual + LayerNorm kernel covers, so torch runs those)
     assert pkg.launch_count() - n0 == (2 if linear == "torch" else 2 + 2 * 6 * 2)
     check(outs, g, 5e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fused,linear", [(False, "torch"), (True, "tf32x3")])
+def test_forward_features_is_cuda_graph_capturable(pkg, fused, linear):
+    """No host read of device data and no host-to-device copy is left in the mirror's forward (position
+    embeddings, reference points and the level tensors are cached per shape), so the whole call records
+    into one CUDA graph; the replay reproduces the eager result bit for bit."""
+    m, feats, g = build(pkg, device="cuda:0", fused=fused, linear=linear)
+    with torch.no_grad():
+        eager = m.forward_features(feats)            # also fills the per-shape caches
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            m.forward_features(feats)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = m.forward_features(feats)
+        for k in feats:
+            feats[k].add_(0.0)                       # inputs stay where they are; replay reads them again
+        graph.replay()
+        torch.cuda.synchronize()
+    assert torch.equal(out[0], eager[0]) and torch.equal(out[1], eager[1])
+    for a, b in zip(out[2], eager[2]):
+        assert torch.equal(a, b)

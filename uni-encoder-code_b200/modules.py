@@ -216,6 +216,22 @@ def reference_points_for(levels: Sequence[Tuple[int, int]], device, dtype=torch.
     return hit
 
 
+_LEVEL_CACHE = {}
+
+
+def level_tensors_for(levels: Sequence[Tuple[int, int]], device):
+    """(spatial_shapes [L, 2], level_start_index [L]) int64 device tensors for a pyramid (msdeformattn.py:82-85),
+    built once per (levels, device): they depend only on the shapes, and a host-to-device copy per
+    forward would keep the call from being captured in a CUDA graph."""
+    key = (tuple((int(h), int(w)) for h, w in levels), str(device))
+    hit = _LEVEL_CACHE.get(key)
+    if hit is None:
+        shapes = torch.tensor(key[0], dtype=torch.long)
+        lsi = torch.cat((shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]))
+        hit = _LEVEL_CACHE[key] = (shapes.to(device), lsi.to(device))
+    return hit
+
+
 class MSDeformAttnTransformerEncoder(nn.Module):
     """msdeformattn.py:145-176."""
 
@@ -277,8 +293,7 @@ class MSDeformAttnTransformerEncoderOnly(nn.Module):
         src = torch.cat([s.flatten(2).transpose(1, 2) for s in srcs], 1)
         pos = torch.cat([p.flatten(2).transpose(1, 2) + self.level_embed[i].view(1, 1, -1)
                          for i, p in enumerate(pos_embeds)], 1)
-        shapes = torch.as_tensor(levels, dtype=torch.long, device=src.device)
-        lsi = torch.cat((shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]))
+        shapes, lsi = level_tensors_for(levels, src.device)
         return src, pos, shapes, lsi, levels
 
     def forward(self, srcs, pos_embeds):
