@@ -159,6 +159,15 @@ int msda_b200_add_layernorm_f32(const float *x, const float *residual, const flo
                                 void *stream);
 
 /*
+ * Backward of the above: grad_v[rows, cols] (= gradient of both x and residual), grad_gamma[cols], grad_beta[cols]
+ * from grad_y, x, residual (may be NULL) and gamma; mean / rstd are recomputed.  grad_gamma / grad_beta are
+ * overwritten.  cols in {128, 256}; MSDA_ERR_UNSUPPORTED otherwise.
+ */
+int msda_b200_add_layernorm_backward_f32(const float *grad_y, const float *x, const float *residual,
+                                         const float *gamma, float *grad_v, float *grad_gamma,
+                                         float *grad_beta, long long rows, int cols, float eps, void *stream);
+
+/*
  * Weight and bias gradient of the same Linear (torch autograd semantics), 3 x TF32 on the tensor cores
  * without transposing the operands in memory:
  *     grad_weight[out_features, in_features] = grad_y[rows, out_features]^T * x[rows, in_features]

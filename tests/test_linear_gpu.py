@@ -144,8 +144,8 @@ def test_encoder_layer_with_tensor_core_linears_matches_torch_linears(pkg):
         yc = b(srcs_b, pos)[0]
         (yc * cot).sum().backward()
         # per layer: MSDA fwd + bwd, 6 x (split + GEMM) forward, 6 x (split + GEMM) for grad_x,
-        # 6 weight / bias gradient kernels
-        assert pkg.launch_count() - n3 == 2 * (2 + 12 + 12 + 6)
+        # 6 weight / bias gradient kernels, 2 x (add + LayerNorm forward, backward)
+        assert pkg.launch_count() - n3 == 2 * (2 + 12 + 12 + 6 + 4)
         assert (yc - ya).abs().max().item() <= 5e-5
         # gradients pass through floor() of the sampling locations: a 1e-6 difference in a location next to
         # a cell edge moves the point into the neighbouring cell, where the location gradient differs by
@@ -279,3 +279,24 @@ def test_linear_wgrad_kernel(pkg, rows, out_f, in_f):
     assert torch.equal(gbi, gyi.double().sum(0).float())
     with pytest.raises(RuntimeError, match="linear_wgrad needs"):
         pkg.ops.linear_wgrad(gy[:, :out_f - 1].contiguous(), x)
+
+
+@pytest.mark.parametrize("rows,cols", [(1000, 256), (77, 128), (20000, 256)])
+def test_add_layernorm_autograd_function(pkg, rows, cols):
+    g = torch.Generator().manual_seed(rows)
+    x = (torch.randn(rows, cols, generator=g) * 2 + 0.5).to(DEV)
+    r = torch.randn(rows, cols, generator=g).to(DEV)
+    w = (torch.randn(cols, generator=g) + 1).to(DEV)
+    b = torch.randn(cols, generator=g).to(DEV)
+    cot = torch.randn(rows, cols, generator=g).to(DEV)
+    leaves = [t.clone().requires_grad_(True) for t in (x, r, w, b)]
+    (pkg.AddLayerNormFunction.apply(*leaves, 1e-5) * cot).sum().backward()
+    ref = [t.clone().double().requires_grad_(True) for t in (x, r, w, b)]
+    (F.layer_norm(ref[0] + ref[1], (cols,), ref[2], ref[3], 1e-5) * cot.double()).sum().backward()
+    t32 = [t.clone().requires_grad_(True) for t in (x, r, w, b)]
+    (F.layer_norm(t32[0] + t32[1], (cols,), t32[2], t32[3], 1e-5) * cot).sum().backward()
+    for mine, r64, r32 in zip(leaves, ref, t32):
+        err = (mine.grad.double() - r64.grad).abs().max().item()
+        err32 = (r32.grad.double() - r64.grad).abs().max().item()
+        assert err <= 3 * err32 + 1e-6 * max(1.0, r64.grad.abs().max().item()), (err, err32)
+    assert torch.equal(leaves[0].grad, leaves[1].grad)

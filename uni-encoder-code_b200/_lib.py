@@ -31,6 +31,7 @@ SYMBOLS = {
     "msda_b200_fused_backward_f32": (_I, [_P] * 5 + [ctypes.c_longlong, _P, _P] + _DIMS + [_P, _P, _P, _P]),
     "msda_b200_linear_f32": (_I, [_P] * 4 + [_I] * 4 + [_P, _P]),
     "msda_b200_add_layernorm_f32": (_I, [_P] * 5 + [ctypes.c_longlong, _I, ctypes.c_float, _P]),
+    "msda_b200_add_layernorm_backward_f32": (_I, [_P] * 7 + [ctypes.c_longlong, _I, ctypes.c_float, _P]),
     "msda_b200_linear_wgrad_f32": (_I, [_P] * 4 + [ctypes.c_longlong, _I, _I, _P]),
     "msda_b200_transpose_f32": (_I, [_P, _P, ctypes.c_longlong, _I, _P]),
     "msda_b200_set_option": (_I, [ctypes.c_char_p, _I]),

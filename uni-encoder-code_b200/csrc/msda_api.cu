@@ -34,6 +34,8 @@ cudaError_t launch_linear_tf32x3(const float *, const float *, const float *, fl
                                  float *, cudaStream_t, bool *handled);
 cudaError_t launch_add_layernorm(const float *, const float *, const float *, const float *, float *, long long,
                                  int, float, cudaStream_t, bool *handled);
+cudaError_t launch_add_layernorm_bwd(const float *, const float *, const float *, const float *, float *, float *,
+                                     float *, long long, int, float, cudaStream_t, bool *handled);
 cudaError_t launch_linear_wgrad(const float *, const float *, float *, float *, long long, int, int, cudaStream_t,
                                 bool *handled);
 cudaError_t launch_transpose(const float *, float *, long long, int, cudaStream_t);
@@ -250,6 +252,18 @@ int msda_b200_add_layernorm_f32(const float *x, const float *residual, const flo
     if (rows <= 0 || cols <= 0) return MSDA_ERR_BAD_SHAPE;
     bool handled = false;
     cudaError_t e = launch_add_layernorm(x, residual, gamma, beta, y, rows, cols, eps, (cudaStream_t)stream, &handled);
+    if (e == cudaSuccess && !handled) return MSDA_ERR_UNSUPPORTED;
+    return (int)e;
+}
+
+int msda_b200_add_layernorm_backward_f32(const float *grad_y, const float *x, const float *residual,
+                                         const float *gamma, float *grad_v, float *grad_gamma, float *grad_beta,
+                                         long long rows, int cols, float eps, void *stream) {
+    if (!grad_y || !x || !gamma || !grad_v || !grad_gamma || !grad_beta) return MSDA_ERR_NULL_POINTER;
+    if (rows <= 0 || cols <= 0) return MSDA_ERR_BAD_SHAPE;
+    bool handled = false;
+    cudaError_t e = launch_add_layernorm_bwd(grad_y, x, residual, gamma, grad_v, grad_gamma, grad_beta, rows, cols,
+                                             eps, (cudaStream_t)stream, &handled);
     if (e == cudaSuccess && !handled) return MSDA_ERR_UNSUPPORTED;
     return (int)e;
 }

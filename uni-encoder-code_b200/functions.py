@@ -96,3 +96,25 @@ class LinearTF32x3Function(Function):
         if want_b and grad_b is None:
             grad_b = g2.sum(0)
         return grad_x, grad_w, grad_b
+
+
+class AddLayerNormFunction(Function):
+    """``apply(x, residual, weight, bias, eps)`` = ``F.layer_norm(x + residual, (C,), weight, bias, eps)`` with one
+    fused kernel each way (ops.add_layernorm / add_layernorm_backward); C in {128, 256}."""
+
+    @staticmethod
+    def supported(x, residual, weight) -> bool:
+        return ops.add_layernorm_supported(x, residual, weight) and x.size(-1) in (128, 256) and residual is not None
+
+    @staticmethod
+    def forward(ctx, x, residual, weight, bias, eps):
+        ctx.save_for_backward(x, residual, weight)
+        ctx.eps = eps
+        return ops.add_layernorm(x, residual, weight, bias, eps)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_y):
+        x, residual, weight = ctx.saved_tensors
+        gv, gg, gb = ops.add_layernorm_backward(grad_y.contiguous(), x, residual, weight, ctx.eps)
+        return gv, gv, gg, gb, None

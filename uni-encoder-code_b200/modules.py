@@ -29,7 +29,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
-from .functions import LinearTF32x3Function, MSDeformAttnFunction, MSDeformAttnFusedFunction
+from .functions import AddLayerNormFunction, LinearTF32x3Function, MSDeformAttnFunction, MSDeformAttnFusedFunction
 
 CoreFn = Callable[..., torch.Tensor]
 
@@ -57,6 +57,9 @@ def _add_norm(norm: nn.LayerNorm, x, sublayer_out, impl: str):
     if impl == "tf32x3" and not torch.is_grad_enabled() and norm.elementwise_affine \
             and ops.add_layernorm_supported(x, sublayer_out, norm.weight):
         return ops.add_layernorm(x, sublayer_out, norm.weight, norm.bias, norm.eps)
+    if impl == "tf32x3" and torch.is_grad_enabled() and norm.elementwise_affine \
+            and sublayer_out.is_contiguous() and AddLayerNormFunction.supported(x, sublayer_out, norm.weight):
+        return AddLayerNormFunction.apply(x, sublayer_out, norm.weight, norm.bias, norm.eps)
     return norm(x + sublayer_out)
 
 

@@ -342,3 +342,21 @@ def linear_wgrad(grad_y, x, with_bias=True):
                                                  torch.cuda.current_stream(x.device).cuda_stream)
     _lib.check(rc, "linear_wgrad")
     return gw, gb
+
+
+def add_layernorm_backward(grad_y, x, residual, weight, eps=1e-5):
+    """(grad_v, grad_weight, grad_bias) of ``layer_norm(x + residual)``; grad_v is the gradient of both x and
+    residual.  Last dimension 128 or 256."""
+    if not (add_layernorm_supported(x, residual, weight) and x.size(-1) in (128, 256)
+            and grad_y.shape == x.shape and grad_y.is_contiguous() and grad_y.dtype == torch.float32):
+        raise RuntimeError("add_layernorm_backward needs contiguous fp32 CUDA tensors with a last dimension of 128 or 256")
+    gv = torch.empty_like(x)
+    gg, gb = torch.empty_like(weight), torch.empty_like(weight)
+    cols = x.size(-1)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib.msda_b200_add_layernorm_backward_f32(
+            grad_y.data_ptr(), x.data_ptr(), residual.data_ptr() if residual is not None else None,
+            weight.data_ptr(), gv.data_ptr(), gg.data_ptr(), gb.data_ptr(), x.numel() // cols, cols, float(eps),
+            torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(rc, "add_layernorm_backward")
+    return gv, gg, gb
