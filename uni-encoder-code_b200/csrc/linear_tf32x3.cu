@@ -15,17 +15,28 @@
 // SECOND accumulator (2^-11 of the magnitude, hence 2^-11 of the truncation error) that is added in the
 // epilogue: one third of the accumulations into the main one.
 //
-// Structure (persistent: one CTA per SM walks 128 x BN output tiles, BN = 128 or 96; 10 warps):
-//   pre-pass  W is split once per call into Whi / Wlo (workspace, 2 x N x K floats);
+// Two kernels in this file (msda_b200_set_option("linear_variant", v) overrides the choice):
+//   * linear_tf32x3_atmem_kernel -- the default for in_features < 512: A operand (x_hi, x_lo) in tensor
+//     memory, see the comment above it;
+//   * linear_tf32x3_kernel -- both operands in shared memory; used with four accumulators {main, main', small,
+//     small'} for in_features >= 512 (the truncating accumulation: error at the fp32 SIMT level needs fewer
+//     MMAs per accumulator), with the weight split inside the kernel when no workspace is given, and split-K
+//     (reductions into the zero-filled output) when the output has few tiles and a very long reduction.
+//
+// Structure of linear_tf32x3_kernel (persistent: one CTA per SM walks 128 x BN output tiles, BN = 128 or 96;
+// 14 warps):
+//   pre-pass  W is split once per call into Whi / Wlo (workspace, 2 x N x K floats), unless WSPLIT;
 //   warp 0   one thread: TMA loads of the fp32 X tile (128 x 32) and the Whi / Wlo tiles (BN x 32) of
 //            each k-block into a STAGES-deep ring (128-byte swizzle: a tile row is one swizzle span);
-//   warps 2-5 compute x_lo of the landed X tile element-wise into a second buffer (same offsets -- the
-//            swizzle is irrelevant to an element-wise pass), fence to the async proxy and hand it to
-//   warp 1   one thread: 3 x 4 tcgen05.mma.kind::tf32 (128 x BN x 8) per k-block into one of TWO
-//            {main, small} accumulator sets in TMEM, tcgen05.commit to release the stage;
-//   warps 6-9 epilogue of tile i while tile i+1 is being computed: tcgen05.ld both accumulators
-//            (lane = row), add them and the bias, ReLU, transpose 32 x 32 blocks through shared memory
-//            and store whole 128-byte row segments.
+//   warps 2-5 compute x_lo (and w_lo if WSPLIT) of the landed tiles element-wise into a second buffer (same
+//            offsets -- the swizzle is irrelevant to an element-wise pass), fence to the async proxy and hand
+//            the stage to
+//   warp 1   one thread: the tcgen05.mma.kind::tf32 of the k-block (x_hi * [W_hi; W_lo]^T as ONE double-width
+//            MMA into the adjacent {main, small} accumulators as soon as TMA has landed -- x_hi is the raw
+//            tile --, x_lo * W_hi^T into small when the split is done), tcgen05.commit to release the stage;
+//   warps 6-13 epilogue (of tile i while tile i+1 is computed when there are two accumulator sets):
+//            tcgen05.ld the accumulators (lane = row) and add them up, hand the set back, then bias, ReLU,
+//            32 x 32 transposes through shared memory and 128-byte row-segment stores (or reductions).
 #include "tc_common.cuh"
 
 namespace msda {
