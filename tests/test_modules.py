@@ -106,6 +106,34 @@ def test_module_refuses_cpu_without_injected_core(pkg):
           torch.tensor(LEVELS), torch.tensor([0, 6, 30]))
 
 
+def test_inference_kernel_option_is_inert_on_cpu_and_wrappers_refuse_cpu(pkg, oracle):
+    """linear="tf32x3" selects CUDA kernels for CUDA tensors only: on CPU tensors (host-logic tests with an
+    injected core) the mirror takes torch's kernels and gives the very same numbers; the wrappers themselves
+    refuse CPU tensors like the reference's extension does."""
+    kw = dict(d_model=64, nhead=2, num_encoder_layers=2, dim_feedforward=128, dropout=0.0,
+              num_feature_levels=3, enc_n_points=4, core=oracle_core(oracle))
+    torch.manual_seed(3)
+    a = pkg.modules.MSDeformAttnTransformerEncoderOnly(**kw).eval()
+    b = pkg.modules.MSDeformAttnTransformerEncoderOnly(linear="tf32x3", **kw).eval()
+    b.load_state_dict(a.state_dict())
+    srcs = [torch.randn(1, 64, h, w) for h, w in LEVELS]
+    pos = [torch.randn(1, 64, h, w) for h, w in LEVELS]
+    with torch.no_grad():
+        assert torch.equal(a(srcs, pos)[0], b(srcs, pos)[0])
+    assert torch.equal(a(srcs, pos)[0], b(srcs, pos)[0])            # autograd on
+    with pytest.raises(ValueError, match="unknown linear implementation"):
+        pkg.modules._linear(torch.nn.Linear(4, 4), torch.randn(2, 4), "fp8")
+    x, w = torch.randn(8, 32), torch.randn(8, 32)
+    for call in (lambda: pkg.linear_tf32x3(x, w, None), lambda: pkg.add_layernorm(x, None, w[0], w[1]),
+                 lambda: pkg.ops.linear_wgrad(x, x)):
+        with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+            call()
+    # the level tensors are cached per (pyramid, device) and equal the reference's construction
+    shapes, lsi = pkg.modules.level_tensors_for(LEVELS, "cpu")
+    assert shapes.tolist() == [list(l) for l in LEVELS] and lsi.tolist() == [0, 6, 30]
+    assert pkg.modules.level_tensors_for(LEVELS, "cpu")[0] is shapes
+
+
 @pytest.mark.gpu
 def test_mirror_plus_cuda_op_matches_reference_encoder_golden(pkg):
     """Reference encoder (fp64, CPU, in the build container) vs mirror + sm_100a kernels in fp32."""
