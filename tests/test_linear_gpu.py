@@ -300,3 +300,26 @@ def test_add_layernorm_autograd_function(pkg, rows, cols):
         err32 = (r32.grad.double() - r64.grad).abs().max().item()
         assert err <= 3 * err32 + 1e-6 * max(1.0, r64.grad.abs().max().item()), (err, err32)
     assert torch.equal(leaves[0].grad, leaves[1].grad)
+
+
+def test_linear_and_wgrad_random_shapes(pkg):
+    """Seeded random problem shapes through whichever kernel the dispatcher picks (A in tensor memory, four
+    accumulators for long reductions, split-K): exact on small integers."""
+    rng = np.random.default_rng(2024)
+    for _ in range(24):
+        rows = int(rng.integers(1, 3000))
+        in_f = 32 * int(rng.integers(1, 40))
+        out_f = 4 * int(rng.integers(1, 100))
+        relu = bool(rng.integers(0, 2))
+        x = torch.from_numpy(rng.integers(-3, 4, (rows, in_f)).astype(np.float32)).to(DEV)
+        w = torch.from_numpy(rng.integers(-3, 4, (out_f, in_f)).astype(np.float32)).to(DEV)
+        b = torch.from_numpy(rng.integers(-5, 6, (out_f,)).astype(np.float32)).to(DEV) if rng.integers(0, 2) else None
+        ref = x.double() @ w.double().t() + (b.double() if b is not None else 0)
+        ref = ref.relu() if relu else ref
+        y = pkg.linear_tf32x3(x, w, b, relu=relu)
+        assert torch.equal(y, ref.float()), (rows, out_f, in_f, relu)
+        gy = torch.from_numpy(rng.integers(-2, 3, (rows, out_f)).astype(np.float32)).to(DEV)
+        xs = x[:, : 4 * int(rng.integers(1, in_f // 4 + 1))].contiguous()
+        gw, gb = pkg.ops.linear_wgrad(gy, xs)
+        assert torch.equal(gw, (gy.double().t() @ xs.double()).float()), (rows, out_f, xs.shape)
+        assert torch.equal(gb, gy.double().sum(0).float())
