@@ -156,3 +156,27 @@ def test_mirror_fp64_cuda_op_matches_reference_encoder_golden(pkg):
     with torch.no_grad():
         memory = m(srcs, pos)[0]
     assert np.abs(memory.cpu().numpy() - g["memory"]).max() <= 1e-9
+
+
+def test_inference_position_cache_tracks_its_inputs(pkg, oracle):
+    """In inference the (position + level) embedding is cached; new position tensors, an in-place change of
+    them or of level_embed must all invalidate it."""
+    m = pkg.modules.MSDeformAttnTransformerEncoderOnly(d_model=64, nhead=2, num_encoder_layers=1, dim_feedforward=64,
+                                                       dropout=0.0, num_feature_levels=3, enc_n_points=4,
+                                                       core=oracle_core(oracle)).eval()
+    srcs = [torch.randn(1, 64, h, w) for h, w in LEVELS]
+
+    def fresh(pos):
+        m._pos_cache_key = None
+        with torch.no_grad():
+            return m(srcs, pos)[0]
+    with torch.no_grad():
+        for _ in range(3):
+            pos = [torch.randn(1, 64, h, w) for h, w in LEVELS]
+            assert torch.equal(m(srcs, pos)[0], fresh(pos))
+            assert torch.equal(m(srcs, pos)[0], fresh(pos))          # second call: served from the cache
+            pos[1].mul_(2.0)
+            assert torch.equal(m(srcs, pos)[0], fresh(pos))
+            m.level_embed.add_(0.5)
+            assert torch.equal(m(srcs, pos)[0], fresh(pos))
+    assert torch.equal(m(srcs, pos)[0], fresh(pos))                   # autograd on: no cache involved

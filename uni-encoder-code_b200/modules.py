@@ -291,11 +291,25 @@ class MSDeformAttnTransformerEncoderOnly(nn.Module):
                 m._reset_parameters()
         nn.init.normal_(self.level_embed)
 
+    def _level_pos(self, pos_embeds):
+        return torch.cat([p.flatten(2).transpose(1, 2) + self.level_embed[i].view(1, 1, -1)
+                          for i, p in enumerate(pos_embeds)], 1)
+
     def flatten_inputs(self, srcs, pos_embeds):
         levels = [(int(s.shape[2]), int(s.shape[3])) for s in srcs]
         src = torch.cat([s.flatten(2).transpose(1, 2) for s in srcs], 1)
-        pos = torch.cat([p.flatten(2).transpose(1, 2) + self.level_embed[i].view(1, 1, -1)
-                         for i, p in enumerate(pos_embeds)], 1)
+        if torch.is_grad_enabled():
+            pos = self._level_pos(pos_embeds)
+        else:
+            # inference: position embedding + level embedding depends on the shapes and on one parameter only;
+            # built once per (position tensors, level_embed version) instead of on every call
+            key = (tuple((p.data_ptr(), p._version, tuple(p.shape), tuple(p.stride())) for p in pos_embeds),
+                   self.level_embed.data_ptr(), self.level_embed._version)
+            if getattr(self, "_pos_cache_key", None) != key:
+                # the position tensors are kept referenced so their memory cannot be handed to other data
+                self._pos_cache_key, self._pos_cache_src = key, list(pos_embeds)
+                self._pos_cache = self._level_pos(pos_embeds)
+            pos = self._pos_cache
         shapes, lsi = level_tensors_for(levels, src.device)
         return src, pos, shapes, lsi, levels
 
