@@ -59,10 +59,14 @@ linear_wgrad_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kblocks_all = (int)((rows + kBK - 1) / kBK);
     const int n_tiles = (out_f + kBM - 1) / kBM, k_tiles = (in_f + BN - 1) / BN;
-    const long long items = (long long)n_tiles * k_tiles * chunks;          // chunk fastest
+    // work items: (row chunk, output tile), output tile fastest -- the items that read the same rows of grad_y
+    // and x run at the same time on neighbouring SMs, so each row is fetched from HBM once (chunk fastest
+    // measured 2x the DRAM reads: every operand came in once per output-tile row / column)
+    const long long items = (long long)n_tiles * k_tiles * chunks;
     auto decode = [&](long long t, int &n0, int &k0, int &kb0, int &nkb) {
-        const int chunk = (int)(t % chunks);
-        const long long o = t / chunks;
+        const int out_tiles = n_tiles * k_tiles;
+        const int chunk = (int)(t / out_tiles);
+        const long long o = t % out_tiles;
         n0 = (int)(o / k_tiles) * kBM;
         k0 = (int)(o % k_tiles) * BN;
         kb0 = chunk * kb_per_chunk;
