@@ -5,6 +5,7 @@
 // Tensor-level checks (contiguity, device, dtype, im2col_step divisibility) live in
 // the Python shim because they need tensor metadata; this layer sees raw pointers.
 #include <atomic>
+#include <cstdint>
 #include <cstring>
 
 #include "../../include/msda_b200.h"
@@ -18,6 +19,9 @@ cudaError_t launch_fwd_d32(const float *, const int64_t *, const int64_t *, cons
 cudaError_t launch_bwd_d32(const float *, const float *, const int64_t *, const int64_t *,
                            const float *, const float *, const Dims &, float *, float *, float *,
                            cudaStream_t, bool *handled);
+cudaError_t launch_bwd_sorted(const float *, const float *, const int64_t *, const int64_t *,
+                              const float *, const float *, const Dims &, float *, float *, float *,
+                              cudaStream_t, bool *handled);
 cudaError_t launch_fwd_d32_fused(const float *, const int64_t *, const int64_t *, const float *,
                                  long long, const float *, const float *, const Dims &, float *,
                                  cudaStream_t, bool *handled);
@@ -67,6 +71,12 @@ static int check_dims(const Dims &d) {
     if (d.L > MSDA_MAX_LEVELS) return MSDA_ERR_UNSUPPORTED;
     return MSDA_OK;
 }
+
+// the 32-channel kernels use 128-bit accesses on value / output rows and 64-bit ones on the
+// locations; a contiguous tensor view with an odd storage offset goes to the generic kernels,
+// which accept any alignment like the reference's scalar kernels do
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static bool aligned8(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
 
 static int option_index(const char *name) {
     if (!name) return -1;
@@ -129,7 +139,8 @@ int msda_b200_forward_f32(const float *value, const int64_t *spatial_shapes,
     cudaStream_t st = (cudaStream_t)stream;
     bool handled = false;
     cudaError_t e = cudaSuccess;
-    if (option_value(OPT_FWD_VARIANT) != 63)   // 63 forces the generic kernel (tests)
+    const bool fast_ok = aligned16(value) && aligned16(output) && aligned8(sampling_loc);
+    if (option_value(OPT_FWD_VARIANT) != 63 && fast_ok)   // 63 forces the generic kernel (tests)
         e = launch_fwd_d32(value, spatial_shapes, level_start, sampling_loc, attn_weight, d, output, st,
                            &handled);
     if (e == cudaSuccess && !handled)
@@ -165,7 +176,15 @@ int msda_b200_backward_f32(const float *grad_output, const float *value,
     cudaStream_t st = (cudaStream_t)stream;
     bool handled = false;
     cudaError_t e = cudaSuccess;
-    if (option_value(OPT_BWD_VARIANT) != 63)
+    const int variant = option_value(OPT_BWD_VARIANT);
+    const bool fast_ok = aligned16(value) && aligned16(grad_output) && aligned16(grad_value) &&
+                         aligned8(sampling_loc) && aligned8(grad_sampling_loc);
+    // 0 (default) / 20: the in-SM merging kernel where it applies (queries == value pixels), else the
+    // per-row reduction kernel; 1..8: CTA shapes of the latter; 63: generic kernel (tests)
+    if ((variant == 0 || variant == 20) && fast_ok)
+        e = launch_bwd_sorted(grad_output, value, spatial_shapes, level_start, sampling_loc, attn_weight,
+                              d, grad_value, grad_sampling_loc, grad_attn_weight, st, &handled);
+    if (e == cudaSuccess && !handled && variant != 63 && fast_ok)
         e = launch_bwd_d32(grad_output, value, spatial_shapes, level_start, sampling_loc, attn_weight,
                            d, grad_value, grad_sampling_loc, grad_attn_weight, st, &handled);
     if (e == cudaSuccess && !handled)

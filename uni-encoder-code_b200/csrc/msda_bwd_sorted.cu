@@ -1,0 +1,599 @@
+// msda_bwd_sorted.cu -- backward MSDA kernel for sm_100a (32 fp32 channels per head) that merges
+// the grad_value contributions of a query tile INSIDE the SM before anything is sent to L2.
+//
+// Replaces ms_deformable_col2im_gpu_kernel_shm_blocksize_aware_reduce_v1<T,32>
+// (ms_deform_im2col_cuda.cuh:306-408) and ms_deform_attn_col2im_bilinear (cuh:92-164), where
+// every one of the 48 corner rows of a (query, head) goes to L2 as 32 scalar atomicAdds
+// (cuh:130-157).  msda_bwd.cu already turned those into one 128-bit reduction per lane, but
+// every corner row still travelled to L2 alone: 3.86 GB of reductions per launch for 88 MB of
+// grad_value at BASELINE configs[1], pinned at the 6.4 TB/s the L2 reduction path sustains
+// (profiles/r1_microbench.txt).  Neighbouring queries of the encoder sample the same pixels
+// (their reference points are their own pixel centres, msdeformattn.py:152-166), so here the
+// corner records of a tile of 128 queries are SORTED BY DESTINATION PIXEL in shared memory and
+// every run of equal pixels is accumulated in registers and sent to L2 once.
+//
+// One work item = (image n, head m, tile of 128 queries = 8 x 16 pixels of one level).  Per item:
+//   pass A   one sampling point per thread: decompose() (the same single home of the integer
+//            work as every other kernel), and for each contributing corner whose pixel lies in
+//            the item's per-level WINDOW (tile footprint +- 9 px, clipped to the level) the
+//            counter of that pixel is incremented (integer shared-memory atomics: 0.84 cycles
+//            per warp instruction measured; fp32 ones are CAS loops).  The point's window slots,
+//            first pixel, fractions and weight stay in registers for pass B;
+//   scan     exclusive prefix sum of the counters (conflict-free warp scans);
+//   pass B   every corner record {pixel:18 | query:7 | - | point*4+corner:6, bilinear*attention
+//            weight} is written to its sorted position (atomicAdd on the counter returns the
+//            rank); corners outside every window are appended behind the sorted ones -- they
+//            are processed by the same loop as runs of length one, so correctness never
+//            depends on the windows, only the amount of merging does;
+//   merge    the record array is cut into equal slices, one per 8-lane group (lane = 16 bytes
+//            of a 128-byte row).  A group walks its slice: at the first record of a pixel it
+//            loads that pixel's value row ONCE (one LDG.128 per lane), then per record reads the
+//            query's grad_output row from shared memory, accumulates weight * grad_output in
+//            registers and forms its part of the dot product D = <value row, grad_output row>;
+//            when the pixel changes the accumulator leaves as ONE red.global.add.v4.f32 per
+//            lane.  A run cut by a slice boundary is simply flushed by both groups.  Eight
+//            records' partial dot products are summed over the 8 lanes with a 7-shuffle
+//            reduce-scatter and land in D[query][point][corner] in shared memory;
+//   epilogue one sampling point per thread again: grad_attn_weight and grad_sampling_loc are the
+//            reference's linear combinations of the point's four D (cuh:128-163), written with
+//            coalesced stores.  Both are deterministic and need no zero fill.
+//
+// Per (query, head) the L1/shared-memory data pipe now carries 48 grad_output rows + the value
+// rows and reductions of the DISTINCT pixels (48 / merge factor, ~9x at configs[1]) instead of
+// 48 value rows + 48 reductions; see DESIGN.md section 4.3 for the measured numbers.
+//
+// Used when the queries are the value pixels (Lq == S, encoder self-attention); when the level
+// layout does not tile them (decided on the device, like the other kernels) the windows are
+// empty and every record takes the run-of-one path.  Other shapes: msda_bwd.cu.
+#include "msda_common.cuh"
+
+namespace msda {
+
+constexpr int kSortTile = 128;           // queries per item: 7 bits of the record word
+constexpr int kSortSlots = 4096;         // window slots (pixel counters) per item
+constexpr int kSortMargin = 9;           // window = tile footprint +- this many pixels
+constexpr uint32_t kNoKey = 0x3ffffu;    // pixel field of an absent record; S < kNoKey (host check)
+constexpr uint32_t kSlotNone = 0xffffu;  // pass A -> pass B: corner does not contribute
+constexpr uint32_t kSlotTail = 0xfffeu;  //                   corner outside every window
+
+// record word: [pixel:18 | query slot:7 | 0 | point*4+corner:6]; (word & 0x3f80) = query slot * 128,
+// the byte offset of the query's grad_output row in shared memory
+__device__ __forceinline__ uint32_t rec_word(uint32_t pix, uint32_t q, uint32_t pc) {
+    return (pix << 14) | (q << 7) | pc;
+}
+
+template <int LP, int WARPS, int TILE_W>
+struct SortCfg {
+    static constexpr int kThreads = WARPS * 32;
+    static constexpr int kTileH = kSortTile / TILE_W;
+    static constexpr int kPC = LP * 4;                       // corner records per query
+    static constexpr int kRecs = kSortTile * kPC;            // record capacity of an item
+    static constexpr int kPoints = kSortTile * LP;
+    static constexpr int kRounds = (kPoints + kThreads - 1) / kThreads;
+    static constexpr int kGroups = WARPS * 4;                // 8-lane groups
+    static constexpr size_t kRecBytes = (size_t)kRecs * sizeof(uint2);
+    static constexpr size_t kGoBytes = (size_t)kSortTile * 128;
+    static constexpr size_t kDBytes = (size_t)kRecs * sizeof(float);
+    static constexpr size_t kCntBytes = (size_t)kSortSlots * sizeof(uint32_t);
+    static constexpr size_t kSmem = kRecBytes + kGoBytes + kDBytes + kCntBytes;
+    static_assert(kPC <= 64 && kSortTile % TILE_W == 0, "record word: 6 bits of point*4+corner");
+    static_assert((kRecs / kGroups) % 8 == 0, "slices are padded to multiples of 8 records");
+    static_assert(kSortSlots < (int)kSlotTail, "16-bit slot numbers between the passes");
+};
+
+// where the queries of a tile live
+struct TileMap {
+    int spatial;        // 1: 2-D tile of level lq; 0: 128 consecutive queries
+    int X0, Y0;         // pixel origin of the tile inside its level (spatial)
+    int H, W, start;    // of the tile's level
+    int q0;             // first query (non-spatial)
+};
+
+template <int TILE_W, int TILE_H>
+__device__ __forceinline__ TileMap tile_of(const LevelTable &lt, int L, int g) {
+    TileMap t;
+    t.spatial = lt.spatial;
+    t.X0 = 0; t.Y0 = 0; t.H = 0; t.W = 0; t.start = 0;
+    t.q0 = g * kSortTile;
+    if (lt.spatial) {
+        int l = 0;
+        while (l + 1 < L && g >= lt.tile_begin[l + 1]) ++l;
+        const int r = g - lt.tile_begin[l];
+        const int ty = r / lt.tiles_x[l], tx = r - ty * lt.tiles_x[l];
+        t.X0 = tx * TILE_W;
+        t.Y0 = ty * TILE_H;
+        t.H = lt.H[l];
+        t.W = lt.W[l];
+        t.start = lt.start[l];
+    }
+    return t;
+}
+
+// query index (inside one image) of slot q of the tile, -1 when the slot is empty
+template <int TILE_W>
+__device__ __forceinline__ int tile_query(const TileMap &t, int q, int Lq) {
+    if (t.spatial) {
+        const int y = t.Y0 + q / TILE_W, x = t.X0 + q % TILE_W;
+        return (y < t.H && x < t.W) ? t.start + y * t.W + x : -1;
+    }
+    const int qg = t.q0 + q;
+    return qg < Lq ? qg : -1;
+}
+
+// Windows of the item whose tile is `t` (warp 0, lane = level): {x0, y0, width | height << 16,
+// first slot}; total slots -> *slots_out.  Heuristic only: a window decides which records can be
+// merged, never what is computed.
+template <int TILE_W, int TILE_H>
+__device__ __forceinline__ void compute_windows(const LevelTable &lt, int L, const TileMap &t,
+                                                int4 *win_out, int *slots_out, int lane) {
+    int x0 = 0, y0 = 0, ww = 0, wh = 0;
+    if (t.spatial && lane < L) {
+        const int Wl = lt.W[lane], Hl = lt.H[lane];
+        const float sx = (float)Wl / (float)t.W, sy = (float)Hl / (float)t.H;
+        const int X1 = min(t.X0 + TILE_W, t.W), Y1 = min(t.Y0 + TILE_H, t.H);
+        int xa = (int)floorf((float)t.X0 * sx) - kSortMargin, xb = (int)ceilf((float)X1 * sx) + kSortMargin;
+        int ya = (int)floorf((float)t.Y0 * sy) - kSortMargin, yb = (int)ceilf((float)Y1 * sy) + kSortMargin;
+        xa = max(xa, 0); ya = max(ya, 0);
+        xb = min(xb, Wl); yb = min(yb, Hl);
+        ww = max(xb - xa, 0); wh = max(yb - ya, 0);
+        x0 = xa; y0 = ya;
+        if ((long long)ww * wh > kSortSlots) { ww = 0; wh = 0; }   // cannot fit on its own
+    }
+    int area = ww * wh;
+    // budget: drop the largest windows (the least merging per slot) until the rest fits
+    for (int round = 0; round < kMaxLevels; ++round) {
+        int total = area, mx = area;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            total += __shfl_xor_sync(kFullMask, total, o);
+            mx = max(mx, __shfl_xor_sync(kFullMask, mx, o));
+        }
+        if (total <= kSortSlots) break;
+        const unsigned who = __ballot_sync(kFullMask, area == mx);
+        if (lane == __ffs(who) - 1) { ww = 0; wh = 0; area = 0; }
+    }
+    int incl = area;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(kFullMask, incl, o);
+        if (lane >= o) incl += up;
+    }
+    if (lane < L) win_out[lane] = make_int4(x0, y0, ww | (wh << 16), incl - area);
+    if (lane == 31) *slots_out = incl;
+}
+
+// What pass A leaves in registers for pass B, per sampling point.
+struct Binned {
+    uint32_t s01, s23;     // window slot of each corner (16 bits each), kSlotNone / kSlotTail
+    int pix0;              // pixel of corner 0 (row above / column left of the sample)
+    float lh, lw, aw;
+};
+
+// Pass A for one point: geometry, window slots, per-pixel counts.
+__device__ __forceinline__ Binned count_point(const LevelTable &lt, const int4 *win, uint32_t *cnt,
+                                              float x, float y, float aw, int p) {
+    Binned b;
+    b.s01 = b.s23 = kSlotNone | (kSlotNone << 16);
+    b.pix0 = 0; b.lh = 0.f; b.lw = 0.f; b.aw = aw;
+    const int l = lt.level_of[p];
+    const int4 lv = lt.hws[l];                       // {H, W, start, -}
+    const Geom<float> gm = decompose(x, y, lv.x, lv.y);
+    if (gm.cmask == 0) return b;                     // point outside (cuh:293): no record
+    const int4 wn = win[l];
+    const int ww = wn.z & 0xffff, wh = wn.z >> 16;
+    const int sx = gm.w_low - wn.x, sy = gm.h_low - wn.y;
+    b.pix0 = lv.z + gm.h_low * lv.y + gm.w_low;      // h_low / w_low may be -1: only used with a valid corner
+    b.lh = gm.lh; b.lw = gm.lw;
+    uint32_t sl[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int dx = k & 1, dy = k >> 1;
+        sl[k] = kSlotNone;
+        if (gm.cmask & (1 << k)) {
+            const bool inwin = (unsigned)(sx + dx) < (unsigned)ww && (unsigned)(sy + dy) < (unsigned)wh;
+            sl[k] = kSlotTail;
+            if (inwin) {
+                const int slot = wn.w + (sy + dy) * ww + sx + dx;
+#ifdef MSDA_CHECK_BOUNDS
+                assert(slot >= 0 && slot < kSortSlots);
+#endif
+                atomicAdd(&cnt[slot], 1u);
+                sl[k] = (uint32_t)slot;
+            }
+        }
+    }
+    b.s01 = sl[0] | (sl[1] << 16);
+    b.s23 = sl[2] | (sl[3] << 16);
+    return b;
+}
+
+// Pass B for one point: its corner records to their places.
+__device__ __forceinline__ void place_point(const Binned &b, uint32_t *cnt, uint2 *rec, uint32_t *tail_ctr,
+                                            uint32_t n_in, int W, int q, int p, int S, int rec_cap) {
+    const float hh = 1.f - b.lh, hw = 1.f - b.lw;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int dx = k & 1, dy = k >> 1;
+        const uint32_t pair = dy ? b.s23 : b.s01;
+        const uint32_t slot = dx ? (pair >> 16) : (pair & 0xffffu);
+        if (slot != kSlotNone) {
+            const uint32_t pos = slot != kSlotTail ? atomicAdd(&cnt[slot], 1u) : n_in + atomicAdd(tail_ctr, 1u);
+            const float wk = ((dy ? b.lh : hh) * (dx ? b.lw : hw)) * b.aw;     // bilinear * attention weight
+            const int pix = b.pix0 + dy * W + dx;
+#ifdef MSDA_CHECK_BOUNDS
+            assert(pix >= 0 && pix < S && (int)pos < rec_cap);
+#else
+            (void)S; (void)rec_cap;
+#endif
+            rec[pos] = make_uint2(rec_word((uint32_t)pix, (uint32_t)q, (uint32_t)(p * 4 + k)), __float_as_uint(wk));
+        }
+    }
+}
+
+// shared-memory accesses by 32-bit shared address (no generic-address arithmetic in the merge loop)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint2 lds_u2(uint32_t a) {
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a) : "memory");
+    return r;
+}
+__device__ __forceinline__ uint32_t lds_u1(uint32_t a) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a) : "memory");
+    return r;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a) : "memory");
+    return r;
+}
+__device__ __forceinline__ void sts_f1(uint32_t a, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_f4(float4 *p, const float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <int LP, int WARPS, int TILE_W, int MIN_CTAS>
+__global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
+msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restrict__ value,
+                       const int64_t *__restrict__ shapes, const int64_t *__restrict__ lstart,
+                       const float *__restrict__ loc, const float *__restrict__ attw, const Dims d,
+                       const int flags, float *__restrict__ grad_value, float *__restrict__ grad_loc,
+                       float *__restrict__ grad_attw) {
+    using Cfg = SortCfg<LP, WARPS, TILE_W>;
+    constexpr int NT = Cfg::kThreads;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ LevelTable lt;
+    __shared__ int4 win[2][kMaxLevels];
+    __shared__ int win_slots[2];
+    __shared__ uint32_t warp_tot[WARPS];
+    __shared__ uint32_t tail_ctr;
+
+    uint2 *rec = reinterpret_cast<uint2 *>(smem_raw);
+    float4 *go_sm = reinterpret_cast<float4 *>(smem_raw + Cfg::kRecBytes);
+    float *dsm = reinterpret_cast<float *>(smem_raw + Cfg::kRecBytes + Cfg::kGoBytes);
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(smem_raw + Cfg::kRecBytes + Cfg::kGoBytes + Cfg::kDBytes);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int grp = lane >> 3, chunk = lane & 7;
+
+    fill_level_table(lt, shapes, lstart, d.L, d.P, d.S, d.Lq, kSortTile, Cfg::kTileH, TILE_W, flags & 1);
+    for (int i = tid; i < kSortSlots; i += NT) cnt[i] = 0u;   // invariant: zero outside pass A .. pass B
+    __syncthreads();
+
+    const int M = d.M, L = d.L, Lq = d.Lq;
+    const long long items = (long long)d.N * M * lt.groups;
+    const uint32_t M8 = (uint32_t)M * 8u;
+
+    long long item = blockIdx.x;
+    if (warp == 0 && item < items) {
+        const TileMap t0 = tile_of<TILE_W, Cfg::kTileH>(lt, L, (int)((item / M) % lt.groups));
+        compute_windows<TILE_W, Cfg::kTileH>(lt, L, t0, win[0], &win_slots[0], lane);
+    }
+    __syncthreads();
+
+    for (int buf = 0; item < items; item += gridDim.x, buf ^= 1) {
+        const int m = (int)(item % M);
+        const long long rest = item / M;
+        const int g = (int)(rest % lt.groups);
+        const long long n = rest / lt.groups;
+        const int4 *wn = win[buf];
+        const int nslots = win_slots[buf];
+        if (tid == 0) tail_ctr = 0u;
+        // rows of image n: 64-bit bases here, 32-bit offsets (query * M + m) * {8, LP} below
+        // (Lq * M * 16 < 2^32: host check)
+        const float4 *go_n = reinterpret_cast<const float4 *>(grad_out) + n * Lq * (long long)M * 8;
+        const float2 *loc_n = reinterpret_cast<const float2 *>(loc) + n * Lq * (long long)M * LP;
+        const float *attw_n = attw + n * Lq * (long long)M * LP;
+
+        uint32_t n_in;
+        {
+            const TileMap tm = tile_of<TILE_W, Cfg::kTileH>(lt, L, g);
+            // ---- the tile's grad_output rows -> shared memory (read once per record in the merge):
+            // asynchronous copies, waited for at the end of pass B; empty query slots are zero-filled ----
+            {
+                const uint32_t go_dst = smem_u32(go_sm);
+#pragma unroll
+                for (int i = tid; i < kSortTile * 8; i += NT) {
+                    const int qg = tile_query<TILE_W>(tm, i >> 3, Lq);
+                    const float4 *src = go_n + (qg >= 0 ? (uint32_t)(qg * M + m) * 8u + (uint32_t)(i & 7) : 0u);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                                 ::"r"(go_dst + 16u * (uint32_t)i), "l"(src), "r"(qg >= 0 ? 16 : 0) : "memory");
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
+
+            // ---- pass A: load the points, count the in-window corners per pixel ----
+            Binned bn[Cfg::kRounds];
+            bool live[Cfg::kRounds];
+            {
+                float px[Cfg::kRounds], py[Cfg::kRounds], pw[Cfg::kRounds];
+#pragma unroll
+                for (int r = 0; r < Cfg::kRounds; ++r) {       // all global loads first
+                    const int s = r * NT + tid;
+                    const int q = s / LP, p = s - q * LP;
+                    live[r] = false;
+                    px[r] = 0.f; py[r] = 0.f; pw[r] = 0.f;
+                    if (s < Cfg::kPoints) {
+                        const int qg = tile_query<TILE_W>(tm, q, Lq);
+                        if (qg >= 0) {
+                            const uint32_t row = (uint32_t)(qg * M + m) * (uint32_t)LP + (uint32_t)p;
+                            const float2 xy = ldg_stream_f2(loc_n + row);
+                            px[r] = xy.x; py[r] = xy.y;
+                            pw[r] = ldg_stream_f1(attw_n + row);
+                            live[r] = true;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < Cfg::kRounds; ++r) {
+                    const int s = r * NT + tid;
+                    const int p = s % LP;
+                    bn[r].s01 = bn[r].s23 = kSlotNone | (kSlotNone << 16);
+                    if (live[r]) bn[r] = count_point(lt, wn, cnt, px[r], py[r], pw[r], p);
+                }
+            }
+            __syncthreads();                                                // B1: counts complete
+
+            // ---- exclusive scan of the pixel counters ----
+            const int wpw = (((nslots + WARPS - 1) / WARPS) + 31) & ~31;    // counters per warp, multiple of 32
+            const int wbeg = warp * wpw, wend = min(wbeg + wpw, nslots);
+            {
+                uint32_t sum = 0;
+                for (int w = wbeg + lane; w < wend; w += 32) sum += cnt[w];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(kFullMask, sum, o);
+                if (lane == 0) warp_tot[warp] = sum;
+            }
+            __syncthreads();                                                // B2: warp totals
+            {
+                const uint32_t wt = lane < WARPS ? warp_tot[lane] : 0u;
+                uint32_t incl = wt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t up = __shfl_up_sync(kFullMask, incl, o);
+                    if (lane >= o) incl += up;
+                }
+                n_in = __shfl_sync(kFullMask, incl, 31);
+                uint32_t run = __shfl_sync(kFullMask, incl - wt, warp);     // records before this warp's counters
+                for (int w0 = wbeg; w0 < wend; w0 += 32) {
+                    const int w = w0 + lane;
+                    const uint32_t c = w < wend ? cnt[w] : 0u;
+                    uint32_t inc = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t up = __shfl_up_sync(kFullMask, inc, o);
+                        if (lane >= o) inc += up;
+                    }
+                    if (w < wend) cnt[w] = run + inc - c;
+                    run += __shfl_sync(kFullMask, inc, 31);
+                }
+            }
+            __syncthreads();                                                // B3: offsets complete
+
+            // ---- pass B: records to their sorted positions (outside every window: appended) ----
+#pragma unroll
+            for (int r = 0; r < Cfg::kRounds; ++r) {
+                const int s = r * NT + tid;
+                const int q = s / LP, p = s - q * LP;
+                if ((bn[r].s01 & bn[r].s23) != (kSlotNone | (kSlotNone << 16)))
+                    place_point(bn[r], cnt, rec, &tail_ctr, n_in, lt.W[lt.level_of[p]], q, p, d.S, Cfg::kRecs);
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();                                                    // B4: records + grad_output tile complete
+
+        // counters back to zero for the next item; warp 0 prepares the next item's windows
+        for (int i = tid; i < nslots; i += NT) cnt[i] = 0u;
+        if (warp == 0 && item + gridDim.x < items) {
+            const TileMap tn = tile_of<TILE_W, Cfg::kTileH>(lt, L, (int)(((item + gridDim.x) / M) % lt.groups));
+            compute_windows<TILE_W, Cfg::kTileH>(lt, L, tn, win[buf ^ 1], &win_slots[buf ^ 1], lane);
+        }
+
+        // ---- merge: equal slices of the record array, one per 8-lane group ----
+        {
+            const int T = (int)(n_in + tail_ctr);
+            // slice length: a multiple of 8 records (kRecs / kGroups is one, so per * kGroups <= kRecs);
+            // what a slice holds beyond T is filled with absent records by the group itself.
+            // Slice of group `grp` of warp `warp`: grp * WARPS + warp -- the sorted array runs from the
+            // coarsest level (long runs, few value rows) to the finest and the unsorted rest, so every
+            // warp gets one slice of each quarter and the warps finish together.
+            const int per = (((T + Cfg::kGroups - 1) / Cfg::kGroups) + 7) & ~7;
+            const int i0 = (grp * WARPS + warp) * per;
+            for (int i = max(i0, T) + chunk; i < i0 + per; i += 8) rec[i] = make_uint2(0xffffffffu, 0u);
+            __syncwarp();
+            const long long img = n * (long long)d.S * M * 8 + chunk;
+            const float4 *vb = reinterpret_cast<const float4 *>(value) + img;
+            float4 *gvb = reinterpret_cast<float4 *>(grad_value) + img;
+            const uint32_t m8 = (uint32_t)m * 8u;
+            const bool b2 = chunk & 4, b1 = chunk & 2, b0 = chunk & 1;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), v = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 gp = make_float4(0.f, 0.f, 0.f, 0.f);              // grad_output row of the previous record
+            uint32_t cur = kNoKey;
+            uint32_t ra = smem_u32(rec) + (uint32_t)i0 * 8u;          // this group's next 8 records
+            const uint32_t go_s = smem_u32(go_sm) + (uint32_t)chunk * 16u;
+            const uint32_t d_s = smem_u32(dsm);
+            // The dot product of a record is formed one step AFTER its accumulation: the value row a
+            // run starts with is requested at the run's first record and first needed a step later.
+            for (int it = 0; it < per; it += 8, ra += 64u) {
+                float dp[8];                                          // dp[j]: record it + j - 1
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint2 rr = lds_u2(ra + 8u * j);
+                    const uint32_t key = rr.x >> 14;
+                    const float4 gq = lds_f4(go_s + (rr.x & 0x3f80u));          // the query's grad_output row
+                    const float wk = __uint_as_float(rr.y);
+                    dp[j] = fmaf(v.w, gp.w, fmaf(v.z, gp.z, fmaf(v.y, gp.y, v.x * gp.x)));
+                    if (key != cur) {                    // first record of a pixel (or of the padding)
+                        if (cur != kNoKey) red_add_f4(at_off16(gvb, cur * M8 + m8), acc);
+                        if (key != kNoKey) v = ldg_keep_f4(at_off16(vb, key * M8 + m8));
+                        cur = key;
+                        acc.x = wk * gq.x; acc.y = wk * gq.y; acc.z = wk * gq.z; acc.w = wk * gq.w;
+                    } else {
+                        acc.x = fmaf(wk, gq.x, acc.x);
+                        acc.y = fmaf(wk, gq.y, acc.y);
+                        acc.z = fmaf(wk, gq.z, acc.z);
+                        acc.w = fmaf(wk, gq.w, acc.w);
+                    }
+                    gp = gq;
+                }
+                // D of record it + j - 1: sum over the group's 8 lanes; lane `chunk` ends up with j = chunk
+                float r1[4], r2[2], r3[1];
+                rs_step<8>(dp, r1, b2, 4);
+                rs_step<4>(r1, r2, b1, 2);
+                rs_step<2>(r2, r3, b0, 1);
+                const int pos = it + chunk - 1;                       // inside the slice
+                if (pos >= 0 && i0 + pos < T) {
+                    const uint32_t xx = lds_u1(ra + 8u * (uint32_t)chunk - 8u);
+                    sts_f1(d_s + 4u * (((xx >> 7) & 127u) * (uint32_t)Cfg::kPC + (xx & 63u)), r3[0]);
+                }
+            }
+            if (cur != kNoKey) red_add_f4(at_off16(gvb, cur * M8 + m8), acc);
+            if (per > 0) {                                            // the slice's last record
+                float dl = fmaf(v.w, gp.w, fmaf(v.z, gp.z, fmaf(v.y, gp.y, v.x * gp.x)));
+                dl += __shfl_xor_sync(kFullMask, dl, 4);
+                dl += __shfl_xor_sync(kFullMask, dl, 2);
+                dl += __shfl_xor_sync(kFullMask, dl, 1);
+                if (chunk == 0 && i0 + per - 1 < T) {
+                    const uint32_t xx = lds_u1(ra - 8u);
+                    sts_f1(d_s + 4u * (((xx >> 7) & 127u) * (uint32_t)Cfg::kPC + (xx & 63u)), dl);
+                }
+            }
+        }
+
+        // ---- epilogue: grad_sampling_loc / grad_attn_weight, one point per thread ----
+        // (the point is re-read from L2 rather than carried in registers across the merge loop; the
+        // loads are issued before the barrier so that they fly while the warp waits)
+        {
+            const TileMap te = tile_of<TILE_W, Cfg::kTileH>(lt, L, g);
+            float2 *gloc_n = reinterpret_cast<float2 *>(grad_loc) + n * Lq * (long long)M * LP;
+            float *gattw_n = grad_attw + n * Lq * (long long)M * LP;
+            float2 exy[Cfg::kRounds];
+            float eaw[Cfg::kRounds];
+            uint32_t erow[Cfg::kRounds];
+            bool elive[Cfg::kRounds];
+#pragma unroll
+            for (int r = 0; r < Cfg::kRounds; ++r) {
+                const int s = r * NT + tid;
+                const int q = s / LP, p = s - q * LP;
+                const int qg = s < Cfg::kPoints ? tile_query<TILE_W>(te, q, Lq) : -1;
+                elive[r] = qg >= 0;
+                erow[r] = (uint32_t)(qg * M + m) * (uint32_t)LP + (uint32_t)p;
+                exy[r] = make_float2(0.f, 0.f);
+                eaw[r] = 0.f;
+                if (elive[r]) {
+                    exy[r] = ldg_stream_f2(loc_n + erow[r]);
+                    eaw[r] = ldg_stream_f1(attw_n + erow[r]);
+                }
+            }
+            __syncthreads();                                                // B5: D complete
+#pragma unroll
+            for (int r = 0; r < Cfg::kRounds; ++r) {
+                const int s = r * NT + tid;
+                const int p = s % LP;
+                if (elive[r]) {
+                    const int4 lv = lt.hws[lt.level_of[p]];
+                    const Geom<float> gm = decompose(exy[r].x, exy[r].y, lv.x, lv.y);
+                    float gx = 0.f, gy = 0.f, ga = 0.f;
+                    if (gm.cmask) {
+                        const float4 D = reinterpret_cast<const float4 *>(dsm)[s];   // [q][p][corner]
+                        const float d0 = (gm.cmask & 1) ? D.x : 0.f, d1 = (gm.cmask & 2) ? D.y : 0.f;
+                        const float d2 = (gm.cmask & 4) ? D.z : 0.f, d3 = (gm.cmask & 8) ? D.w : 0.f;
+                        const float lh = gm.lh, lw = gm.lw, hh = 1.f - gm.lh, hw = 1.f - gm.lw;
+                        // cuh:161: sum_c grad_out[c] * val[c], val = w1 v1 + w2 v2 + w3 v3 + w4 v4
+                        ga = fmaf(hh * hw, d0, fmaf(hh * lw, d1, fmaf(lh * hw, d2, (lh * lw) * d3)));
+                        // cuh:128-156,162-163: W * aw * sum_c g[c] (-hh v1 + hh v2 - lh v3 + lh v4), same for h
+                        gx = (eaw[r] * (float)lv.y) * fmaf(hh, d1 - d0, lh * (d3 - d2));
+                        gy = (eaw[r] * (float)lv.x) * fmaf(hw, d2 - d0, lw * (d3 - d1));
+                    }
+                    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};"
+                                 ::"l"(gloc_n + erow[r]), "f"(gx), "f"(gy) : "memory");
+                    stg_stream_f1(gattw_n + erow[r], ga);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+template <int LP, int WARPS, int TILE_W, int MIN_CTAS>
+static cudaError_t launch_bwd_sorted_cfg(const float *grad_out, const float *value, const int64_t *shapes,
+                                         const int64_t *lstart, const float *loc, const float *attw,
+                                         const Dims &d, float *gv, float *gl, float *gw, cudaStream_t stream) {
+    using Cfg = SortCfg<LP, WARPS, TILE_W>;
+    auto kern = msda_bwd_sorted_kernel<LP, WARPS, TILE_W, MIN_CTAS>;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    static std::atomic<int> ctas_per_sm_of[kMaxDevices];
+    int per_sm = ctas_per_sm_of[dev].load(std::memory_order_acquire);
+    if (per_sm == 0) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
+        if (e != cudaSuccess) return e;
+        int nb = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, WARPS * 32, Cfg::kSmem);
+        if (e != cudaSuccess) return e;
+        per_sm = nb > 0 ? nb : 1;
+        ctas_per_sm_of[dev].store(per_sm, std::memory_order_release);
+    }
+    const int cap = option_value(OPT_CTAS_PER_SM);
+    if (cap > 0 && cap < per_sm) per_sm = cap;
+    long long blocks = (long long)sm_count() * per_sm;
+    const long long items_ub = (long long)d.N * d.M * d.Lq;
+    if (blocks > items_ub) blocks = items_ub;
+    if (blocks < 1) blocks = 1;
+    const int flags = option_value(OPT_TILE_ORDER) != 1 ? 1 : 0;
+    kern<<<(unsigned)blocks, WARPS * 32, Cfg::kSmem, stream>>>(grad_out, value, shapes, lstart, loc, attw, d,
+                                                              flags, gv, gl, gw);
+    note_launch();
+    return cudaGetLastError();
+}
+
+// `handled` = false: shape outside this kernel's domain (the caller falls back to msda_bwd.cu)
+cudaError_t launch_bwd_sorted(const float *grad_out, const float *value, const int64_t *shapes,
+                              const int64_t *lstart, const float *loc, const float *attw, const Dims &d,
+                              float *gv, float *gl, float *gw, cudaStream_t stream, bool *handled) {
+    *handled = true;
+    const int LP = d.L * d.P;
+    if (d.D != 32 || d.Lq != d.S || (long long)d.S >= (long long)kNoKey ||
+        (long long)d.S * d.M * 8 >= 0x7fffffffLL) {
+        *handled = false;
+        return cudaSuccess;
+    }
+#define MSDA_SORTED(LPV, C) \
+    launch_bwd_sorted_cfg<LPV, 16, 16, C>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, stream)
+    switch (LP) {
+        case 4: return MSDA_SORTED(4, 2);
+        case 8: return MSDA_SORTED(8, 2);
+        case 12: return MSDA_SORTED(12, 2);
+        case 16: return MSDA_SORTED(16, 1);
+        default: *handled = false; return cudaSuccess;
+    }
+#undef MSDA_SORTED
+}
+
+}  // namespace msda

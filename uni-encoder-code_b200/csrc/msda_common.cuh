@@ -8,6 +8,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #ifdef MSDA_CHECK_BOUNDS
 #include <cassert>     // `make checked`: every corner offset is asserted to lie inside its image
 #endif
@@ -17,6 +18,7 @@ namespace msda {
 constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kMaxLevels = 16;           // == MSDA_MAX_LEVELS in include/msda_b200.h
 constexpr int kMaxSamples = 64;          // L*P bound for the shared sample->level table
+constexpr int kMaxDevices = 64;          // per-device launch-attribute caches; higher ordinals are refused
 constexpr uint32_t kNoCorner = 0xffffffffu;  // record marker: corner outside the level
 
 // ---------------------------------------------------------------------------
