@@ -126,7 +126,8 @@ def test_kernels_match_oracle(pkg, oracle, levels, batch, heads, channels, point
     (1, 1, 0), (2, 2, 0), (3, 3, 0), (4, 4, 0), (5, 5, 0), (6, 6, 0), (7, 7, 0), (8, 8, 0), (2, 2, 1),
     (7, 8, 1), (63, 63, 0),
     (2, 20, 0),      # in-SM merging backward (the default when Lq == S), query tiles + windows
-    (2, 20, 1)])     # the same kernel with consecutive-query groups: no windows, every record a run of one
+    (2, 20, 1),      # the same kernel with consecutive-query groups: no windows, every record a run of one
+    (2, 21, 0), (2, 22, 0), (2, 23, 0), (2, 24, 0), (2, 25, 0), (2, 22, 1)])   # its tuning variants
 def test_kernel_variants_agree(pkg, oracle, fwd_variant, bwd_variant, tile_order):
     """Every tile shape / query order / the generic kernel computes the same function."""
     inp = pkg.synthetic.make_inputs([(5, 11), (10, 22), (20, 44)], 2, mode="model", seed=3)

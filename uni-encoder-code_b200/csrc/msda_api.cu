@@ -179,9 +179,9 @@ int msda_b200_backward_f32(const float *grad_output, const float *value,
     const int variant = option_value(OPT_BWD_VARIANT);
     const bool fast_ok = aligned16(value) && aligned16(grad_output) && aligned16(grad_value) &&
                          aligned8(sampling_loc) && aligned8(grad_sampling_loc);
-    // 0 (default) / 20: the in-SM merging kernel where it applies (queries == value pixels), else the
+    // 0 (default) / 20..39: the in-SM merging kernel (and its tuning variants) where it applies (queries == value pixels), else the
     // per-row reduction kernel; 1..8: CTA shapes of the latter; 63: generic kernel (tests)
-    if ((variant == 0 || variant == 20) && fast_ok)
+    if ((variant == 0 || (variant >= 20 && variant < 40)) && fast_ok)
         e = launch_bwd_sorted(grad_output, value, spatial_shapes, level_start, sampling_loc, attn_weight,
                               d, grad_value, grad_sampling_loc, grad_attn_weight, st, &handled);
     if (e == cudaSuccess && !handled && variant != 63 && fast_ok)

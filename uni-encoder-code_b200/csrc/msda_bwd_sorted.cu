@@ -49,8 +49,7 @@
 
 namespace msda {
 
-constexpr int kSortTile = 128;           // queries per item: 7 bits of the record word
-constexpr int kSortSlots = 4096;         // window slots (pixel counters) per item
+constexpr int kSortTileMax = 128;        // queries per item <= 128: 7 bits of the record word
 constexpr int kSortMargin = 9;           // window = tile footprint +- this many pixels
 constexpr uint32_t kNoKey = 0x3ffffu;    // pixel field of an absent record; S < kNoKey (host check)
 constexpr uint32_t kSlotNone = 0xffffu;  // pass A -> pass B: corner does not contribute
@@ -62,23 +61,24 @@ __device__ __forceinline__ uint32_t rec_word(uint32_t pix, uint32_t q, uint32_t 
     return (pix << 14) | (q << 7) | pc;
 }
 
-template <int LP, int WARPS, int TILE_W>
+// TILE_Q queries per item (a TILE_W-wide 2-D tile of one level), SLOTS window pixels per item
+template <int LP, int WARPS, int TILE_W, int TILE_Q, int SLOTS>
 struct SortCfg {
+    static constexpr int kSortTile = TILE_Q, kSortSlots = SLOTS;
     static constexpr int kThreads = WARPS * 32;
     static constexpr int kTileH = kSortTile / TILE_W;
     static constexpr int kPC = LP * 4;                       // corner records per query
     static constexpr int kRecs = kSortTile * kPC;            // record capacity of an item
     static constexpr int kPoints = kSortTile * LP;
     static constexpr int kRounds = (kPoints + kThreads - 1) / kThreads;
-    static constexpr int kGroups = WARPS * 4;                // 8-lane groups
     static constexpr size_t kRecBytes = (size_t)kRecs * sizeof(uint2);
     static constexpr size_t kGoBytes = (size_t)kSortTile * 128;
     static constexpr size_t kDBytes = (size_t)kRecs * sizeof(float);
     static constexpr size_t kCntBytes = (size_t)kSortSlots * sizeof(uint32_t);
     static constexpr size_t kSmem = kRecBytes + kGoBytes + kDBytes + kCntBytes;
     static_assert(kPC <= 64 && kSortTile % TILE_W == 0, "record word: 6 bits of point*4+corner");
-    static_assert((kRecs / kGroups) % 8 == 0, "slices are padded to multiples of 8 records");
     static_assert(kSortSlots < (int)kSlotTail, "16-bit slot numbers between the passes");
+    static_assert(TILE_Q <= kSortTileMax, "7-bit query slot");
 };
 
 // where the queries of a tile live
@@ -94,7 +94,7 @@ __device__ __forceinline__ TileMap tile_of(const LevelTable &lt, int L, int g) {
     TileMap t;
     t.spatial = lt.spatial;
     t.X0 = 0; t.Y0 = 0; t.H = 0; t.W = 0; t.start = 0;
-    t.q0 = g * kSortTile;
+    t.q0 = g * (TILE_W * TILE_H);
     if (lt.spatial) {
         int l = 0;
         while (l + 1 < L && g >= lt.tile_begin[l + 1]) ++l;
@@ -123,7 +123,7 @@ __device__ __forceinline__ int tile_query(const TileMap &t, int q, int Lq) {
 // Windows of the item whose tile is `t` (warp 0, lane = level): {x0, y0, width | height << 16,
 // first slot}; total slots -> *slots_out.  Heuristic only: a window decides which records can be
 // merged, never what is computed.
-template <int TILE_W, int TILE_H>
+template <int TILE_W, int TILE_H, int kSortSlots>
 __device__ __forceinline__ void compute_windows(const LevelTable &lt, int L, const TileMap &t,
                                                 int4 *win_out, int *slots_out, int lane) {
     int x0 = 0, y0 = 0, ww = 0, wh = 0;
@@ -170,8 +170,12 @@ struct Binned {
 };
 
 // Pass A for one point: geometry, window slots, per-pixel counts.
+// `vrow0` = value row of pixel 0 of this (image, head): the first thread to count a pixel requests
+// its row into L2, so that the merge loop, several microseconds later, does not wait for HBM.
+template <int PF2>
 __device__ __forceinline__ Binned count_point(const LevelTable &lt, const int4 *win, uint32_t *cnt,
-                                              float x, float y, float aw, int p) {
+                                              float x, float y, float aw, int p, int kSortSlots,
+                                              const float *vrow0, uint32_t pix_stride_bytes) {
     Binned b;
     b.s01 = b.s23 = kSlotNone | (kSlotNone << 16);
     b.pix0 = 0; b.lh = 0.f; b.lw = 0.f; b.aw = aw;
@@ -192,13 +196,19 @@ __device__ __forceinline__ Binned count_point(const LevelTable &lt, const int4 *
         if (gm.cmask & (1 << k)) {
             const bool inwin = (unsigned)(sx + dx) < (unsigned)ww && (unsigned)(sy + dy) < (unsigned)wh;
             sl[k] = kSlotTail;
+            bool first = PF2 >= 2;                   // outside every window: nobody else asks for this row
             if (inwin) {
                 const int slot = wn.w + (sy + dy) * ww + sx + dx;
 #ifdef MSDA_CHECK_BOUNDS
                 assert(slot >= 0 && slot < kSortSlots);
 #endif
-                atomicAdd(&cnt[slot], 1u);
+                first = atomicAdd(&cnt[slot], 1u) == 0u;
                 sl[k] = (uint32_t)slot;
+            }
+            if (PF2 && first) {
+                const char *row = reinterpret_cast<const char *>(vrow0) +
+                                  (size_t)(uint32_t)(b.pix0 + dy * lv.y + dx) * pix_stride_bytes;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
             }
         }
     }
@@ -237,6 +247,11 @@ __device__ __forceinline__ uint2 lds_u2(uint32_t a) {
     asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a) : "memory");
     return r;
 }
+__device__ __forceinline__ uint4 lds_u4s(uint32_t a) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a) : "memory");
+    return r;
+}
 __device__ __forceinline__ uint32_t lds_u1(uint32_t a) {
     uint32_t r;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a) : "memory");
@@ -247,6 +262,38 @@ __device__ __forceinline__ float4 lds_f4(uint32_t a) {
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a) : "memory");
     return r;
 }
+// packed fp32x2 arithmetic (SASS FFMA2 / FMUL2): two IEEE fp32 operations per instruction on a
+// 64-bit register pair {lo, hi}
+__device__ __forceinline__ void ffma2_bcast(uint64_t &acc, uint32_t w_bits, uint64_t g) {   // acc += {w, w} * g
+    asm("{\n\t.reg .b64 rw;\n\tmov.b64 rw, {%1,%1};\n\tfma.rn.f32x2 %0, rw, %2, %0;\n\t}" : "+l"(acc) : "r"(w_bits), "l"(g));
+}
+__device__ __forceinline__ void ffma2_p(uint64_t &acc, uint64_t a, uint64_t b) {            // acc += a * b
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ uint64_t fmul2_p(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float sum2(uint64_t a) {
+    float lo, hi;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
+    return lo + hi;
+}
+__device__ __forceinline__ void lds_2x64(uint32_t a, uint64_t &x, uint64_t &y) {
+    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(x), "=l"(y) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void ldg_2x64(const char *p, uint64_t &x, uint64_t &y) {
+    asm volatile("ld.global.nc.v2.b64 {%0,%1}, [%2];" : "=l"(x), "=l"(y) : "l"(p));
+}
+__device__ __forceinline__ void red_2x64(char *p, uint64_t x, uint64_t y) {
+    asm volatile("{\n\t.reg .f32 a, b, c, d;\n\tmov.b64 {a,b}, %1;\n\tmov.b64 {c,d}, %2;\n\t"
+                 "red.global.add.v4.f32 [%0], {a,b,c,d};\n\t}" ::"l"(p), "l"(x), "l"(y) : "memory");
+}
+template <typename P>
+__device__ __forceinline__ P xor64(P p) {       // the other 64-byte half of a 128-byte aligned row
+    return reinterpret_cast<P>(reinterpret_cast<uintptr_t>(p) ^ (uintptr_t)64);
+}
 __device__ __forceinline__ void sts_f1(uint32_t a, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
 }
@@ -254,16 +301,22 @@ __device__ __forceinline__ void red_add_f4(float4 *p, const float4 v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-template <int LP, int WARPS, int TILE_W, int MIN_CTAS>
+// GW: lanes per record in the merge loop (8: 16 bytes of a row per lane, 4: 32 bytes)
+// PFV: bit 0 = the first thread that counts a window pixel prefetches its value row into L2,
+//      bit 1 = also every corner outside the windows, bit 2 = the merge loop looks one body ahead
+//      and prefetches the rows of the pixel runs that start there into L1
+template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int TILE_Q, int SLOTS, int GW, int PFV>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
 msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restrict__ value,
                        const int64_t *__restrict__ shapes, const int64_t *__restrict__ lstart,
                        const float *__restrict__ loc, const float *__restrict__ attw, const Dims d,
                        const int flags, float *__restrict__ grad_value, float *__restrict__ grad_loc,
                        float *__restrict__ grad_attw) {
-    using Cfg = SortCfg<LP, WARPS, TILE_W>;
+    using Cfg = SortCfg<LP, WARPS, TILE_W, TILE_Q, SLOTS>;
     constexpr int NT = Cfg::kThreads;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int kSortTile = Cfg::kSortTile, kSortSlots = Cfg::kSortSlots;
+    constexpr int PF2 = PFV & 3, LOOK = (PFV >> 2) & 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ LevelTable lt;
     __shared__ int4 win[2][kMaxLevels];
     __shared__ int win_slots[2];
@@ -289,7 +342,7 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
     long long item = blockIdx.x;
     if (warp == 0 && item < items) {
         const TileMap t0 = tile_of<TILE_W, Cfg::kTileH>(lt, L, (int)((item / M) % lt.groups));
-        compute_windows<TILE_W, Cfg::kTileH>(lt, L, t0, win[0], &win_slots[0], lane);
+        compute_windows<TILE_W, Cfg::kTileH, Cfg::kSortSlots>(lt, L, t0, win[0], &win_slots[0], lane);
     }
     __syncthreads();
 
@@ -351,7 +404,9 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
                     const int s = r * NT + tid;
                     const int p = s % LP;
                     bn[r].s01 = bn[r].s23 = kSlotNone | (kSlotNone << 16);
-                    if (live[r]) bn[r] = count_point(lt, wn, cnt, px[r], py[r], pw[r], p);
+                    if (live[r])
+                        bn[r] = count_point<PF2>(lt, wn, cnt, px[r], py[r], pw[r], p, Cfg::kSortSlots,
+                                                 value + (n * (long long)d.S * M + m) * 32, (uint32_t)M * 128u);
                 }
             }
             __syncthreads();                                                // B1: counts complete
@@ -408,77 +463,123 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
         for (int i = tid; i < nslots; i += NT) cnt[i] = 0u;
         if (warp == 0 && item + gridDim.x < items) {
             const TileMap tn = tile_of<TILE_W, Cfg::kTileH>(lt, L, (int)(((item + gridDim.x) / M) % lt.groups));
-            compute_windows<TILE_W, Cfg::kTileH>(lt, L, tn, win[buf ^ 1], &win_slots[buf ^ 1], lane);
+            compute_windows<TILE_W, Cfg::kTileH, Cfg::kSortSlots>(lt, L, tn, win[buf ^ 1], &win_slots[buf ^ 1], lane);
         }
 
-        // ---- merge: equal slices of the record array, one per 8-lane group ----
+        // ---- merge: equal slices of the record array, one per GW-lane group ----
         {
+            // a group = GW lanes sharing a record; a lane owns NCH 16-byte chunks of the 128-byte rows.
+            // GW = 4: chunk c0 = (lane & 3) | 4 * (group parity) and c0 ^ 4, so that the two halves of
+            // the warp's groups read the two halves of the shared-memory banks
+            constexpr int NCH = 8 / GW, kGroups = WARPS * (32 / GW);
+            static_assert((Cfg::kRecs / kGroups) % 8 == 0, "slices are padded to multiples of 8 records");
+            const int gl = lane / GW, cl = lane % GW;                  // group in warp, lane in group
+            const int c0 = (GW == 8) ? cl : (cl | ((gl & 1) << 2));
             const int T = (int)(n_in + tail_ctr);
-            // slice length: a multiple of 8 records (kRecs / kGroups is one, so per * kGroups <= kRecs);
-            // what a slice holds beyond T is filled with absent records by the group itself.
-            // Slice of group `grp` of warp `warp`: grp * WARPS + warp -- the sorted array runs from the
-            // coarsest level (long runs, few value rows) to the finest and the unsorted rest, so every
-            // warp gets one slice of each quarter and the warps finish together.
-            const int per = (((T + Cfg::kGroups - 1) / Cfg::kGroups) + 7) & ~7;
-            const int i0 = (grp * WARPS + warp) * per;
-            for (int i = max(i0, T) + chunk; i < i0 + per; i += 8) rec[i] = make_uint2(0xffffffffu, 0u);
+            // slice length: a multiple of 8 records (per * kGroups <= kRecs); what a slice holds beyond T
+            // is filled with absent records by the group itself.  Slice of group gl of warp `warp`:
+            // gl * WARPS + warp -- the sorted array runs from the coarsest level (long runs, few value
+            // rows) to the finest and the unsorted rest, so every warp gets a slice of every part and
+            // the warps finish together.
+            const int per = (((T + kGroups - 1) / kGroups) + 7) & ~7;
+            const int i0 = (gl * WARPS + warp) * per;
+            for (int i = max(i0, T) + cl; i < i0 + per; i += GW) rec[i] = make_uint2(0xffffffffu, 0u);
             __syncwarp();
-            const long long img = n * (long long)d.S * M * 8 + chunk;
-            const float4 *vb = reinterpret_cast<const float4 *>(value) + img;
-            float4 *gvb = reinterpret_cast<float4 *>(grad_value) + img;
-            const uint32_t m8 = (uint32_t)m * 8u;
-            const bool b2 = chunk & 4, b1 = chunk & 2, b0 = chunk & 1;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), v = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 gp = make_float4(0.f, 0.f, 0.f, 0.f);              // grad_output row of the previous record
-            uint32_t cur = kNoKey;
-            uint32_t ra = smem_u32(rec) + (uint32_t)i0 * 8u;          // this group's next 8 records
-            const uint32_t go_s = smem_u32(go_sm) + (uint32_t)chunk * 16u;
-            const uint32_t d_s = smem_u32(dsm);
-            // The dot product of a record is formed one step AFTER its accumulation: the value row a
-            // run starts with is requested at the run's first record and first needed a step later.
-            for (int it = 0; it < per; it += 8, ra += 64u) {
-                float dp[8];                                          // dp[j]: record it + j - 1
+            // value / grad_value row of pixel 0 for this lane: + key * (M * 128) bytes per pixel; the
+            // lane's second chunk is the same address ^ 64 (rows are 128-byte aligned: host check)
+            const size_t lane_off = ((size_t)(n * (long long)d.S * M + m) * 8 + c0) * 16;
+            const char *v_lane = reinterpret_cast<const char *>(value) + lane_off;
+            char *gv_lane = reinterpret_cast<char *>(grad_value) + lane_off;
+            const uint32_t row_bytes = (uint32_t)M * 128u;
+            uint64_t acc[2 * NCH], v[2 * NCH];                        // channel pairs: packed fp32x2 math
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+            for (int h = 0; h < 2 * NCH; ++h) acc[h] = v[h] = 0ull;
+            uint32_t cur = kNoKey;
+            const uint32_t rec_s = smem_u32(rec) + (uint32_t)i0 * 8u;
+            const uint32_t go_s0 = smem_u32(go_sm) + (uint32_t)c0 * 16u;
+            const uint32_t d_s = smem_u32(dsm);
+            // The groups of a warp start at different bodies of their slices (and wrap around): slice
+            // starts are multiples of 128 bytes apart, so walking them in step would put every group's
+            // record reads on the same banks.  The wrap is just one more change of pixel.
+            const int nb = per / GW;
+            int bi = nb > 0 ? gl % nb : 0;
+            const char *v_row0 = reinterpret_cast<const char *>(value) + (size_t)(n * (long long)d.S * M + m) * 128;
+            for (int b = 0; b < nb; ++b) {
+                const uint32_t ra = rec_s + (uint32_t)bi * (8u * GW);   // this body's GW records
+                if (LOOK) {
+                    // look one body ahead: the value row of every pixel run that STARTS there is requested
+                    // into L1 now, a whole body before the run's first record needs it
+                    const int bn = (bi + 1 == nb) ? 0 : bi + 1;
+                    const uint32_t rn = rec_s + (uint32_t)bn * (8u * GW);
+                    uint32_t kprev = lds_u1(ra + 8u * (GW - 1)) >> 14;
+#pragma unroll
+                    for (int j = 0; j < GW; j += 2) {
+                        const uint4 two = lds_u4s(rn + 8u * j);
+                        const uint32_t k0 = two.x >> 14, k1 = two.z >> 14;
+                        if (cl == 0 && k0 != kprev && k0 != kNoKey)
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(v_row0 + (size_t)k0 * row_bytes));
+                        if (cl == 0 && k1 != k0 && k1 != kNoKey)
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(v_row0 + (size_t)k1 * row_bytes));
+                        kprev = k1;
+                    }
+                }
+                float dp[GW];
+#pragma unroll
+                for (int j = 0; j < GW; ++j) {
                     const uint2 rr = lds_u2(ra + 8u * j);
                     const uint32_t key = rr.x >> 14;
-                    const float4 gq = lds_f4(go_s + (rr.x & 0x3f80u));          // the query's grad_output row
-                    const float wk = __uint_as_float(rr.y);
-                    dp[j] = fmaf(v.w, gp.w, fmaf(v.z, gp.z, fmaf(v.y, gp.y, v.x * gp.x)));
+                    const uint32_t ga = go_s0 + (rr.x & 0x3f80u);              // the query's grad_output row
+                    uint64_t g[2 * NCH];
+                    lds_2x64(ga, g[0], g[1]);
+                    if (NCH == 2) lds_2x64(ga ^ 64u, g[2], g[3]);
                     if (key != cur) {                    // first record of a pixel (or of the padding)
-                        if (cur != kNoKey) red_add_f4(at_off16(gvb, cur * M8 + m8), acc);
-                        if (key != kNoKey) v = ldg_keep_f4(at_off16(vb, key * M8 + m8));
+                        if (cur != kNoKey) {
+                            char *p = gv_lane + (size_t)cur * row_bytes;
+                            red_2x64(p, acc[0], acc[1]);
+                            if (NCH == 2) red_2x64(xor64(p), acc[2], acc[3]);
+                        }
+                        if (key != kNoKey) {
+                            const char *p = v_lane + (size_t)key * row_bytes;
+                            ldg_2x64(p, v[0], v[1]);
+                            if (NCH == 2) ldg_2x64(xor64(p), v[2], v[3]);
+                        }
                         cur = key;
-                        acc.x = wk * gq.x; acc.y = wk * gq.y; acc.z = wk * gq.z; acc.w = wk * gq.w;
-                    } else {
-                        acc.x = fmaf(wk, gq.x, acc.x);
-                        acc.y = fmaf(wk, gq.y, acc.y);
-                        acc.z = fmaf(wk, gq.z, acc.z);
-                        acc.w = fmaf(wk, gq.w, acc.w);
+#pragma unroll
+                        for (int h = 0; h < 2 * NCH; ++h) acc[h] = 0ull;
                     }
-                    gp = gq;
+                    uint64_t d2;
+#pragma unroll
+                    for (int h = 0; h < 2 * NCH; ++h) {
+                        ffma2_bcast(acc[h], rr.y, g[h]);                         // acc += weight * grad_output
+                        if (h == 0) d2 = fmul2_p(v[0], g[0]);
+                        else ffma2_p(d2, v[h], g[h]);                            // <value row, grad_output row>
+                    }
+                    dp[j] = sum2(d2);
                 }
-                // D of record it + j - 1: sum over the group's 8 lanes; lane `chunk` ends up with j = chunk
-                float r1[4], r2[2], r3[1];
-                rs_step<8>(dp, r1, b2, 4);
-                rs_step<4>(r1, r2, b1, 2);
-                rs_step<2>(r2, r3, b0, 1);
-                const int pos = it + chunk - 1;                       // inside the slice
-                if (pos >= 0 && i0 + pos < T) {
-                    const uint32_t xx = lds_u1(ra + 8u * (uint32_t)chunk - 8u);
-                    sts_f1(d_s + 4u * (((xx >> 7) & 127u) * (uint32_t)Cfg::kPC + (xx & 63u)), r3[0]);
+                // D of record j: sum over the group's lanes; lane cl ends up with record j = cl
+                float dsum;
+                if (GW == 8) {
+                    float r1[4], r2[2], r3[1];
+                    rs_step<8>(reinterpret_cast<float (&)[8]>(dp), r1, cl & 4, 4);
+                    rs_step<4>(r1, r2, cl & 2, 2);
+                    rs_step<2>(r2, r3, cl & 1, 1);
+                    dsum = r3[0];
+                } else {
+                    float r1[2], r2[1];
+                    rs_step<4>(reinterpret_cast<float (&)[4]>(dp), r1, cl & 2, 2);
+                    rs_step<2>(r1, r2, cl & 1, 1);
+                    dsum = r2[0];
                 }
+                if (i0 + bi * GW + cl < T) {
+                    const uint32_t xx = lds_u1(ra + 8u * (uint32_t)cl);
+                    sts_f1(d_s + 4u * (((xx >> 7) & 127u) * (uint32_t)Cfg::kPC + (xx & 63u)), dsum);
+                }
+                if (++bi == nb) bi = 0;
             }
-            if (cur != kNoKey) red_add_f4(at_off16(gvb, cur * M8 + m8), acc);
-            if (per > 0) {                                            // the slice's last record
-                float dl = fmaf(v.w, gp.w, fmaf(v.z, gp.z, fmaf(v.y, gp.y, v.x * gp.x)));
-                dl += __shfl_xor_sync(kFullMask, dl, 4);
-                dl += __shfl_xor_sync(kFullMask, dl, 2);
-                dl += __shfl_xor_sync(kFullMask, dl, 1);
-                if (chunk == 0 && i0 + per - 1 < T) {
-                    const uint32_t xx = lds_u1(ra - 8u);
-                    sts_f1(d_s + 4u * (((xx >> 7) & 127u) * (uint32_t)Cfg::kPC + (xx & 63u)), dl);
-                }
+            if (cur != kNoKey) {
+                char *p = gv_lane + (size_t)cur * row_bytes;
+                red_2x64(p, acc[0], acc[1]);
+                if (NCH == 2) red_2x64(xor64(p), acc[2], acc[3]);
             }
         }
 
@@ -539,12 +640,12 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
-template <int LP, int WARPS, int TILE_W, int MIN_CTAS>
+template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int TILE_Q, int SLOTS, int GW, int PFV>
 static cudaError_t launch_bwd_sorted_cfg(const float *grad_out, const float *value, const int64_t *shapes,
                                          const int64_t *lstart, const float *loc, const float *attw,
                                          const Dims &d, float *gv, float *gl, float *gw, cudaStream_t stream) {
-    using Cfg = SortCfg<LP, WARPS, TILE_W>;
-    auto kern = msda_bwd_sorted_kernel<LP, WARPS, TILE_W, MIN_CTAS>;
+    using Cfg = SortCfg<LP, WARPS, TILE_W, TILE_Q, SLOTS>;
+    auto kern = msda_bwd_sorted_kernel<LP, WARPS, TILE_W, MIN_CTAS, TILE_Q, SLOTS, GW, PFV>;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -579,18 +680,30 @@ cudaError_t launch_bwd_sorted(const float *grad_out, const float *value, const i
                               float *gv, float *gl, float *gw, cudaStream_t stream, bool *handled) {
     *handled = true;
     const int LP = d.L * d.P;
-    if (d.D != 32 || d.Lq != d.S || (long long)d.S >= (long long)kNoKey ||
+    // rows of value / grad_value must be 128-byte aligned (the merge loop addresses the two halves
+    // of a row as p and p ^ 64); torch allocations are, odd views take the other kernel
+    const bool rows_aligned = ((reinterpret_cast<uintptr_t>(value) | reinterpret_cast<uintptr_t>(gv)) & 127u) == 0;
+    if (d.D != 32 || d.Lq != d.S || (long long)d.S >= (long long)kNoKey || !rows_aligned ||
         (long long)d.S * d.M * 8 >= 0x7fffffffLL) {
         *handled = false;
         return cudaSuccess;
     }
-#define MSDA_SORTED(LPV, C) \
-    launch_bwd_sorted_cfg<LPV, 16, 16, C>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, stream)
+    // (warps, tile width, min CTAs per SM, queries per tile, window slots, lanes per record, L2 prefetch)
+#define MSDA_SORTED(LPV, W, TW, C, TQ, SL, GWV, PFV) \
+    launch_bwd_sorted_cfg<LPV, W, TW, C, TQ, SL, GWV, PFV>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, stream)
+    const int variant = option_value(OPT_BWD_VARIANT);
     switch (LP) {
-        case 4: return MSDA_SORTED(4, 2);
-        case 8: return MSDA_SORTED(8, 2);
-        case 12: return MSDA_SORTED(12, 2);
-        case 16: return MSDA_SORTED(16, 1);
+        case 4: return MSDA_SORTED(4, 16, 16, 2, 128, 4096, 8, 0);
+        case 8: return MSDA_SORTED(8, 16, 16, 2, 128, 4096, 8, 0);
+        case 12:
+            switch (variant) {
+                case 21: return MSDA_SORTED(12, 16, 16, 2, 128, 4096, 4, 0);   // 4 lanes per record
+                case 22: return MSDA_SORTED(12, 16, 16, 2, 128, 4096, 8, 4);   // 8 lanes + look-ahead L1 prefetch
+                case 23: return MSDA_SORTED(12, 16, 16, 2, 128, 4096, 4, 4);   // 4 lanes + look-ahead L1 prefetch
+                case 24: return MSDA_SORTED(12, 12, 16, 2, 128, 4096, 4, 4);   // 12 warps, 80 registers, look-ahead
+                default: return MSDA_SORTED(12, 16, 16, 2, 128, 4096, 8, 0);
+            }
+        case 16: return MSDA_SORTED(16, 16, 16, 1, 128, 4096, 8, 0);
         default: *handled = false; return cudaSuccess;
     }
 #undef MSDA_SORTED
