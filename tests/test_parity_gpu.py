@@ -382,11 +382,35 @@ def test_non_default_stream_and_cuda_graph(pkg):
 
 
 def test_launches_are_counted(pkg):
-    inp = pkg.synthetic.make_inputs([(4, 6), (8, 12)], 1, heads=2, points=2, mode="uniform")
+    inp = pkg.synthetic.make_inputs([(4, 6), (8, 12)], 1, heads=2, points=2, num_query=50, mode="uniform")
     d = to_dev(inp)
     n0 = pkg.launch_count()
     run_fwd_bwd(pkg, d)
-    assert pkg.launch_count() - n0 == 2
+    assert pkg.launch_count() - n0 == 2           # decoder-style Lq != S: forward + per-row backward
+    # encoder self-attention (Lq == S): the backward is a one-CTA probe of the locations plus the
+    # merging and the per-row kernel behind its verdict (the one not chosen returns at once)
+    d = to_dev(pkg.synthetic.make_inputs([(4, 6), (8, 12)], 1, heads=2, points=2, mode="uniform"))
+    n0 = pkg.launch_count()
+    run_fwd_bwd(pkg, d)
+    assert pkg.launch_count() - n0 == 4
+
+
+@pytest.mark.parametrize("mode,bwd_variant", [("model", 2), ("model", 20), ("uniform", 2), ("uniform", 20)])
+def test_probe_gated_default_equals_either_backward_kernel(pkg, oracle, mode, bwd_variant):
+    """Whatever the probe decides, the default backward agrees with both kernels forced."""
+    inp = pkg.synthetic.make_inputs([(16, 32), (32, 64), (64, 128)], 1, mode=mode, seed=5)
+    d = to_dev(inp)
+    a = (d["value"], d["spatial_shapes"], d["level_start_index"], d["sampling_locations"], d["attention_weights"])
+    auto = pkg.ms_deform_attn_backward(*a, d["grad_output"], 128)
+    try:
+        pkg.set_option("bwd_variant", bwd_variant)
+        forced = pkg.ms_deform_attn_backward(*a, d["grad_output"], 128)
+    finally:
+        pkg.set_option("bwd_variant", 0)
+    for x, y in zip(auto, forced):
+        assert rel_err(x.cpu().numpy(), y.cpu().numpy()) <= 1e-5
+    refs = oracle_refs(oracle, inp)
+    assert rel_err(auto[0].cpu().numpy(), np.reshape(refs[1], auto[0].shape)) <= GRAD_REL_TOL
 
 
 def test_non_finite_and_far_away_locations_are_skipped(pkg, oracle):

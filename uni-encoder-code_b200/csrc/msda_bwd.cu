@@ -63,7 +63,8 @@ msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict_
                     const float *__restrict__ loc, const float *__restrict__ attw,
                     const Producers pr, const Dims d, const int flags,
                     float *__restrict__ grad_value, float *__restrict__ grad_loc,
-                    float *__restrict__ grad_attw) {
+                    float *__restrict__ grad_attw, const int *__restrict__ gate) {
+    if (gate && *gate != 0) return;      // the probe chose the merging kernel (msda_bwd_sorted.cu)
     using Cfg = BwdCfg<LP, WARPS, TILE_W, QPW>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ LevelTable lt;
@@ -247,7 +248,7 @@ static cudaError_t launch_bwd_cfg(const float *grad_out, const float *value, con
                                   const int64_t *lstart, const float *loc, const float *attw,
                                   const Dims &d, float *grad_value, float *grad_loc,
                                   float *grad_attw, cudaStream_t stream,
-                                  Producers pr = Producers{nullptr, 0}) {
+                                  Producers pr = Producers{nullptr, 0}, const int *gate = nullptr) {
     using Cfg = BwdCfg<LP, WARPS, TILE_W, QPW>;
     auto kern = msda_bwd_d32_kernel<LP, WARPS, TILE_W, MIN_CTAS, BATCH, QPW, FUSED>;
     // the opt-in shared-memory size is a per-device function attribute: set it (and query the
@@ -275,7 +276,7 @@ static cudaError_t launch_bwd_cfg(const float *grad_out, const float *value, con
     const int flags = (option_value(OPT_TILE_ORDER) != 1 ? 1 : 0) | (option_value(OPT_WHATIF_DROP_REDS) << 1);
     kern<<<(unsigned)blocks, WARPS * 32, Cfg::kSmem, stream>>>(grad_out, value, shapes, lstart, loc,
                                                               attw, pr, d, flags, grad_value,
-                                                              grad_loc, grad_attw);
+                                                              grad_loc, grad_attw, gate);
     note_launch();
     return cudaGetLastError();
 }
@@ -283,11 +284,13 @@ static cudaError_t launch_bwd_cfg(const float *grad_out, const float *value, con
 template <int LP>
 static cudaError_t launch_bwd_lp(const float *grad_out, const float *value, const int64_t *shapes,
                                  const int64_t *lstart, const float *loc, const float *attw,
-                                 const Dims &d, float *gv, float *gl, float *gw, cudaStream_t st) {
+                                 const Dims &d, float *gv, float *gl, float *gw, cudaStream_t st,
+                                 const int *gate) {
     // variant = (warps, query tile width, min CTAs per SM -> register budget, load batch in pairs,
     //            queries per warp)
 #define MSDA_BWD(W, TW, C, B, Q) \
-    launch_bwd_cfg<LP, W, TW, C, B, Q>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, st)
+    launch_bwd_cfg<LP, W, TW, C, B, Q>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, st, \
+                                       Producers{nullptr, 0}, gate)
     switch (option_value(OPT_BWD_VARIANT)) {
         case 1: return MSDA_BWD(8, 8, 4, 1, 8);     //  8 warps, tile  8x8
         case 3: return MSDA_BWD(32, 16, 1, 1, 8);   // 32 warps, tile 16x16, one CTA per SM
@@ -304,7 +307,8 @@ static cudaError_t launch_bwd_lp(const float *grad_out, const float *value, cons
 
 cudaError_t launch_bwd_d32(const float *grad_out, const float *value, const int64_t *shapes,
                            const int64_t *lstart, const float *loc, const float *attw, const Dims &d,
-                           float *gv, float *gl, float *gw, cudaStream_t stream, bool *handled) {
+                           float *gv, float *gl, float *gw, cudaStream_t stream, bool *handled,
+                           const int *gate) {
     *handled = true;
     const int LP = d.L * d.P;
     if (d.D != 32 || (long long)d.S * d.M * 8 >= 0x7fffffffLL) {
@@ -312,10 +316,10 @@ cudaError_t launch_bwd_d32(const float *grad_out, const float *value, const int6
         return cudaSuccess;
     }
     switch (LP) {
-        case 4: return launch_bwd_lp<4>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, stream);
-        case 8: return launch_bwd_lp<8>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, stream);
-        case 12: return launch_bwd_lp<12>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, stream);
-        case 16: return launch_bwd_lp<16>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, stream);
+        case 4: return launch_bwd_lp<4>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, stream, gate);
+        case 8: return launch_bwd_lp<8>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, stream, gate);
+        case 12: return launch_bwd_lp<12>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, stream, gate);
+        case 16: return launch_bwd_lp<16>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, stream, gate);
         default: *handled = false; return cudaSuccess;
     }
 }

@@ -275,6 +275,11 @@ __device__ __forceinline__ uint64_t fmul2_p(uint64_t a, uint64_t b) {
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+__device__ __forceinline__ uint64_t fadd2_p(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 __device__ __forceinline__ float sum2(uint64_t a) {
     float lo, hi;
     asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
@@ -311,7 +316,8 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
                        const int64_t *__restrict__ shapes, const int64_t *__restrict__ lstart,
                        const float *__restrict__ loc, const float *__restrict__ attw, const Dims d,
                        const int flags, float *__restrict__ grad_value, float *__restrict__ grad_loc,
-                       float *__restrict__ grad_attw) {
+                       float *__restrict__ grad_attw, const int *__restrict__ gate) {
+    if (gate && *gate != 1) return;      // the probe chose the per-row reduction kernel for these inputs
     using Cfg = SortCfg<LP, WARPS, TILE_W, TILE_Q, SLOTS>;
     constexpr int NT = Cfg::kThreads;
     constexpr int kSortTile = Cfg::kSortTile, kSortSlots = Cfg::kSortSlots;
@@ -329,7 +335,6 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
     uint32_t *cnt = reinterpret_cast<uint32_t *>(smem_raw + Cfg::kRecBytes + Cfg::kGoBytes + Cfg::kDBytes);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int grp = lane >> 3, chunk = lane & 7;
 
     fill_level_table(lt, shapes, lstart, d.L, d.P, d.S, d.Lq, kSortTile, Cfg::kTileH, TILE_W, flags & 1);
     for (int i = tid; i < kSortSlots; i += NT) cnt[i] = 0u;   // invariant: zero outside pass A .. pass B
@@ -337,7 +342,6 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
 
     const int M = d.M, L = d.L, Lq = d.Lq;
     const long long items = (long long)d.N * M * lt.groups;
-    const uint32_t M8 = (uint32_t)M * 8u;
 
     long long item = blockIdx.x;
     if (warp == 0 && item < items) {
@@ -547,13 +551,19 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
 #pragma unroll
                         for (int h = 0; h < 2 * NCH; ++h) acc[h] = 0ull;
                     }
-                    uint64_t d2;
+                    // <value row, grad_output row>: one packed dot product per 16-byte chunk, added at the
+                    // end -- the sum does not depend on which chunk a lane happened to load first, so
+                    // grad_sampling_loc / grad_attn_weight stay bit-reproducible from run to run
+                    uint64_t d2 = 0ull, d2b = 0ull;
 #pragma unroll
-                    for (int h = 0; h < 2 * NCH; ++h) {
-                        ffma2_bcast(acc[h], rr.y, g[h]);                         // acc += weight * grad_output
-                        if (h == 0) d2 = fmul2_p(v[0], g[0]);
-                        else ffma2_p(d2, v[h], g[h]);                            // <value row, grad_output row>
+                    for (int h = 0; h < NCH; ++h) {
+                        ffma2_bcast(acc[2 * h], rr.y, g[2 * h]);                 // acc += weight * grad_output
+                        ffma2_bcast(acc[2 * h + 1], rr.y, g[2 * h + 1]);
+                        uint64_t t = fmul2_p(v[2 * h], g[2 * h]);
+                        ffma2_p(t, v[2 * h + 1], g[2 * h + 1]);
+                        if (h == 0) d2 = t; else d2b = t;
                     }
+                    if (NCH == 2) d2 = fadd2_p(d2, d2b);
                     dp[j] = sum2(d2);
                 }
                 // D of record j: sum over the group's lanes; lane cl ends up with record j = cl
@@ -643,7 +653,8 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
 template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int TILE_Q, int SLOTS, int GW, int PFV>
 static cudaError_t launch_bwd_sorted_cfg(const float *grad_out, const float *value, const int64_t *shapes,
                                          const int64_t *lstart, const float *loc, const float *attw,
-                                         const Dims &d, float *gv, float *gl, float *gw, cudaStream_t stream) {
+                                         const Dims &d, float *gv, float *gl, float *gw, cudaStream_t stream,
+                                         const int *gate) {
     using Cfg = SortCfg<LP, WARPS, TILE_W, TILE_Q, SLOTS>;
     auto kern = msda_bwd_sorted_kernel<LP, WARPS, TILE_W, MIN_CTAS, TILE_Q, SLOTS, GW, PFV>;
     int dev = 0;
@@ -669,39 +680,136 @@ static cudaError_t launch_bwd_sorted_cfg(const float *grad_out, const float *val
     if (blocks < 1) blocks = 1;
     const int flags = option_value(OPT_TILE_ORDER) != 1 ? 1 : 0;
     kern<<<(unsigned)blocks, WARPS * 32, Cfg::kSmem, stream>>>(grad_out, value, shapes, lstart, loc, attw, d,
-                                                              flags, gv, gl, gw);
+                                                              flags, gv, gl, gw, gate);
     note_launch();
     return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Which backward kernel?  Merging pays when the sampling points stay near their query (the encoder:
+// offsets of a few pixels, ms_deform_attn.py:71-77); with locations spread over the whole image
+// nearly every record is a run of one and the per-row reduction kernel of msda_bwd.cu is faster.
+// The host cannot look at the locations (no device read-back, CUDA-graph capturable), so a
+// one-CTA probe samples 4096 points, measures the fraction that lands within the merge windows'
+// margin of its query and leaves the verdict in a device word that both kernels are launched with:
+// the one not chosen returns at once.
+// ---------------------------------------------------------------------------
+constexpr int kGateSlots = 1024;
+__device__ int g_bwd_gate[kGateSlots];
+
+__global__ void __launch_bounds__(1024, 1)
+msda_bwd_probe_kernel(const int64_t *__restrict__ shapes, const int64_t *__restrict__ lstart,
+                      const float *__restrict__ loc, const Dims d, int *__restrict__ gate) {
+    __shared__ LevelTable lt;
+    __shared__ int tot_in[32], tot_all[32];
+    fill_level_table(lt, shapes, lstart, d.L, d.P, d.S, d.Lq, kSortTileMax, 8, 16, 1);
+    __syncthreads();
+    const int LP = d.L * d.P;
+    int n_in = 0, n_all = 0;
+    if (lt.spatial) {
+        uint32_t h = threadIdx.x * 2654435761u + 12345u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            h = h * 1664525u + 1013904223u;                 // LCG: which (image, query, head, point)
+            const int n = (int)((h >> 8) % (uint32_t)d.N);
+            h = h * 1664525u + 1013904223u;
+            const int q = (int)((h >> 4) % (uint32_t)d.Lq);
+            h = h * 1664525u + 1013904223u;
+            const int m = (int)((h >> 8) % (uint32_t)d.M), sp = (int)((h >> 16) % (uint32_t)LP);
+            int lq = 0;
+            while (lq + 1 < d.L && q >= lt.start[lq + 1]) ++lq;
+            const int qy = (q - lt.start[lq]) / lt.W[lq], qx = (q - lt.start[lq]) - qy * lt.W[lq];
+            const int l = sp / d.P;
+            const float2 xy = reinterpret_cast<const float2 *>(loc)[(((long long)n * d.Lq + q) * d.M + m) * LP + sp];
+            const float W = (float)lt.W[l], H = (float)lt.H[l];
+            const float x = xy.x * W - 0.5f, y = xy.y * H - 0.5f;
+            if (x > -1.f && y > -1.f && x < W && y < H) {   // the op's own range test (cuh:293)
+                const float rx = ((float)qx + 0.5f) * (W / (float)lt.W[lq]) - 0.5f;
+                const float ry = ((float)qy + 0.5f) * (H / (float)lt.H[lq]) - 0.5f;
+                ++n_all;
+                if (fabsf(x - rx) <= (float)kSortMargin - 1.f && fabsf(y - ry) <= (float)kSortMargin - 1.f) ++n_in;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_in += __shfl_xor_sync(kFullMask, n_in, o);
+        n_all += __shfl_xor_sync(kFullMask, n_all, o);
+    }
+    if ((threadIdx.x & 31) == 0) { tot_in[threadIdx.x >> 5] = n_in; tot_all[threadIdx.x >> 5] = n_all; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int a = 0, b = 0;
+        for (int w = 0; w < 32; ++w) { a += tot_in[w]; b += tot_all[w]; }
+        *gate = (b > 0 && 4 * a >= 3 * b) ? 1 : 0;          // >= 75 % near their query: merge
+    }
+}
+
+// device word for this backward call (a ring: calls in flight never share a word in practice)
+static cudaError_t next_gate(int **gate) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    static std::atomic<int *> base_of[kMaxDevices];
+    static std::atomic<unsigned> counter{0};
+    int *base = base_of[dev].load(std::memory_order_acquire);
+    if (!base) {
+        void *p = nullptr;
+        e = cudaGetSymbolAddress(&p, g_bwd_gate);
+        if (e != cudaSuccess) return e;
+        base = static_cast<int *>(p);
+        base_of[dev].store(base, std::memory_order_release);
+    }
+    *gate = base + counter.fetch_add(1, std::memory_order_relaxed) % kGateSlots;
+    return cudaSuccess;
+}
+
+cudaError_t launch_bwd_probe(const int64_t *shapes, const int64_t *lstart, const float *loc, const Dims &d,
+                             cudaStream_t stream, int **gate) {
+    cudaError_t e = next_gate(gate);
+    if (e != cudaSuccess) return e;
+    msda_bwd_probe_kernel<<<1, 1024, 0, stream>>>(shapes, lstart, loc, d, *gate);
+    note_launch();
+    return cudaGetLastError();
+}
+
+// whether launch_bwd_sorted() covers this problem (shape + alignment)
+bool bwd_sorted_applies(const float *value, const float *gv, const Dims &d) {
+    const int LP = d.L * d.P;
+    // rows of value / grad_value must be 128-byte aligned (the merge loop addresses the two halves
+    // of a row as p and p ^ 64); torch allocations are, odd views take the other kernel
+    const bool rows_aligned = ((reinterpret_cast<uintptr_t>(value) | reinterpret_cast<uintptr_t>(gv)) & 127u) == 0;
+    return d.D == 32 && d.Lq == d.S && (long long)d.S < (long long)kNoKey && rows_aligned &&
+           (long long)d.S * d.M * 8 < 0x7fffffffLL && (LP == 4 || LP == 8 || LP == 12 || LP == 16);
 }
 
 // `handled` = false: shape outside this kernel's domain (the caller falls back to msda_bwd.cu)
 cudaError_t launch_bwd_sorted(const float *grad_out, const float *value, const int64_t *shapes,
                               const int64_t *lstart, const float *loc, const float *attw, const Dims &d,
-                              float *gv, float *gl, float *gw, cudaStream_t stream, bool *handled) {
+                              float *gv, float *gl, float *gw, cudaStream_t stream, bool *handled,
+                              const int *gate) {
     *handled = true;
     const int LP = d.L * d.P;
-    // rows of value / grad_value must be 128-byte aligned (the merge loop addresses the two halves
-    // of a row as p and p ^ 64); torch allocations are, odd views take the other kernel
-    const bool rows_aligned = ((reinterpret_cast<uintptr_t>(value) | reinterpret_cast<uintptr_t>(gv)) & 127u) == 0;
-    if (d.D != 32 || d.Lq != d.S || (long long)d.S >= (long long)kNoKey || !rows_aligned ||
-        (long long)d.S * d.M * 8 >= 0x7fffffffLL) {
+    if (!bwd_sorted_applies(value, gv, d)) {
         *handled = false;
         return cudaSuccess;
     }
     // (warps, tile width, min CTAs per SM, queries per tile, window slots, lanes per record, L2 prefetch)
 #define MSDA_SORTED(LPV, W, TW, C, TQ, SL, GWV, PFV) \
-    launch_bwd_sorted_cfg<LPV, W, TW, C, TQ, SL, GWV, PFV>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, stream)
+    launch_bwd_sorted_cfg<LPV, W, TW, C, TQ, SL, GWV, PFV>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, stream, gate)
     const int variant = option_value(OPT_BWD_VARIANT);
     switch (LP) {
         case 4: return MSDA_SORTED(4, 16, 16, 2, 128, 4096, 8, 0);
         case 8: return MSDA_SORTED(8, 16, 16, 2, 128, 4096, 8, 0);
         case 12:
             switch (variant) {
-                case 21: return MSDA_SORTED(12, 16, 16, 2, 128, 4096, 4, 0);   // 4 lanes per record
+                case 21: return MSDA_SORTED(12, 16, 16, 2, 128, 4096, 8, 0);   // 8 lanes per record
                 case 22: return MSDA_SORTED(12, 16, 16, 2, 128, 4096, 8, 4);   // 8 lanes + look-ahead L1 prefetch
                 case 23: return MSDA_SORTED(12, 16, 16, 2, 128, 4096, 4, 4);   // 4 lanes + look-ahead L1 prefetch
-                case 24: return MSDA_SORTED(12, 12, 16, 2, 128, 4096, 4, 4);   // 12 warps, 80 registers, look-ahead
-                default: return MSDA_SORTED(12, 16, 16, 2, 128, 4096, 8, 0);
+                case 24: return MSDA_SORTED(12, 12, 16, 2, 128, 4096, 4, 0);   // 12 warps, 80 registers
+                case 25: return MSDA_SORTED(12, 8, 8, 4, 64, 2048, 4, 0);      // 64-query tiles, 4 CTAs of 8 warps
+                default: return MSDA_SORTED(12, 16, 16, 2, 128, 4096, 4, 0);   // 4 lanes per record (32 bytes each)
             }
         case 16: return MSDA_SORTED(16, 16, 16, 1, 128, 4096, 8, 0);
         default: *handled = false; return cudaSuccess;
