@@ -1,18 +1,30 @@
-"""Import pieces of the reference (build container only) without running its package __init__
-files, which need detectron2.  Test infrastructure; returns None-equivalents when /root/reference
-is absent (the GPU box)."""
+"""Import pieces of the reference without running its package __init__ files, which need
+detectron2.  Test infrastructure.
+
+Where the files come from: /root/reference in the build container; on the GPU box, which has no
+checkout, the byte-identical copies that baseline/stage_reference_py.py (run by build()) staged
+under git-ignored baseline/_ref/py/ and that travel with the gpurun snapshot."""
 import importlib
 import os
 import sys
 import types
 
 REF = "/root/reference"
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_STAGED = os.path.join(os.path.dirname(_HERE), "baseline", "_ref", "py", "modeling")
 REF_MODELING = os.path.join(REF, "model", "modeling")
-STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_stubs")
+if not os.path.isdir(REF_MODELING):
+    REF_MODELING = _STAGED
+STUBS = os.path.join(_HERE, "ref_stubs")
 
 
 def available():
-    return os.path.isdir(REF_MODELING)
+    return os.path.isfile(os.path.join(REF_MODELING, "pixel_decoder", "msdeformattn.py"))
+
+
+def source():
+    """'checkout' (build container) or 'staged' (copies shipped to the GPU box)."""
+    return "staged" if REF_MODELING == _STAGED else "checkout"
 
 
 def _pkg(name, path):

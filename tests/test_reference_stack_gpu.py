@@ -1,0 +1,177 @@
+"""The reference's OWN Python stack -- MSDeformAttnFunction (func.py:35-52), MSDeformAttn
+(ops/modules/ms_deform_attn.py:85-126), the encoder and MSDeformAttnPixelDecoder
+(msdeformattn.py:26-386) -- imported UNMODIFIED and run on the drop-in
+``MultiScaleDeformableAttention`` module on a B200.  This is the drop-in claim of BASELINE.json's
+north_star ("model/modeling/pixel_decoder ... run unchanged") executed on hardware.
+
+The reference files come from /root/reference where it exists and otherwise from the byte-identical
+copies staged by baseline/stage_reference_py.py under git-ignored baseline/_ref/py/ (they travel to
+the GPU box with the gpurun snapshot; tests/ref_stubs/ stands in for detectron2 / fvcore, which are
+third-party dependencies, not reference code).
+"""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GRAD_REL_TOL, load_golden, rel_err
+import ref_import
+from test_parity_gpu import check_against, oracle_refs, to_dev
+from test_pixel_decoder import PD_KW, PD_SHAPES, check
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not ref_import.available(), reason="reference files neither checked out nor staged")]
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ref(pkg):
+    pkg.install_dropin()            # before func.py's `import MultiScaleDeformableAttention` (func.py:21-30)
+    ns = ref_import.load()
+    func = importlib.import_module("refmodeling.pixel_decoder.ops.functions.ms_deform_attn_func")
+    import MultiScaleDeformableAttention as shim
+    assert func.MSDA is shim and shim.ms_deform_attn_forward is pkg.ms_deform_attn_forward
+    ns.func = func
+    return ns
+
+
+def test_reference_autograd_function_on_the_shim(pkg, oracle, ref):
+    inp = pkg.synthetic.make_inputs([(6, 10), (12, 20), (24, 40)], 2, mode="model", seed=11)
+    d = to_dev(inp)
+    v = d["value"].clone().requires_grad_(True)
+    loc = d["sampling_locations"].clone().requires_grad_(True)
+    w = d["attention_weights"].clone().requires_grad_(True)
+    n0 = pkg.launch_count()
+    out = ref.func.MSDeformAttnFunction.apply(v, d["spatial_shapes"], d["level_start_index"], loc, w, 128)
+    out.backward(d["grad_output"])
+    assert pkg.launch_count() - n0 == 4        # our kernels ran: forward + (probe, two gated backward kernels)
+    check_against(out.detach(), v.grad, loc.grad, w.grad, *oracle_refs(oracle, inp), tag="reference function")
+    # the reference's CPU formulation of the same function (func.py:55-75) agrees with it on the GPU
+    core = ref.ms_deform_attn_core_pytorch(d["value"].double(), d["spatial_shapes"], d["sampling_locations"].double(),
+                                           d["attention_weights"].double())
+    assert (core - out.detach().double()).abs().max().item() <= 1e-5
+
+
+def test_reference_msdeformattn_module_on_the_shim(pkg, ref):
+    """ops/modules/ms_deform_attn.py:85-126 unchanged: same weights in the reference module (CUDA op =
+    the shim) and in the reference module forced onto its own CPU formulation."""
+    levels = [(6, 10), (12, 20), (24, 40)]
+    torch.manual_seed(3)
+    attn = ref.MSDeformAttn(256, 3, 8, 4).to(DEV)
+    with torch.no_grad():
+        attn.sampling_offsets.weight.normal_(std=0.02)
+        attn.attention_weights.weight.normal_(std=0.05)
+    S = sum(h * w for h, w in levels)
+    q = torch.randn(2, S, 256, device=DEV)
+    shapes, lsi = pkg.synthetic.level_tensors(levels, DEV)
+    ref_pts = pkg.modules.reference_points_for(levels, DEV).expand(2, -1, -1, -1)
+    n0 = pkg.launch_count()
+    y = attn(q, ref_pts, q, shapes, lsi)
+    assert pkg.launch_count() - n0 == 1 and y.shape == (2, S, 256)
+    # same module, core op swapped for the reference's grid_sample formulation
+    mod = importlib.import_module("refmodeling.pixel_decoder.ops.modules.ms_deform_attn")
+    real = mod.MSDeformAttnFunction
+
+    class _Core:
+        @staticmethod
+        def apply(value, shapes_, lsi_, loc, w, step):
+            return ref.ms_deform_attn_core_pytorch(value, shapes_, loc, w)
+    mod.MSDeformAttnFunction = _Core
+    try:
+        y_ref = attn.double()(q.double(), ref_pts.double(), q.double(), shapes, lsi)
+    finally:
+        mod.MSDeformAttnFunction = real
+        attn.float()
+    assert (y.double() - y_ref).abs().max().item() <= 2e-5
+
+
+def test_reference_encoder_on_the_shim_matches_its_golden(pkg, ref):
+    """msdeformattn.py:26-175 in fp64 (the op's fp64 kernels) against tests/golden/encoder_small.npz,
+    produced by the same class on the CPU path."""
+    g = load_golden("encoder_small")
+    enc = ref.MSDeformAttnTransformerEncoderOnly(d_model=64, nhead=2, num_encoder_layers=2, dim_feedforward=128,
+                                                 dropout=0.0, num_feature_levels=3, enc_n_points=4).double()
+    enc.load_state_dict({k[len("state::"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("state::")})
+    enc = enc.to(DEV).eval()
+    srcs = [torch.from_numpy(g[f"src{i}"]).to(DEV) for i in range(3)]
+    srcs[2].requires_grad_(True)
+    pos = [torch.from_numpy(g[f"pos{i}"]).to(DEV) for i in range(3)]
+    n0 = pkg.launch_count()
+    memory, shapes, lsi, _ = enc(srcs, pos)
+    assert pkg.launch_count() - n0 == 2                      # one op call per encoder layer
+    assert shapes.tolist() == g["spatial_shapes"].tolist() and lsi.tolist() == g["level_start_index"].tolist()
+    assert np.abs(memory.detach().cpu().numpy() - g["memory"]).max() <= 1e-9
+    (memory * torch.from_numpy(g["cotangent"]).to(DEV)).sum().backward()
+    assert rel_err(srcs[2].grad.cpu().numpy(), g["grad_src2"]) <= 1e-8
+
+
+def test_reference_pixel_decoder_forward_features_on_the_shim_matches_its_golden(pkg, ref):
+    """MSDeformAttnPixelDecoder.forward_features (msdeformattn.py:336-386) unchanged, CUDA op = the shim,
+    against tests/golden/pixel_decoder_small.npz (the same class on the reference's CPU path)."""
+    g = load_golden("pixel_decoder_small")
+    shapes = {k: ref.ShapeSpec(channels=c, stride=s) for k, (c, s) in PD_SHAPES.items()}
+    dec = ref.MSDeformAttnPixelDecoder(shapes, **PD_KW)
+    dec.load_state_dict({k[len("state::"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("state::")})
+    dec = dec.to(DEV).eval()
+    feats = {k[len("feat::"):]: torch.from_numpy(v).to(DEV) for k, v in g.items() if k.startswith("feat::")}
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False      # the golden is true fp32
+    try:
+        n0 = pkg.launch_count()
+        with torch.no_grad():
+            outs = dec.forward_features(feats)
+        assert pkg.launch_count() - n0 == PD_KW["transformer_enc_layers"]
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    check(outs, g, 5e-4)
+    # and the repo's mirror of the class gives the same tensors as the reference class, both on the GPU
+    mine = pkg.pixel_decoder.MSDeformAttnPixelDecoder(PD_SHAPES, **PD_KW)
+    mine.load_state_dict(dec.state_dict())
+    mine = mine.to(DEV).eval()
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            mo = mine.forward_features(feats)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    assert (mo[0] - outs[0]).abs().max().item() <= 1e-4 and (mo[1] - outs[1]).abs().max().item() <= 1e-4
+
+
+def test_reference_encoder_training_step_on_the_shim(pkg, ref):
+    """fp32 forward + backward through the reference encoder with the shim's autograd path
+    (func.py:44-52 -> ms_deform_attn_backward): gradients reach every parameter and agree with the
+    same model evaluated through the reference's CPU formulation."""
+    levels = [(8, 12), (16, 24), (32, 48)]
+    torch.manual_seed(5)
+    enc = ref.MSDeformAttnTransformerEncoderOnly(d_model=64, nhead=2, num_encoder_layers=1, dim_feedforward=128,
+                                                 dropout=0.0, num_feature_levels=3, enc_n_points=4).to(DEV)
+    with torch.no_grad():
+        for layer in enc.encoder.layers:
+            layer.self_attn.sampling_offsets.weight.normal_(std=0.05)
+            layer.self_attn.attention_weights.weight.normal_(std=0.1)
+    srcs = [torch.randn(2, 64, h, w, device=DEV) for h, w in levels]
+    pos = [torch.randn(2, 64, h, w, device=DEV) * 0.1 for h, w in levels]
+    memory = enc(srcs, pos)[0]
+    loss = memory.square().mean()
+    loss.backward()
+    grads = {k: p.grad.clone() for k, p in enc.named_parameters()}
+    assert all(torch.isfinite(gr).all() for gr in grads.values())
+    mod = importlib.import_module("refmodeling.pixel_decoder.ops.modules.ms_deform_attn")
+    real = mod.MSDeformAttnFunction
+
+    class _Core:
+        @staticmethod
+        def apply(value, shapes_, lsi_, loc, w, step):
+            return ref.ms_deform_attn_core_pytorch(value, shapes_, loc, w)
+    enc.zero_grad()
+    mod.MSDeformAttnFunction = _Core
+    try:
+        enc.double()
+        m2 = enc([s.double() for s in srcs], [p.double() for p in pos])[0]
+        m2.square().mean().backward()
+    finally:
+        mod.MSDeformAttnFunction = real
+    assert (m2.float() - memory).abs().max().item() <= 5e-5
+    for k, p in enc.named_parameters():
+        assert rel_err(grads[k].cpu().numpy(), p.grad.cpu().numpy()) <= 2e-3, k

@@ -38,23 +38,42 @@ def shard_batch(tensors: Dict[str, torch.Tensor], rank: int, world: int,
     return {k: (v if k in replicated else v[a:b].contiguous()) for k, v in tensors.items()}
 
 
+class RowGather:
+    """All-gather of per-rank row blocks ``[N, rows_r, C]`` along dim 1 (ragged sizes allowed), started
+    asynchronously: ``RowGather(local, sizes, group)`` issues the collective (NCCL runs it on its own
+    stream), ``.result()`` makes the current stream wait for it and returns ``[N, sum(rows), C]``.
+    Work that only needs the local rows goes between the two calls."""
+
+    def __init__(self, local: torch.Tensor, sizes: List[int], group=None):
+        world = dist.get_world_size(group)
+        n = local.shape[0]
+        self.sizes, self.n, self.world = sizes, n, world
+        self.even = len(set(sizes)) == 1
+        if self.even:
+            send = local.contiguous()
+        else:
+            # ragged: pad every block to the largest one (one collective; the backends' list-based
+            # all_gather does not accept uneven sizes everywhere), the padding is dropped in result()
+            send = local.new_zeros((n, max(sizes)) + tuple(local.shape[2:]))
+            send[:, :local.shape[1]] = local
+        self.block = tuple(send.shape)
+        self.out = local.new_empty((world * n,) + self.block[1:])        # rank-major along dim 0
+        self.work = dist.all_gather_into_tensor(self.out, send, group=group, async_op=True)
+
+    def result(self) -> torch.Tensor:
+        self.work.wait()
+        if self.even and self.n == 1:
+            # one image: rank-major blocks of rows ARE the concatenation along dim 1 -- no copy
+            return self.out.view((1, self.world * self.block[1]) + self.block[2:])
+        blocks = self.out.view((self.world,) + self.block)
+        if self.even:
+            return torch.cat(list(blocks.unbind(0)), 1)
+        return torch.cat([blocks[r, :, :sz] for r, sz in enumerate(self.sizes)], 1)
+
+
 def all_gather_rows(local: torch.Tensor, sizes: List[int], group=None) -> torch.Tensor:
-    """Concatenate per-rank row blocks ``[N, rows_r, C]`` along dim 1 (ragged sizes allowed)."""
-    world = dist.get_world_size(group)
-    n = local.shape[0]
-    if len(set(sizes)) == 1:
-        out = local.new_empty((world * n,) + tuple(local.shape[1:]))     # rank-major along dim 0
-        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
-        return torch.cat(list(out.view((world, n) + tuple(local.shape[1:])).unbind(0)), 1)
-    # ragged: pad every block to the largest one (one collective; the backends' list-based
-    # all_gather does not accept uneven sizes everywhere), then drop the padding
-    top = max(sizes)
-    padded = local.new_zeros((local.shape[0], top) + tuple(local.shape[2:]))
-    padded[:, :local.shape[1]] = local
-    out = local.new_empty((world * n,) + tuple(padded.shape[1:]))
-    dist.all_gather_into_tensor(out, padded, group=group)
-    out = out.view((world,) + tuple(padded.shape))
-    return torch.cat([out[r, :, :s] for r, s in enumerate(sizes)], 1)
+    """Blocking form of :class:`RowGather`."""
+    return RowGather(local, sizes, group).result()
 
 
 class QueryShardedEncoder:
@@ -62,8 +81,10 @@ class QueryShardedEncoder:
 
     Every rank holds the same weights and the same flattened inputs; rank r keeps rows
     ``shard_range(S, r, world)`` of the running ``src``.  Per layer: local ``value_proj`` on the
-    rank's rows, all-gather of ``value`` (S*256*4 bytes in total), the MSDA op on the rank's
-    queries against the full ``value``, then the local output projection / LayerNorm / FFN.
+    rank's rows, all-gather of ``value`` (S*256*4 bytes in total) started asynchronously and
+    overlapped with the sampling-offset / attention-weight projections and softmax of the local rows
+    (they do not depend on it), the MSDA op on the rank's queries against the full ``value``, then
+    the local output projection / LayerNorm / FFN.
     A final all-gather returns the full memory on every rank.
     """
 
@@ -84,10 +105,10 @@ class QueryShardedEncoder:
         x, p = src[:, a:b], pos[:, a:b]
         for layer in m.encoder.layers:
             attn = layer.self_attn
-            value_local = attn.value_proj(x)
-            value = all_gather_rows(value_local, sizes, self.group)
+            gather = RowGather(attn.value_proj(x), sizes, self.group)      # in flight ...
+            loc, w = attn.sampling_inputs(x + p, ref, shapes)              # ... while the local rows' producers run
+            value = gather.result()
             value = value.view(value.shape[0], S, attn.n_heads, attn.d_model // attn.n_heads)
-            loc, w = attn.sampling_inputs(x + p, ref, shapes)
             out = attn._core(value, shapes, lsi, loc.contiguous(), w.contiguous(), attn.im2col_step)
             x = layer.forward_ffn(layer.norm1(x + layer.dropout1(attn.output_proj(out))))
         return all_gather_rows(x, sizes, self.group), shapes, lsi
