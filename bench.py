@@ -30,14 +30,12 @@ METRIC = "msda_fwd_bwd_queries_per_s"
 UNIT = "queries/s"
 DEFAULT_WORKLOAD = "cityscapes_512x1024_b8"
 NOMINAL_HBM_GBS = 8000.0          # north_star's "~8 TB/s"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of
-# this command (profiles/r1_ncu_bench_summary.csv); only valid for the default workload / mode
-NCU_DRAM_TRAFFIC = {("cityscapes_512x1024_b8", "model"): {"forward": 246.6e6, "backward": 527.4e6}}
-# What actually bounds the dominant (backward) kernel on chip, from the same capture and from
-# tools/microbench.cu (profiles/r1_microbench.txt): 120.5 M reduction sectors of 32 B per launch
-# against a reduction-path throughput of ~6.4 TB/s chip-wide (independent of occupancy, instruction width and engine).
-NCU_RED_BYTES = {("cityscapes_512x1024_b8", "model"): 120499092 * 32}
-L2_REDUCTION_GBS = 6400.0
+# Counters of the dominant kernel that only a profiler can give (DRAM bytes, reduction sectors): read
+# from the committed summary of the ncu --set full capture of THIS command for the current kernels
+# (tools/ncu_counters.py writes it from the .ncu-rep; profiles/README.md).  A kernel the summary does
+# not name gets null -- nothing here is pasted by hand.
+NCU_COUNTERS_JSON = os.path.join(ROOT, "profiles", "r2_ncu_bench_counters.json")
+L2_REDUCTION_GBS = 6400.0         # measured: profiles/r1_microbench.txt (red.global.add payload, chip-wide)
 FALLBACK_HBM_GBS = 6650.0         # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -51,7 +49,8 @@ def parse_args():
     p.add_argument("--mode", default="model", choices=["model", "uniform"])
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
-    p.add_argument("--cpu-sample-batch", type=int, default=2)
+    p.add_argument("--cpu-sample-batch", type=int, default=0,
+                   help="images per CPU step; 0 = the workload's whole batch")
     return p.parse_args()
 
 
@@ -118,35 +117,106 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+# ----------------------------------------------------------------------------- shared helpers
+def load_synthetic():
+    """uni-encoder-code_b200/synthetic.py imported BY PATH (plain torch, no CUDA library): the
+    reference arm builds the same tensors as the GPU arm without ever loading libmsda_b200.so."""
+    import importlib.util
+    name = "msda_b200_synthetic"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "uni-encoder-code_b200", "synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def make_config(args, w):
+    """Identical in both arms (the driver compares them key by key)."""
+    return {
+        "workload": f"{args.workload} fwd+bwd (BASELINE.json configs[1])",
+        "levels": [list(x) for x in w.levels], "batch_per_gpu": w.batch, "heads": w.heads,
+        "channels": w.channels, "points": w.points,
+        "queries_per_step_per_gpu": w.batch * w.spatial_size, "loc_mode": args.mode,
+        "l2": "512 MiB memset between steps (untimed); step working set 640 MB > 126 MB L2",
+        "step": "forward + backward of the op on one batch, inputs resident in memory",
+        "sharding": "batch (independent images per rank), no data-path collective",
+    }
+
+
+def ncu_counters(kernel_name, workload, mode):
+    """{dram_bytes, red_sectors, ...} per launch for `kernel_name` from the committed capture, or {}."""
+    try:
+        with open(NCU_COUNTERS_JSON) as f:
+            doc = json.load(f)
+        if doc.get("workload") != workload or doc.get("mode") != mode:
+            return {}
+        return doc.get("kernels", {}).get(kernel_name, {})
+    except Exception:
+        return {}
+
+
 # ----------------------------------------------------------------------------- CPU arms
+def load_reference_core():
+    """-> (function(value, shapes, loc, w) -> output, kind).
+
+    kind "reference": the reference's OWN ms_deform_attn_core_pytorch, executed from the unmodified
+    copy of ops/functions/ms_deform_attn_func.py that baseline/stage_reference_py.py stages under
+    git-ignored baseline/_ref/py/ (it travels to the GPU box; /root/reference does not).  On a box
+    with a GPU that file imports `MultiScaleDeformableAttention` when it is loaded (func.py:21-30);
+    an empty stand-in module satisfies the import, so neither the repo's shim nor its CUDA library
+    is touched -- the CPU function never uses it.
+    kind "port": the restatement oracle.core_grid_sample, only when the staged file is absent."""
+    import importlib.util
+    import types
+    path = os.path.join(ROOT, "baseline", "_ref", "py", "modeling", "pixel_decoder", "ops", "functions",
+                        "ms_deform_attn_func.py")
+    if os.path.isfile(path):
+        had = sys.modules.get("MultiScaleDeformableAttention")
+        if had is None:
+            sys.modules["MultiScaleDeformableAttention"] = types.ModuleType("MultiScaleDeformableAttention")
+        try:
+            spec = importlib.util.spec_from_file_location("ref_ms_deform_attn_func", path)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+        finally:
+            if had is None:
+                sys.modules.pop("MultiScaleDeformableAttention", None)
+        return mod.ms_deform_attn_core_pytorch, "reference"
+    from __graft_entry__ import load_oracle
+    return load_oracle().core_grid_sample, "port"
+
+
 def cpu_reference_run(workload_name, mode, sample_batch, steps, warmup):
-    """The reference's CPU path for this op is ms_deform_attn_core_pytorch
-    (ops/functions/ms_deform_attn_func.py:55-75) + autograd.  It is Python and cannot travel to
-    the GPU box, so the timed code is its restatement oracle.core_grid_sample (kind "port"),
-    pinned to the reference by tests/golden.  Each step is forward+backward on `sample_batch`
-    images of the workload's shape, with every host thread torch can use."""
+    """The reference's CPU path for this op: ms_deform_attn_core_pytorch
+    (ops/functions/ms_deform_attn_func.py:55-75) + autograd, fp32, on every host thread torch can
+    use.  Each step is forward+backward on `sample_batch` images of the workload's shape."""
     import torch
-    from __graft_entry__ import load_oracle, load_package
-    oracle = load_oracle()
-    syn = load_package().synthetic
+    core, kind = load_reference_core()
+    syn = load_synthetic()
     torch.set_num_threads(os.cpu_count() or 1)
     w = syn.WORKLOADS[workload_name]
     inp = syn.make_inputs(w.levels, sample_batch, w.heads, w.channels, w.points, mode=mode, seed=0)
     times = []
     for i in range(warmup + steps):
+        v = inp["value"].detach().requires_grad_(True)
+        loc = inp["sampling_locations"].detach().requires_grad_(True)
+        wts = inp["attention_weights"].detach().requires_grad_(True)
         t0 = time.perf_counter()
-        oracle.core_grid_sample_grads(inp["value"], inp["spatial_shapes"], inp["sampling_locations"],
-                                      inp["attention_weights"], inp["grad_output"])
+        out = core(v, inp["spatial_shapes"], loc, wts)
+        torch.autograd.grad(out, (v, loc, wts), inp["grad_output"])
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     q = sample_batch * w.spatial_size
     mean = sum(times) / len(times)
-    return {"value": q / mean, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+    what = ("the reference's ms_deform_attn_core_pytorch (staged unmodified file)" if kind == "reference"
+            else "oracle.core_grid_sample (restated ms_deform_attn_core_pytorch)")
+    return {"value": q / mean, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
             "host_cpus": os.cpu_count(),
-            "sample": f"fwd+bwd of oracle.core_grid_sample (restated ms_deform_attn_core_pytorch, fp32) "
-                      f"on {sample_batch} image(s) of {workload_name} = {q} queries/step, "
-                      f"{len(times)} timed steps after {warmup} warm-up",
+            "sample": f"fwd+bwd (autograd) of {what}, fp32, on {sample_batch} image(s) of {workload_name} = "
+                      f"{q} queries/step, {len(times)} timed steps after {warmup} warm-up",
             "ms_per_step": mean * 1e3}
 
 
@@ -154,21 +224,19 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # ~0.6 s per step on 8 cores: honour K and W up to a cap that keeps the run within minutes
-    steps = max(1, min(args.steps, 100))
-    warmup = max(1, min(args.warmup, 10))
-    base = cpu_reference_run(args.workload, args.mode, args.cpu_sample_batch, steps, warmup)
-    from __graft_entry__ import load_package
-    w = load_package().synthetic.WORKLOADS[args.workload]
+    w = load_synthetic().WORKLOADS[args.workload]
+    # the whole batch of the workload per step (~0.4-0.6 s on the box's cores): K and W are honoured
+    # up to a cap that keeps the run within minutes
+    steps = max(1, min(args.steps, 60))
+    warmup = max(1, min(args.warmup, 5))
+    batch = w.batch if args.cpu_sample_batch <= 0 else args.cpu_sample_batch
+    base = cpu_reference_run(args.workload, args.mode, batch, steps, warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT,
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": base["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"{args.workload} fwd+bwd (BASELINE.json configs[1])",
-                   "levels": [list(x) for x in w.levels], "batch_per_gpu": w.batch,
-                   "loc_mode": args.mode,
-                   "note": "CPU arm: bounded sample per step, see cpu_baseline.sample"},
+        "config": make_config(args, w),
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -190,9 +258,7 @@ def run_b200_arm(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there at VERSION/INFO
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL_DEBUG is left as the caller set it: whatever NCCL prints on fd 1 goes to stderr (main())
         dist.init_process_group("nccl", device_id=dev)
 
     pkg = load_package()
@@ -290,40 +356,44 @@ def run_b200_arm(args):
     bwd_bytes = queries_rank * syn.BWD_BYTES_PER_QUERY
     fwd_bytes = queries_rank * syn.FWD_BYTES_PER_QUERY
     achieved = bwd_bytes / (bwd_mean * 1e-3) / 1e9
+    # which backward kernel the library's location probe picked for these inputs (model-like
+    # locations: the in-SM merging kernel; uniform ones: the per-row reduction kernel)
+    bwd_kernel = "msda_bwd_sorted_kernel" if args.mode == "model" else "msda_bwd_d32_kernel"
+    ctr = ncu_counters(bwd_kernel, args.workload, args.mode)
+    red_bytes = ctr.get("red_sectors", 0) * 32
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {
-            "workload": f"{args.workload} fwd+bwd (BASELINE.json configs[1])",
-            "levels": [list(x) for x in w.levels], "batch_per_gpu": N, "heads": M, "channels": D,
-            "points": P, "queries_per_step_per_gpu": queries_rank, "loc_mode": args.mode,
-            "l2": "512 MiB memset between steps (untimed); step working set 640 MB > 126 MB L2",
-            "step": "forward kernel + grad_value memset + backward kernel, inputs resident in HBM",
-            "sharding": "batch (independent images per rank), no data-path collective",
-        },
+        "config": make_config(args, w),
         "roofline": {
-            "bound": "hbm", "kernel": "msda_bwd_d32_kernel", "achieved": achieved, "peak": peak,
+            "bound": "hbm", "kernel": bwd_kernel, "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak,
-            "traffic": NCU_DRAM_TRAFFIC.get((args.workload, args.mode), {}).get("backward"),
-            "traffic_source": "profiles/r1_ncu_bench_summary.csv (ncu --set full, per launch)",
+            "traffic": ctr.get("dram_bytes"),
+            "traffic_source": ("profiles/r2_ncu_bench_counters.json (ncu --set full of this command, per launch)"
+                               if ctr else "no committed capture names this kernel: see profiles/"),
             "peak_source": peak_src,
             "algorithmic_bytes_per_launch": bwd_bytes, "ms_per_launch": bwd_mean,
+            "timed": "CUDA events around msda_b200_backward_f32 (location probe + the chosen kernel), "
+                     "mean over the timed steps",
             "frac_of_nominal_8TBs": achieved / NOMINAL_HBM_GBS,
             "on_chip_limiter": ({
-                "resource": "L2 reduction (red.global.add) throughput",
-                "bytes_per_launch": NCU_RED_BYTES[(args.workload, args.mode)],
-                "achieved_GBs": NCU_RED_BYTES[(args.workload, args.mode)] / (bwd_mean * 1e-3) / 1e9,
+                "resource": "L2 reduction (red.global.add) payload",
+                "bytes_per_launch": red_bytes,
+                "achieved_GBs": red_bytes / (bwd_mean * 1e-3) / 1e9,
                 "measured_peak_GBs": L2_REDUCTION_GBS,
-                "frac": NCU_RED_BYTES[(args.workload, args.mode)] / (bwd_mean * 1e-3) / 1e9 / L2_REDUCTION_GBS,
-                "source": "profiles/r1_ncu_bench_summary.csv, profiles/r1_microbench.txt; DESIGN.md section 4",
-            } if (args.workload, args.mode) in NCU_RED_BYTES else None),
+                "frac": red_bytes / (bwd_mean * 1e-3) / 1e9 / L2_REDUCTION_GBS,
+                "l1_data_pipe_pct": ctr.get("l1_data_pipe_pct"),
+                "issue_slot_pct": ctr.get("issue_active_pct"),
+                "source": "profiles/r2_ncu_bench_counters.json, profiles/r1_microbench.txt; DESIGN.md section 4",
+            } if ctr else None),
         },
         "kernels": {
             "forward": {"ms": fwd_mean, "algorithmic_GBs": fwd_bytes / (fwd_mean * 1e-3) / 1e9,
                         "frac": fwd_bytes / (fwd_mean * 1e-3) / 1e9 / peak},
             "grad_value_memset": {"ms": statistics.mean(zero_ms)},
-            "backward": {"ms": bwd_mean, "algorithmic_GBs": achieved, "frac": achieved / peak},
+            "backward": {"ms": bwd_mean, "algorithmic_GBs": achieved, "frac": achieved / peak,
+                         "kernel": bwd_kernel},
             "fwd_bwd": {"algorithmic_GBs": (fwd_bytes + bwd_bytes) / (ms_per_step * 1e-3) / 1e9,
                         "frac": (fwd_bytes + bwd_bytes) / (ms_per_step * 1e-3) / 1e9 / peak},
         },
@@ -338,7 +408,8 @@ def run_b200_arm(args):
         if ref_cuda is not None:
             line["reference_cuda_same_gpu"] = ref_cuda
     if world == 1 and not args.no_cpu_baseline:
-        base = cpu_reference_run(args.workload, args.mode, args.cpu_sample_batch, 3, 1)
+        batch = w.batch if args.cpu_sample_batch <= 0 else args.cpu_sample_batch
+        base = cpu_reference_run(args.workload, args.mode, batch, 5, 1)
         line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -461,7 +532,7 @@ def run_e2e(pkg, host, dev, world, steps, dist):
     if dist is not None:
         dist.barrier()
     # the host side (pinned memory, PCIe root) is shared with other tenants of the box: three
-    # repetitions of `steps` steps, the fastest one is reported (all three are listed)
+    # repetitions of `steps` steps, the MEDIAN is reported and all three are listed
     trials = []
     for _ in range(3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -473,7 +544,7 @@ def run_e2e(pkg, host, dev, world, steps, dist):
         e1.record(cur)
         torch.cuda.synchronize()
         trials.append(e0.elapsed_time(e1))
-    ms = min(trials)
+    ms = statistics.median(trials)
     if dist is not None:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -484,7 +555,7 @@ def run_e2e(pkg, host, dev, world, steps, dist):
             "trials_ms_per_step": [t / steps for t in trials],
             "api": "MSDeformAttnFunction.apply + autograd.grad; pinned host -> device inputs and "
                    "device -> pinned host results every step, copies overlapped with compute on "
-                   "3 streams (double-buffered); fastest of 3 repetitions of `steps` steps"}
+                   "3 streams (double-buffered); median of 3 repetitions of `steps` steps"}
 
 
 def main():
