@@ -145,7 +145,7 @@ def test_encoder_layer_with_tensor_core_linears_matches_torch_linears(pkg):
         (yc * cot).sum().backward()
         # per layer: MSDA fwd + bwd, 6 x (split + GEMM) forward, 6 x (split + GEMM) for grad_x,
         # 6 weight / bias gradient kernels, 2 x (add + LayerNorm forward, backward)
-        assert pkg.launch_count() - n3 == 2 * (4 + 12 + 12 + 6 + 4)   # MSDA backward = probe + 2 gated kernels
+        assert pkg.launch_count() - n3 == 2 * (3 + 12 + 12 + 6 + 4)   # MSDA backward = 2 gated kernels
         assert (yc - ya).abs().max().item() <= 5e-5
         # gradients pass through floor() of the sampling locations: a 1e-6 difference in a location next to
         # a cell edge moves the point into the neighbouring cell, where the location gradient differs by

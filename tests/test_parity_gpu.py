@@ -411,12 +411,12 @@ def test_launches_are_counted(pkg):
     n0 = pkg.launch_count()
     run_fwd_bwd(pkg, d)
     assert pkg.launch_count() - n0 == 2           # decoder-style Lq != S: forward + per-row backward
-    # encoder self-attention (Lq == S): the backward is a one-CTA probe of the locations plus the
-    # merging and the per-row kernel behind its verdict (the one not chosen returns at once)
+    # encoder self-attention (Lq == S): the backward launches the merging and the per-row kernel; both
+    # probe the locations first and the one the verdict goes against returns at once
     d = to_dev(pkg.synthetic.make_inputs([(4, 6), (8, 12)], 1, heads=2, points=2, mode="uniform"))
     n0 = pkg.launch_count()
     run_fwd_bwd(pkg, d)
-    assert pkg.launch_count() - n0 == 4
+    assert pkg.launch_count() - n0 == 3
 
 
 @pytest.mark.parametrize("mode,bwd_variant", [("model", 2), ("model", 20), ("uniform", 2), ("uniform", 20)])

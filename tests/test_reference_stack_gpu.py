@@ -45,7 +45,7 @@ def test_reference_autograd_function_on_the_shim(pkg, oracle, ref):
     n0 = pkg.launch_count()
     out = ref.func.MSDeformAttnFunction.apply(v, d["spatial_shapes"], d["level_start_index"], loc, w, 128)
     out.backward(d["grad_output"])
-    assert pkg.launch_count() - n0 == 4        # our kernels ran: forward + (probe, two gated backward kernels)
+    assert pkg.launch_count() - n0 == 3        # our kernels ran: forward + the two gated backward kernels
     check_against(out.detach(), v.grad, loc.grad, w.grad, *oracle_refs(oracle, inp), tag="reference function")
     # the reference's CPU formulation of the same function (func.py:55-75) agrees with it on the GPU
     core = ref.ms_deform_attn_core_pytorch(d["value"].double(), d["spatial_shapes"], d["sampling_locations"].double(),
@@ -176,5 +176,8 @@ def test_reference_encoder_training_step_on_the_shim(pkg, ref):
     for k, p in enc.named_parameters():
         # the attention module's own parameters see the op's three gradients directly; level_embed and
         # the norms are long fp32 sums of cancelling terms (1e-9 in size here): fp32-vs-fp64 noise of torch
-        tol = 2e-3 if "self_attn" in k else 3e-2
+        # sampling_offsets: the locations themselves come out of an fp32 Linear here and an fp64 one there;
+        # the few samples that round into a different bilinear cell change grad_sampling_loc (floor is
+        # discontinuous), which this sum over all queries picks up at the per-cent level
+        tol = 5e-2 if "sampling_offsets" in k else (2e-3 if "self_attn" in k else 3e-2)
         assert rel_err(grads[k].cpu().numpy(), p.grad.cpu().numpy()) <= tol, k

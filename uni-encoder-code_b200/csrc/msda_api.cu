@@ -18,11 +18,10 @@ cudaError_t launch_fwd_d32(const float *, const int64_t *, const int64_t *, cons
                            const float *, const Dims &, float *, cudaStream_t, bool *handled);
 cudaError_t launch_bwd_d32(const float *, const float *, const int64_t *, const int64_t *,
                            const float *, const float *, const Dims &, float *, float *, float *,
-                           cudaStream_t, bool *handled, const int *gate);
+                           cudaStream_t, bool *handled, int gate);
 cudaError_t launch_bwd_sorted(const float *, const float *, const int64_t *, const int64_t *,
                               const float *, const float *, const Dims &, float *, float *, float *,
-                              cudaStream_t, bool *handled, const int *gate);
-cudaError_t launch_bwd_probe(const int64_t *, const int64_t *, const float *, const Dims &, cudaStream_t, int **gate);
+                              cudaStream_t, bool *handled, int gate);
 bool bwd_sorted_applies(const float *value, const float *grad_value, const Dims &);
 cudaError_t launch_fwd_d32_fused(const float *, const int64_t *, const int64_t *, const float *,
                                  long long, const float *, const float *, const Dims &, float *,
@@ -181,21 +180,21 @@ int msda_b200_backward_f32(const float *grad_output, const float *value,
     const int variant = option_value(OPT_BWD_VARIANT);
     const bool fast_ok = aligned16(value) && aligned16(grad_output) && aligned16(grad_value) &&
                          aligned8(sampling_loc) && aligned8(grad_sampling_loc);
-    // 0 (default): where the queries are the value pixels (encoder self-attention) a one-CTA probe
-    //     of the sampling locations picks the in-SM merging kernel (points near their query) or the
-    //     per-row reduction kernel (points anywhere); both are launched, the other returns at once;
+    // 0 (default): where the queries are the value pixels (encoder self-attention) the in-SM merging
+    //     kernel (points near their query) and the per-row reduction kernel (points anywhere) are both
+    //     launched; every CTA of both runs the same probe of the sampling locations first and the
+    //     kernel the verdict goes against returns at once (msda_common.cuh);
     // 20..39: merging kernel forced (and its tuning variants); 1..8: CTA shapes of the per-row
     //     reduction kernel; 63: generic kernel (tests)
-    int *gate = nullptr;
+    int gate = GATE_NONE;
     if (variant == 0 && fast_ok && bwd_sorted_applies(value, grad_value, d)) {
-        e = launch_bwd_probe(spatial_shapes, level_start, sampling_loc, d, st, &gate);
-        if (e == cudaSuccess)
-            e = launch_bwd_sorted(grad_output, value, spatial_shapes, level_start, sampling_loc, attn_weight,
-                                  d, grad_value, grad_sampling_loc, grad_attn_weight, st, &handled, gate);
-        handled = false;                     // the per-row kernel is launched behind the same gate
+        e = launch_bwd_sorted(grad_output, value, spatial_shapes, level_start, sampling_loc, attn_weight,
+                              d, grad_value, grad_sampling_loc, grad_attn_weight, st, &handled, GATE_RUN_IF_LOCAL);
+        handled = false;                     // the per-row kernel follows, gated the other way
+        gate = GATE_RUN_IF_SPREAD;
     } else if (variant >= 20 && variant < 40 && fast_ok) {
         e = launch_bwd_sorted(grad_output, value, spatial_shapes, level_start, sampling_loc, attn_weight,
-                              d, grad_value, grad_sampling_loc, grad_attn_weight, st, &handled, nullptr);
+                              d, grad_value, grad_sampling_loc, grad_attn_weight, st, &handled, GATE_NONE);
     }
     if (e == cudaSuccess && !handled && variant != 63 && fast_ok)
         e = launch_bwd_d32(grad_output, value, spatial_shapes, level_start, sampling_loc, attn_weight,

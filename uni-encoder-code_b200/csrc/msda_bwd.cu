@@ -63,8 +63,7 @@ msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict_
                     const float *__restrict__ loc, const float *__restrict__ attw,
                     const Producers pr, const Dims d, const int flags,
                     float *__restrict__ grad_value, float *__restrict__ grad_loc,
-                    float *__restrict__ grad_attw, const int *__restrict__ gate) {
-    if (gate && *gate != 0) return;      // the probe chose the merging kernel (msda_bwd_sorted.cu)
+                    float *__restrict__ grad_attw, const int gate) {
     using Cfg = BwdCfg<LP, WARPS, TILE_W, QPW>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ LevelTable lt;
@@ -81,6 +80,8 @@ msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict_
     // scheme that merges those contributions before they reach L2 could hope for
     const int drop_pairs = flags >> 1;
     __syncthreads();
+    // launched next to the merging kernel (msda_bwd_sorted.cu): the shared probe of the locations decides
+    if (gate == GATE_RUN_IF_SPREAD && probe_points_stay_local(lt, loc, d.N, d.Lq, d.M, d.L, d.P)) return;
 
     const int M = d.M;
     const long long items = (long long)d.N * M * lt.groups;
@@ -248,7 +249,7 @@ static cudaError_t launch_bwd_cfg(const float *grad_out, const float *value, con
                                   const int64_t *lstart, const float *loc, const float *attw,
                                   const Dims &d, float *grad_value, float *grad_loc,
                                   float *grad_attw, cudaStream_t stream,
-                                  Producers pr = Producers{nullptr, 0}, const int *gate = nullptr) {
+                                  Producers pr = Producers{nullptr, 0}, int gate = GATE_NONE) {
     using Cfg = BwdCfg<LP, WARPS, TILE_W, QPW>;
     auto kern = msda_bwd_d32_kernel<LP, WARPS, TILE_W, MIN_CTAS, BATCH, QPW, FUSED>;
     // the opt-in shared-memory size is a per-device function attribute: set it (and query the
@@ -285,7 +286,7 @@ template <int LP>
 static cudaError_t launch_bwd_lp(const float *grad_out, const float *value, const int64_t *shapes,
                                  const int64_t *lstart, const float *loc, const float *attw,
                                  const Dims &d, float *gv, float *gl, float *gw, cudaStream_t st,
-                                 const int *gate) {
+                                 int gate) {
     // variant = (warps, query tile width, min CTAs per SM -> register budget, load batch in pairs,
     //            queries per warp)
 #define MSDA_BWD(W, TW, C, B, Q) \
@@ -308,7 +309,7 @@ static cudaError_t launch_bwd_lp(const float *grad_out, const float *value, cons
 cudaError_t launch_bwd_d32(const float *grad_out, const float *value, const int64_t *shapes,
                            const int64_t *lstart, const float *loc, const float *attw, const Dims &d,
                            float *gv, float *gl, float *gw, cudaStream_t stream, bool *handled,
-                           const int *gate) {
+                           int gate) {
     *handled = true;
     const int LP = d.L * d.P;
     if (d.D != 32 || (long long)d.S * d.M * 8 >= 0x7fffffffLL) {

@@ -316,8 +316,7 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
                        const int64_t *__restrict__ shapes, const int64_t *__restrict__ lstart,
                        const float *__restrict__ loc, const float *__restrict__ attw, const Dims d,
                        const int flags, float *__restrict__ grad_value, float *__restrict__ grad_loc,
-                       float *__restrict__ grad_attw, const int *__restrict__ gate) {
-    if (gate && *gate != 1) return;      // the probe chose the per-row reduction kernel for these inputs
+                       float *__restrict__ grad_attw, const int gate) {
     using Cfg = SortCfg<LP, WARPS, TILE_W, TILE_Q, SLOTS>;
     constexpr int NT = Cfg::kThreads;
     constexpr int kSortTile = Cfg::kSortTile, kSortSlots = Cfg::kSortSlots;
@@ -339,6 +338,8 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
     fill_level_table(lt, shapes, lstart, d.L, d.P, d.S, d.Lq, kSortTile, Cfg::kTileH, TILE_W, flags & 1);
     for (int i = tid; i < kSortSlots; i += NT) cnt[i] = 0u;   // invariant: zero outside pass A .. pass B
     __syncthreads();
+    // launched next to the per-row reduction kernel: the shared probe of the locations decides
+    if (gate == GATE_RUN_IF_LOCAL && !probe_points_stay_local(lt, loc, d.N, d.Lq, d.M, d.L, d.P)) return;
 
     const int M = d.M, L = d.L, Lq = d.Lq;
     const long long items = (long long)d.N * M * lt.groups;
@@ -654,7 +655,7 @@ template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int TILE_Q, int SLOTS, in
 static cudaError_t launch_bwd_sorted_cfg(const float *grad_out, const float *value, const int64_t *shapes,
                                          const int64_t *lstart, const float *loc, const float *attw,
                                          const Dims &d, float *gv, float *gl, float *gw, cudaStream_t stream,
-                                         const int *gate) {
+                                         int gate) {
     using Cfg = SortCfg<LP, WARPS, TILE_W, TILE_Q, SLOTS>;
     auto kern = msda_bwd_sorted_kernel<LP, WARPS, TILE_W, MIN_CTAS, TILE_Q, SLOTS, GW, PFV>;
     int dev = 0;
@@ -685,95 +686,6 @@ static cudaError_t launch_bwd_sorted_cfg(const float *grad_out, const float *val
     return cudaGetLastError();
 }
 
-// ---------------------------------------------------------------------------
-// Which backward kernel?  Merging pays when the sampling points stay near their query (the encoder:
-// offsets of a few pixels, ms_deform_attn.py:71-77); with locations spread over the whole image
-// nearly every record is a run of one and the per-row reduction kernel of msda_bwd.cu is faster.
-// The host cannot look at the locations (no device read-back, CUDA-graph capturable), so a
-// one-CTA probe samples 4096 points, measures the fraction that lands within the merge windows'
-// margin of its query and leaves the verdict in a device word that both kernels are launched with:
-// the one not chosen returns at once.
-// ---------------------------------------------------------------------------
-constexpr int kGateSlots = 1024;
-__device__ int g_bwd_gate[kGateSlots];
-
-__global__ void __launch_bounds__(1024, 1)
-msda_bwd_probe_kernel(const int64_t *__restrict__ shapes, const int64_t *__restrict__ lstart,
-                      const float *__restrict__ loc, const Dims d, int *__restrict__ gate) {
-    __shared__ LevelTable lt;
-    __shared__ int tot_in[32], tot_all[32];
-    fill_level_table(lt, shapes, lstart, d.L, d.P, d.S, d.Lq, kSortTileMax, 8, 16, 1);
-    __syncthreads();
-    const int LP = d.L * d.P;
-    int n_in = 0, n_all = 0;
-    if (lt.spatial) {
-        uint32_t h = threadIdx.x * 2654435761u + 12345u;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            h = h * 1664525u + 1013904223u;                 // LCG: which (image, query, head, point)
-            const int n = (int)((h >> 8) % (uint32_t)d.N);
-            h = h * 1664525u + 1013904223u;
-            const int q = (int)((h >> 4) % (uint32_t)d.Lq);
-            h = h * 1664525u + 1013904223u;
-            const int m = (int)((h >> 8) % (uint32_t)d.M), sp = (int)((h >> 16) % (uint32_t)LP);
-            int lq = 0;
-            while (lq + 1 < d.L && q >= lt.start[lq + 1]) ++lq;
-            const int qy = (q - lt.start[lq]) / lt.W[lq], qx = (q - lt.start[lq]) - qy * lt.W[lq];
-            const int l = sp / d.P;
-            const float2 xy = reinterpret_cast<const float2 *>(loc)[(((long long)n * d.Lq + q) * d.M + m) * LP + sp];
-            const float W = (float)lt.W[l], H = (float)lt.H[l];
-            const float x = xy.x * W - 0.5f, y = xy.y * H - 0.5f;
-            if (x > -1.f && y > -1.f && x < W && y < H) {   // the op's own range test (cuh:293)
-                const float rx = ((float)qx + 0.5f) * (W / (float)lt.W[lq]) - 0.5f;
-                const float ry = ((float)qy + 0.5f) * (H / (float)lt.H[lq]) - 0.5f;
-                ++n_all;
-                if (fabsf(x - rx) <= (float)kSortMargin - 1.f && fabsf(y - ry) <= (float)kSortMargin - 1.f) ++n_in;
-            }
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        n_in += __shfl_xor_sync(kFullMask, n_in, o);
-        n_all += __shfl_xor_sync(kFullMask, n_all, o);
-    }
-    if ((threadIdx.x & 31) == 0) { tot_in[threadIdx.x >> 5] = n_in; tot_all[threadIdx.x >> 5] = n_all; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int a = 0, b = 0;
-        for (int w = 0; w < 32; ++w) { a += tot_in[w]; b += tot_all[w]; }
-        *gate = (b > 0 && 4 * a >= 3 * b) ? 1 : 0;          // >= 75 % near their query: merge
-    }
-}
-
-// device word for this backward call (a ring: calls in flight never share a word in practice)
-static cudaError_t next_gate(int **gate) {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
-    static std::atomic<int *> base_of[kMaxDevices];
-    static std::atomic<unsigned> counter{0};
-    int *base = base_of[dev].load(std::memory_order_acquire);
-    if (!base) {
-        void *p = nullptr;
-        e = cudaGetSymbolAddress(&p, g_bwd_gate);
-        if (e != cudaSuccess) return e;
-        base = static_cast<int *>(p);
-        base_of[dev].store(base, std::memory_order_release);
-    }
-    *gate = base + counter.fetch_add(1, std::memory_order_relaxed) % kGateSlots;
-    return cudaSuccess;
-}
-
-cudaError_t launch_bwd_probe(const int64_t *shapes, const int64_t *lstart, const float *loc, const Dims &d,
-                             cudaStream_t stream, int **gate) {
-    cudaError_t e = next_gate(gate);
-    if (e != cudaSuccess) return e;
-    msda_bwd_probe_kernel<<<1, 1024, 0, stream>>>(shapes, lstart, loc, d, *gate);
-    note_launch();
-    return cudaGetLastError();
-}
-
 // whether launch_bwd_sorted() covers this problem (shape + alignment)
 bool bwd_sorted_applies(const float *value, const float *gv, const Dims &d) {
     const int LP = d.L * d.P;
@@ -788,7 +700,7 @@ bool bwd_sorted_applies(const float *value, const float *gv, const Dims &d) {
 cudaError_t launch_bwd_sorted(const float *grad_out, const float *value, const int64_t *shapes,
                               const int64_t *lstart, const float *loc, const float *attw, const Dims &d,
                               float *gv, float *gl, float *gw, cudaStream_t stream, bool *handled,
-                              const int *gate) {
+                              int gate) {
     *handled = true;
     const int LP = d.L * d.P;
     if (!bwd_sorted_applies(value, gv, d)) {

@@ -420,6 +420,63 @@ __device__ __forceinline__ void phase1_records(const LevelTable &lt, uint2 *rec,
 }
 
 // ---------------------------------------------------------------------------
+// Which backward kernel?  (encoder self-attention, Lq == S)
+// Merging grad_value contributions inside the SM (msda_bwd_sorted.cu) pays when the sampling points
+// stay near their query (the encoder: offsets of a few pixels, ms_deform_attn.py:71-77); with
+// locations spread over the whole image nearly every record is a run of one and the per-row
+// reduction kernel (msda_bwd.cu) is faster.  The host cannot look at the locations (no device
+// read-back, CUDA-graph capturable), so BOTH kernels are launched and every CTA of both first runs
+// this probe: kProbeSamples pseudo-random (image, query, head, point) samples, the same in every CTA
+// and in both kernels, and the fraction of them that lands within the merge windows' margin of its
+// query.  The verdict is therefore identical everywhere; the kernel it goes against returns at once.
+// Must be called by all threads of the CTA, after fill_level_table() + __syncthreads().
+// ---------------------------------------------------------------------------
+constexpr int kProbeSamples = 1024;
+constexpr float kProbeMarginPx = 8.f;     // kSortMargin - 1 (msda_bwd_sorted.cu)
+enum { GATE_NONE = 0, GATE_RUN_IF_LOCAL = 1, GATE_RUN_IF_SPREAD = 2 };
+
+__device__ __forceinline__ bool probe_points_stay_local(const LevelTable &lt, const float *__restrict__ loc,
+                                                        int N, int Lq, int M, int L, int P) {
+    __shared__ int probe_in, probe_all;
+    if (threadIdx.x == 0) { probe_in = 0; probe_all = 0; }
+    __syncthreads();
+    const int LP = L * P;
+    int n_in = 0, n_all = 0;
+    if (lt.spatial) {
+        for (int i = threadIdx.x; i < kProbeSamples; i += blockDim.x) {
+            uint32_t h = (uint32_t)i * 2654435761u + 12345u;      // which (image, query, head, point)
+            h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+            const int n = (int)(h % (uint32_t)N);
+            h = h * 1664525u + 1013904223u;
+            const int q = (int)((h >> 4) % (uint32_t)Lq);
+            h = h * 1664525u + 1013904223u;
+            const int m = (int)((h >> 8) % (uint32_t)M), sp = (int)((h >> 16) % (uint32_t)LP);
+            int lq = 0;
+            while (lq + 1 < L && q >= lt.start[lq + 1]) ++lq;
+            const int qy = (q - lt.start[lq]) / lt.W[lq], qx = (q - lt.start[lq]) - qy * lt.W[lq];
+            const int l = sp / P;
+            const float2 xy = reinterpret_cast<const float2 *>(loc)[(((long long)n * Lq + q) * M + m) * LP + sp];
+            const float W = (float)lt.W[l], H = (float)lt.H[l];
+            const float x = xy.x * W - 0.5f, y = xy.y * H - 0.5f;
+            if (x > -1.f && y > -1.f && x < W && y < H) {         // the op's own range test (cuh:293)
+                const float rx = ((float)qx + 0.5f) * (W / (float)lt.W[lq]) - 0.5f;
+                const float ry = ((float)qy + 0.5f) * (H / (float)lt.H[lq]) - 0.5f;
+                ++n_all;
+                if (fabsf(x - rx) <= kProbeMarginPx && fabsf(y - ry) <= kProbeMarginPx) ++n_in;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_in += __shfl_xor_sync(kFullMask, n_in, o);
+        n_all += __shfl_xor_sync(kFullMask, n_all, o);
+    }
+    if ((threadIdx.x & 31) == 0 && n_all) { atomicAdd(&probe_in, n_in); atomicAdd(&probe_all, n_all); }
+    __syncthreads();
+    return probe_all > 0 && 4 * probe_in >= 3 * probe_all;       // >= 75 % near their query: merge
+}
+
+// ---------------------------------------------------------------------------
 // launch bookkeeping shared by the translation units
 // ---------------------------------------------------------------------------
 struct Dims {
