@@ -203,19 +203,22 @@ int msda_b200_debug_indices_f32(const int64_t *spatial_shapes, const int64_t *le
  * backward: identical up to the order of the grad_value reductions).  Defaults
  * are what the shipped path uses.  Not thread-safe against concurrent launches.
  *   "fwd_variant"  0 = auto, other values select a specific forward kernel
- *   "bwd_variant"  0 = auto, other values select a specific backward kernel
+ *   "bwd_variant"  0 = auto: where the queries are the value pixels (Lq == S, D = 32) the in-SM merging
+ *                  kernel and the per-row reduction kernel are both launched, every CTA of both probes the
+ *                  sampling locations and the kernel the verdict goes against returns at once; 1..8 = CTA
+ *                  shapes of the per-row reduction kernel, 20..39 = the merging kernel and its tuning
+ *                  variants, 63 = generic kernel
  *   "tile_order"   0 = auto (2-D tiles when the queries are laid out like the value pixels),
  *                  1 = groups of consecutive queries
  *   "ctas_per_sm"  0 = occupancy limit, k > 0 caps the persistent grid at k CTAs per SM
- *   "whatif_drop_reds"  MEASUREMENT ONLY, breaks grad_value: k > 0 drops the grad_value reductions
- *                  of the first k point pairs of every query (k = 4: the two coarsest of 3 levels x 4
- *                  points) to time the best case of any pre-L2 aggregation scheme; 0 = off
  *   "linear_variant"  msda_b200_linear_f32: 0 = auto (128/96-column tiles; A operand in tensor memory
  *                  for in_features < 512, four accumulators in one set with both operands in shared
  *                  memory from 512 on), 2 = four accumulators in one set, 3 = two {main, small} sets
  *                  with both operands in shared memory, 4 = A operand in tensor memory always
- *   "whatif_linear"  MEASUREMENT ONLY, breaks msda_b200_linear_f32: bit mask 1 no MMAs, 2 no split
- *                  work, 4 no output stores, 8 no W loads, 16 no X loads; 0 = off
+ *   "wgrad_chunk"  msda_b200_linear_wgrad_f32: 32-row blocks per work item (0 = 16, i.e. 512 rows)
+ * Only in the profiling build (`make -C uni-encoder-code_b200/csrc profile`, -DMSDA_PROFILE_KNOBS; the
+ * shipped library rejects the names): "whatif_drop_reds" and "whatif_linear" make kernels SKIP work on
+ * purpose (wrong results) to time what-if experiments for profiles/; see tools/whatif*.py.
  */
 int msda_b200_set_option(const char *name, int value);
 int msda_b200_get_option(const char *name, int *value);

@@ -180,3 +180,42 @@ def test_inference_position_cache_tracks_its_inputs(pkg, oracle):
             m.level_embed.add_(0.5)
             assert torch.equal(m(srcs, pos)[0], fresh(pos))
     assert torch.equal(m(srcs, pos)[0], fresh(pos))                   # autograd on: no cache involved
+
+
+def test_encoder_and_pixel_decoder_run_under_inference_mode(pkg, oracle):
+    """The reference works under torch.inference_mode(); inference tensors do not track ._version, so
+    the mirror's position cache must not read it (advisor finding, round 1)."""
+    m, g = build_small(pkg, core=oracle_core(oracle))
+    srcs = [torch.from_numpy(g[f"src{i}"]) for i in range(3)]
+    pos = [torch.from_numpy(g[f"pos{i}"]) for i in range(3)]
+    with torch.no_grad():
+        want = m(srcs, pos)[0]
+    with torch.inference_mode():
+        got = m([s.clone() for s in srcs], [p.clone() for p in pos])[0]     # inference tensors as inputs
+        again = m(srcs, pos)[0]
+    assert torch.equal(got, want) and torch.equal(again, want)
+    from test_pixel_decoder import build
+    dec, feats, _ = build(pkg, core=oracle_core(oracle))
+    with torch.no_grad():
+        ref_out = dec.forward_features(feats)
+    with torch.inference_mode():
+        out = dec.forward_features({k: v.clone() for k, v in feats.items()})
+    assert torch.equal(out[0], ref_out[0]) and torch.equal(out[1], ref_out[1])
+
+
+def test_shape_keyed_caches_are_bounded(pkg):
+    """Variable-resolution datasets present thousands of pyramids: the device-side constants cached per
+    shape (reference points, level tensors, sine embeddings) must not grow without bound."""
+    mod = pkg.modules
+    for i in range(40):
+        levels = [(2 + i, 3), (4, 5 + i)]
+        mod.reference_points_for(levels, "cpu")
+        mod.level_tensors_for(levels, "cpu")
+    assert len(mod._REF_CACHE) <= mod._REF_CACHE.maxsize <= 16
+    assert len(mod._LEVEL_CACHE) <= mod._LEVEL_CACHE.maxsize <= 16
+    pe = pkg.pixel_decoder.PositionEmbeddingSine(8, normalize=True)
+    for i in range(40):
+        pe(torch.zeros(1, 1, 3 + i, 4))
+    assert len(pe._cache) <= pe._cache.maxsize <= 16
+    a = pe(torch.zeros(1, 1, 5, 4))
+    assert torch.equal(a, pe(torch.zeros(2, 1, 5, 4))[:1])                 # hit == rebuilt

@@ -24,7 +24,7 @@ for out_f, in_f in ((256, 256), (192, 256), (96, 256), (1024, 256), (256, 1024))
          "torch_bias_sum_ms": t(lambda: gy.sum(0))}
     ref = gy.double().t() @ x.double()
     for kbpc in (8, 16, 32, 64):
-        pkg.set_option("linear_variant", 100 + kbpc)
+        pkg.set_option("wgrad_chunk", kbpc)
         gw_, _ = pkg.ops.linear_wgrad(gy, x)
         r[f"kb{kbpc}_ms"] = round(t(lambda: pkg.ops.linear_wgrad(gy, x)), 4)
         r[f"kb{kbpc}_err"] = (gw_.double() - ref).abs().max().item()

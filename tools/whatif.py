@@ -2,6 +2,7 @@
 """What-if timing for profiles/: the backward kernel with the grad_value reductions of the coarse
 levels dropped (results are WRONG on purpose) -- an upper bound for any scheme that merges those
 contributions before they reach L2."""
+# needs the profiling build: make -C uni-encoder-code_b200/csrc profile && MSDA_B200_LIB=uni-encoder-code_b200/lib/libmsda_b200_profile.so
 import json, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

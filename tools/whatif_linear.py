@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Timing experiments on the 3xTF32 GEMM with both operands in shared memory (linear_variant 3 / the
 four-accumulator kernel for in = 1024); results WRONG on purpose for the knob runs."""
+# needs the profiling build: make -C uni-encoder-code_b200/csrc profile && MSDA_B200_LIB=uni-encoder-code_b200/lib/libmsda_b200_profile.so
 import os, sys, json
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -523,13 +523,16 @@ cudaError_t launch_linear(const float *x, const float *w, const float *bias, flo
                           int relu, float *workspace, cudaStream_t stream) {
     using Cfg = LinCfg<BN, STAGES, NBUF, NACC>;
     auto kern = linear_tf32x3_kernel<BN, STAGES, NBUF, NACC, WSPLIT>;
-    static bool attr_set[64] = {false};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
-    if (!attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
-        if (e != cudaSuccess) return e;
-        attr_set[dev] = true;
+    static std::atomic<bool> attr_set[msda::kMaxDevices];
+    {
+        cudaError_t e = cudaSuccess;
+        const int dev = msda::device_slot(&e);
+        if (dev < 0) return e;
+        if (!attr_set[dev].load(std::memory_order_acquire)) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+            if (e != cudaSuccess) return e;
+            attr_set[dev].store(true, std::memory_order_release);
+        }
     }
     CUtensorMap mx, mwh, mwl;
     if (WSPLIT) {
@@ -562,7 +565,7 @@ cudaError_t launch_linear(const float *x, const float *w, const float *bias, flo
     const long long tiles = out_tiles * k_chunks;
     const long long grid = tiles < sm_count() ? tiles : sm_count();     // persistent: one CTA per SM
     kern<<<(unsigned)grid, kThreads, Cfg::kSmem, stream>>>(mx, mwh, mwl, bias, y, M, N, K, relu,
-                                                           option_value(OPT_WHATIF_LINEAR), k_chunks, kb_per_chunk);
+                                                           whatif_value(OPT_WHATIF_LINEAR), k_chunks, kb_per_chunk);
     note_launch();
     return cudaGetLastError();
 }
@@ -572,13 +575,16 @@ cudaError_t launch_linear_atmem(const float *x, const float *w, const float *bia
                                 int relu, float *workspace, cudaStream_t stream) {
     using Cfg = LinCfgT<BN>;
     auto kern = linear_tf32x3_atmem_kernel<BN>;
-    static bool attr_set[64] = {false};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
-    if (!attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
-        if (e != cudaSuccess) return e;
-        attr_set[dev] = true;
+    static std::atomic<bool> attr_set[msda::kMaxDevices];
+    {
+        cudaError_t e = cudaSuccess;
+        const int dev = msda::device_slot(&e);
+        if (dev < 0) return e;
+        if (!attr_set[dev].load(std::memory_order_acquire)) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+            if (e != cudaSuccess) return e;
+            attr_set[dev].store(true, std::memory_order_release);
+        }
     }
     float *whi = workspace, *wlo = workspace + (size_t)N * K;
     CUtensorMap mx, mwh, mwl;

@@ -252,13 +252,16 @@ cudaError_t launch_linear_wgrad(const float *grad_y, const float *x, float *grad
     constexpr int BN = 128;
     using Cfg = WgCfg<BN>;
     auto kern = linear_wgrad_kernel<BN>;
-    static bool attr_set[64] = {false};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
-    if (!attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
-        if (e != cudaSuccess) return e;
-        attr_set[dev] = true;
+    static std::atomic<bool> attr_set[msda::kMaxDevices];
+    {
+        cudaError_t e = cudaSuccess;
+        const int dev = msda::device_slot(&e);
+        if (dev < 0) return e;
+        if (!attr_set[dev].load(std::memory_order_acquire)) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+            if (e != cudaSuccess) return e;
+            attr_set[dev].store(true, std::memory_order_release);
+        }
     }
     CUtensorMap mgy, mx;
     if (!make_map_plain(&mgy, grad_y, rows, out_f, kBK, kBM) || !make_map_plain(&mx, x, rows, in_f, kBK, BN))
@@ -271,7 +274,7 @@ cudaError_t launch_linear_wgrad(const float *grad_y, const float *x, float *grad
     // rows per work item: the tensor core truncates when it adds into the fp32 accumulators, so the error
     // grows with the number of MMAs per accumulator -- 16 k-blocks (512 rows, 64 MMAs) per item keep it at
     // the level of an fp32 SIMT GEMM (73 k-blocks measured 5x that); more items than 2 per SM are welcome
-    int kb_per_chunk = option_value(OPT_LINEAR_VARIANT) >= 100 ? option_value(OPT_LINEAR_VARIANT) - 100 : 16;
+    int kb_per_chunk = option_value(OPT_WGRAD_CHUNK) > 0 ? option_value(OPT_WGRAD_CHUNK) : 16;   // "wgrad_chunk" option
     if (kb_per_chunk < 1) kb_per_chunk = 1;
     if (kb_per_chunk > kblocks) kb_per_chunk = kblocks;
     const long long chunks = (kblocks + kb_per_chunk - 1) / kb_per_chunk;

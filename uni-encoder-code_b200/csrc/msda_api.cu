@@ -54,9 +54,9 @@ void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 int option_value(int which) { return g_options[which].load(std::memory_order_relaxed); }
 
 int sm_count() {
-    static std::atomic<int> cached[64];
+    static std::atomic<int> cached[kMaxDevices];
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;   // launches refuse such a device
     int v = cached[dev].load(std::memory_order_relaxed);
     if (v == 0) {
         if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0)
@@ -85,9 +85,12 @@ static int option_index(const char *name) {
     if (!strcmp(name, "bwd_variant")) return OPT_BWD_VARIANT;
     if (!strcmp(name, "tile_order")) return OPT_TILE_ORDER;
     if (!strcmp(name, "ctas_per_sm")) return OPT_CTAS_PER_SM;
-    if (!strcmp(name, "whatif_drop_reds")) return OPT_WHATIF_DROP_REDS;
     if (!strcmp(name, "linear_variant")) return OPT_LINEAR_VARIANT;
+    if (!strcmp(name, "wgrad_chunk")) return OPT_WGRAD_CHUNK;
+#ifdef MSDA_PROFILE_KNOBS      // `make profile`: knobs that skip work on purpose (WRONG results), timing experiments only
+    if (!strcmp(name, "whatif_drop_reds")) return OPT_WHATIF_DROP_REDS;
     if (!strcmp(name, "whatif_linear")) return OPT_WHATIF_LINEAR;
+#endif
     return -1;
 }
 

@@ -254,19 +254,20 @@ static cudaError_t launch_bwd_cfg(const float *grad_out, const float *value, con
     auto kern = msda_bwd_d32_kernel<LP, WARPS, TILE_W, MIN_CTAS, BATCH, QPW, FUSED>;
     // the opt-in shared-memory size is a per-device function attribute: set it (and query the
     // occupancy) once per device; the values are immutable afterwards
-    static int ctas_per_sm_of[64] = {0};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
-    if (ctas_per_sm_of[dev] == 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)Cfg::kSmem);
+    static std::atomic<int> ctas_per_sm_of[kMaxDevices];
+    cudaError_t e = cudaSuccess;
+    const int dev = device_slot(&e);
+    if (dev < 0) return e;
+    int ctas_per_sm = ctas_per_sm_of[dev].load(std::memory_order_acquire);
+    if (ctas_per_sm == 0) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
         if (e != cudaSuccess) return e;
         int nb = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, WARPS * 32, Cfg::kSmem);
         if (e != cudaSuccess) return e;
-        ctas_per_sm_of[dev] = nb > 0 ? nb : 1;
+        ctas_per_sm = nb > 0 ? nb : 1;
+        ctas_per_sm_of[dev].store(ctas_per_sm, std::memory_order_release);
     }
-    const int ctas_per_sm = ctas_per_sm_of[dev];
     int per_sm = ctas_per_sm;
     const int cap = option_value(OPT_CTAS_PER_SM);
     if (cap > 0 && cap < per_sm) per_sm = cap;
@@ -274,7 +275,7 @@ static cudaError_t launch_bwd_cfg(const float *grad_out, const float *value, con
     const long long items_ub = (long long)d.N * d.M * d.Lq;
     if (blocks > items_ub) blocks = items_ub;
     if (blocks < 1) blocks = 1;
-    const int flags = (option_value(OPT_TILE_ORDER) != 1 ? 1 : 0) | (option_value(OPT_WHATIF_DROP_REDS) << 1);
+    const int flags = (option_value(OPT_TILE_ORDER) != 1 ? 1 : 0) | (whatif_value(OPT_WHATIF_DROP_REDS) << 1);
     kern<<<(unsigned)blocks, WARPS * 32, Cfg::kSmem, stream>>>(grad_out, value, shapes, lstart, loc,
                                                               attw, pr, d, flags, grad_value,
                                                               grad_loc, grad_attw, gate);

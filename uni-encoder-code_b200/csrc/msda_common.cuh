@@ -487,6 +487,24 @@ void note_launch();                   // increments the library launch counter
 int sm_count();                       // SMs of the current device (cached)
 int option_value(int which);          // tuning knobs, see msda_api.cu
 enum { OPT_FWD_VARIANT = 0, OPT_BWD_VARIANT = 1, OPT_TILE_ORDER = 2, OPT_CTAS_PER_SM = 3,
-       OPT_WHATIF_DROP_REDS = 4, OPT_LINEAR_VARIANT = 5, OPT_WHATIF_LINEAR = 6, OPT_COUNT = 7 };
+       OPT_WHATIF_DROP_REDS = 4, OPT_LINEAR_VARIANT = 5, OPT_WHATIF_LINEAR = 6, OPT_WGRAD_CHUNK = 7,
+       OPT_COUNT = 8 };
+// The two what-if knobs make kernels skip work ON PURPOSE (wrong results, timing experiments for
+// profiles/ only): they exist only in a library built with -DMSDA_PROFILE_KNOBS (`make profile`);
+// in the shipped library they read as 0 and cannot be set.
+#ifdef MSDA_PROFILE_KNOBS
+inline int whatif_value(int which) { return option_value(which); }
+#else
+inline int whatif_value(int) { return 0; }
+#endif
+// Slot of the current device in the per-device launch-attribute caches, -1 with *err set when the
+// device cannot be determined or its ordinal is beyond kMaxDevices (never aliased onto device 0).
+inline int device_slot(cudaError_t *err) {
+    int dev = 0;
+    *err = cudaGetDevice(&dev);
+    if (*err != cudaSuccess) return -1;
+    if (dev < 0 || dev >= kMaxDevices) { *err = cudaErrorInvalidDevice; return -1; }
+    return dev;
+}
 
 }  // namespace msda

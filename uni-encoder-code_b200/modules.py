@@ -34,6 +34,46 @@ from .functions import AddLayerNormFunction, LinearTF32x3Function, MSDeformAttnF
 CoreFn = Callable[..., torch.Tensor]
 
 
+class ShapeCache:
+    """Small LRU for shape-keyed device constants (position embeddings, reference points, level
+    tensors).  The reference recomputes these on every forward and holds nothing; caching them is
+    what makes the decoder CUDA-graph capturable, but datasets with variable resolution (ADE20K,
+    COCO) present thousands of distinct pyramids, so only the most recent `maxsize` shapes stay
+    resident -- a deployment that captures graphs uses a fixed set of shapes well below that."""
+
+    def __init__(self, maxsize: int = 8):
+        from collections import OrderedDict
+        self.maxsize, self._d = maxsize, OrderedDict()
+
+    def get(self, key):
+        hit = self._d.get(key)
+        if hit is not None:
+            self._d.move_to_end(key)
+        return hit
+
+    def put(self, key, value):
+        self._d[key] = value
+        self._d.move_to_end(key)
+        while len(self._d) > self.maxsize:
+            self._d.popitem(last=False)
+        return value
+
+    def __len__(self):
+        return len(self._d)
+
+    def __contains__(self, key):
+        return key in self._d
+
+    def clear(self):
+        self._d.clear()
+
+
+def _version_of(t: torch.Tensor) -> int:
+    """In-place modification counter for cache keys; inference tensors (created under
+    torch.inference_mode()) do not track one -- reading ._version on them raises."""
+    return -1 if t.is_inference() else t._version
+
+
 def _linear(layer: nn.Linear, x, impl: str, relu: bool = False):
     """``layer(x)`` (+ ReLU).  impl == "tf32x3" selects the inference kernels of SURVEY 8f.3 (this GEMM and the
     fused residual + LayerNorm of `_add_norm`): in inference (autograd off) the fp32 GEMM runs on the
@@ -55,10 +95,11 @@ def _linear(layer: nn.Linear, x, impl: str, relu: bool = False):
 def _add_norm(norm: nn.LayerNorm, x, sublayer_out, impl: str):
     """``norm(x + sublayer_out)``; impl == "tf32x3" (inference): one fused pass (ops.add_layernorm)."""
     if impl == "tf32x3" and not torch.is_grad_enabled() and norm.elementwise_affine \
-            and ops.add_layernorm_supported(x, sublayer_out, norm.weight):
+            and ops.add_layernorm_supported(x, sublayer_out, norm.weight, norm.bias, need_bias=True):
         return ops.add_layernorm(x, sublayer_out, norm.weight, norm.bias, norm.eps)
     if impl == "tf32x3" and torch.is_grad_enabled() and norm.elementwise_affine \
-            and sublayer_out.is_contiguous() and AddLayerNormFunction.supported(x, sublayer_out, norm.weight):
+            and norm.bias is not None and sublayer_out.is_contiguous() \
+            and AddLayerNormFunction.supported(x, sublayer_out, norm.weight):
         return AddLayerNormFunction.apply(x, sublayer_out, norm.weight, norm.bias, norm.eps)
     return norm(x + sublayer_out)
 
@@ -193,7 +234,7 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
         return self.forward_ffn(_add_norm(self.norm1, src, self.dropout1(attn), self.linear))
 
 
-_REF_CACHE = {}
+_REF_CACHE = ShapeCache()
 
 
 def reference_points_for(levels: Sequence[Tuple[int, int]], device, dtype=torch.float32):
@@ -214,12 +255,11 @@ def reference_points_for(levels: Sequence[Tuple[int, int]], device, dtype=torch.
             yy, xx = torch.meshgrid(ys, xs, indexing="ij")
             pts.append(torch.stack((xx.reshape(-1), yy.reshape(-1)), -1))
         ref = torch.cat(pts, 0)
-        hit = ref[None, :, None, :].expand(1, ref.shape[0], len(key[0]), 2).contiguous().to(device)
-        _REF_CACHE[key] = hit
+        hit = _REF_CACHE.put(key, ref[None, :, None, :].expand(1, ref.shape[0], len(key[0]), 2).contiguous().to(device))
     return hit
 
 
-_LEVEL_CACHE = {}
+_LEVEL_CACHE = ShapeCache()
 
 
 def level_tensors_for(levels: Sequence[Tuple[int, int]], device):
@@ -231,7 +271,7 @@ def level_tensors_for(levels: Sequence[Tuple[int, int]], device):
     if hit is None:
         shapes = torch.tensor(key[0], dtype=torch.long)
         lsi = torch.cat((shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]))
-        hit = _LEVEL_CACHE[key] = (shapes.to(device), lsi.to(device))
+        hit = _LEVEL_CACHE.put(key, (shapes.to(device), lsi.to(device)))
     return hit
 
 
@@ -303,8 +343,8 @@ class MSDeformAttnTransformerEncoderOnly(nn.Module):
         else:
             # inference: position embedding + level embedding depends on the shapes and on one parameter only;
             # built once per (position tensors, level_embed version) instead of on every call
-            key = (tuple((p.data_ptr(), p._version, tuple(p.shape), tuple(p.stride())) for p in pos_embeds),
-                   self.level_embed.data_ptr(), self.level_embed._version)
+            key = (tuple((p.data_ptr(), _version_of(p), tuple(p.shape), tuple(p.stride())) for p in pos_embeds),
+                   self.level_embed.data_ptr(), _version_of(self.level_embed))
             if getattr(self, "_pos_cache_key", None) != key:
                 # the position tensors are kept referenced so their memory cannot be handed to other data
                 self._pos_cache_key, self._pos_cache_src = key, list(pos_embeds)

@@ -246,12 +246,15 @@ def ms_deform_attn_fused_backward(value, spatial_shapes, level_start_index, refe
 def linear_tf32x3_supported(x, weight) -> bool:
     return (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32
             and weight.dtype == torch.float32 and weight.dim() == 2 and x.size(-1) == weight.size(1)
+            and weight.is_contiguous() and weight.device == x.device
             and weight.size(1) % 32 == 0 and weight.size(0) % 4 == 0 and x.numel() > 0)
 
 
 def linear_tf32x3(x, weight, bias=None, relu=False, split_weight_in_kernel=False):
     """``F.linear(x, weight, bias)`` (then ``relu`` if set) for fp32 CUDA tensors; ``x`` [..., in],
-    ``weight`` [out, in] with in % 32 == 0 and out % 4 == 0.  ``split_weight_in_kernel``: no pre-pass over
+    ``weight`` [out, in] with in % 32 == 0 and out % 4 == 0.  Non-finite inputs give non-finite outputs in
+    the affected rows, but an infinite input may come out as NaN where F.linear returns +-inf (the
+    error-compensated split forms inf - inf and inf * w_lo of either sign).  ``split_weight_in_kernel``: no pre-pass over
     (and no workspace for) the weight -- for a one-shot "weight" such as transposed activations."""
     if not x.is_cuda:
         raise RuntimeError("Not implemented on the CPU")
@@ -279,10 +282,16 @@ def linear_tf32x3(x, weight, bias=None, relu=False, split_weight_in_kernel=False
     return y
 
 
-def add_layernorm_supported(x, residual, weight) -> bool:
+def add_layernorm_supported(x, residual, weight, bias=None, need_bias=False) -> bool:
+    """Whether the fused residual + LayerNorm kernels cover these tensors; callers pass the norm's bias
+    with need_bias=True so that an nn.LayerNorm(bias=False), or affine parameters that are not
+    contiguous fp32 tensors on x's device, take torch's own path."""
+    def affine_ok(t):
+        return (isinstance(t, torch.Tensor) and t.dtype == torch.float32 and t.is_contiguous()
+                and t.device == x.device and t.numel() == x.size(-1))
     return (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
-            and x.size(-1) in (128, 256, 384, 512) and x.numel() > 0 and weight is not None
-            and weight.dtype == torch.float32 and weight.numel() == x.size(-1)
+            and x.size(-1) in (128, 256, 384, 512) and x.numel() > 0 and affine_ok(weight)
+            and (affine_ok(bias) if (need_bias or bias is not None) else True)
             and (residual is None or (residual.shape == x.shape and residual.is_contiguous()
                                       and residual.dtype == torch.float32 and residual.device == x.device)))
 

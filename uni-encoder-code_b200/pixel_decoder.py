@@ -23,7 +23,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .modules import CoreFn, MSDeformAttnTransformerEncoderOnly
+from .modules import CoreFn, MSDeformAttnTransformerEncoderOnly, ShapeCache
 
 
 class PositionEmbeddingSine(nn.Module):
@@ -35,7 +35,7 @@ class PositionEmbeddingSine(nn.Module):
             raise ValueError("normalize should be True if scale is passed")
         self.num_pos_feats, self.temperature, self.normalize = num_pos_feats, temperature, normalize
         self.scale = 2 * math.pi if scale is None else scale
-        self._cache = {}
+        self._cache = ShapeCache()        # per instance, most recent shapes only
 
     def _build(self, H, W, device):
         ones = torch.ones((1, H, W), dtype=torch.float32, device=device)
@@ -57,7 +57,7 @@ class PositionEmbeddingSine(nn.Module):
         key = (x.shape[2], x.shape[3], str(x.device))
         pos = self._cache.get(key)
         if pos is None:
-            pos = self._cache[key] = self._build(x.shape[2], x.shape[3], x.device)
+            pos = self._cache.put(key, self._build(x.shape[2], x.shape[3], x.device))
         return pos.expand(x.shape[0], -1, -1, -1)
 
 
