@@ -131,3 +131,28 @@ def test_fp32_geometry_mode(oracle, pkg):
     mixed = oracle.forward(*a, geometry=np.float32)
     assert np.abs(oracle.forward(*a, dtype=np.float32) - mixed).max() <= 2e-6
     assert np.abs(oracle.forward(*a) - mixed).max() <= 1e-4
+
+
+def test_reference_binary_rounds_the_pixel_coordinate_with_one_fma():
+    """The bit-exact contract depends on how nvcc contracts the reference's `loc * size - 0.5`
+    (cuh:290-291): the reference op built for sm_100 (baseline/build_reference_cuda.py) must show a
+    single `FFMA ..., -0.5` per coordinate in its forward and D=32 backward kernels, which is what
+    decompose() and the fp32-geometry oracle reproduce (profiles/r2_reference_sass_ffma.md)."""
+    import os
+    import shutil
+    import subprocess
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "ref_msda_cuda.so")
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not (os.path.exists(so) and os.path.exists(cuobjdump)):
+        pytest.skip("reference CUDA op or cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", so], capture_output=True, text=True, check=True).stdout
+    per_kernel, cur = {}, None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            cur = line.split("Function :")[1].strip()
+        elif cur and "FFMA" in line and "-0.5" in line:
+            per_kernel[cur] = per_kernel.get(cur, 0) + 1
+    fwd = [k for k in per_kernel if "ms_deformable_im2col_gpu_kernelIf" in k]
+    bwd = [k for k in per_kernel if "blocksize_aware_reduce_v1IfLj32" in k]
+    assert fwd and bwd, sorted(per_kernel)[:5]
+    assert all(per_kernel[k] >= 2 for k in fwd + bwd)      # x and y
