@@ -168,6 +168,21 @@ int msda_b200_add_layernorm_backward_f32(const float *grad_y, const float *x, co
                                          float *grad_beta, long long rows, int cols, float eps, void *stream);
 
 /*
+ * GroupNorm over an NCHW fp32 map with the pixel decoder's epilogues fused in (SURVEY 8f.4;
+ * msdeformattn.py:233-248, :286-300, :369-379):
+ *     y = group_norm(x, groups, gamma, beta, eps)            torch.nn.functional.group_norm semantics
+ *     if relu:        y = max(y, 0)
+ *     if up != NULL:  y += bilinear up-sampling of up[N, C, up_h, up_w] to H x W, align_corners=False
+ * `workspace` must hold msda_b200_group_norm_workspace_bytes(N, groups) bytes (per-group partial sums;
+ * its contents are meaningless before and after the call).  Needs H*W and W to be multiples of 4 and
+ * 16-byte aligned x / y; MSDA_ERR_UNSUPPORTED otherwise.  Inference only (no backward).
+ */
+int msda_b200_group_norm_nchw_f32(const float *x, const float *gamma, const float *beta, float *y, int batch,
+                                  int channels, int height, int width, int groups, float eps, int relu,
+                                  const float *up, int up_h, int up_w, void *workspace, void *stream);
+long long msda_b200_group_norm_workspace_bytes(int batch, int groups);
+
+/*
  * Weight and bias gradient of the same Linear (torch autograd semantics), 3 x TF32 on the tensor cores
  * without transposing the operands in memory:
  *     grad_weight[out_features, in_features] = grad_y[rows, out_features]^T * x[rows, in_features]

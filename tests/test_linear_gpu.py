@@ -323,3 +323,56 @@ def test_linear_and_wgrad_random_shapes(pkg):
         gw, gb = pkg.ops.linear_wgrad(gy, xs)
         assert torch.equal(gw, (gy.double().t() @ xs.double()).float()), (rows, out_f, xs.shape)
         assert torch.equal(gb, gy.double().sum(0).float())
+
+
+# ---------------------------------------------------------------- fused GroupNorm
+@pytest.mark.parametrize("shape,groups,relu,up", [
+    ((2, 64, 12, 20), 32, False, None),          # input projection of the small decoder
+    ((2, 256, 16, 24), 32, True, None),          # output convolution: GroupNorm + ReLU
+    ((3, 256, 24, 40), 32, False, (12, 20)),     # lateral: GroupNorm + up-sampled add (x2)
+    ((1, 64, 10, 28), 8, True, (7, 9)),          # odd up-sampling ratio, 8 channels per group
+    ((2, 256, 96, 160), 32, False, (48, 80)),    # larger map: several parts per plane
+])
+def test_group_norm_kernel_matches_torch(pkg, shape, groups, relu, up):
+    """ops.group_norm == F.group_norm [+ ReLU] [+ F.interpolate(bilinear, align_corners=False)] against
+    an fp64 evaluation, no worse than torch's own fp32 kernels (x 2 + 1e-6)."""
+    gen = torch.Generator().manual_seed(hash((shape, groups)) % 1000)
+    x = (torch.randn(shape, generator=gen) * 2.0 + 3.0).to(DEV)           # mean >> 0: the cancellation case
+    norm = torch.nn.GroupNorm(groups, shape[1]).to(DEV)
+    with torch.no_grad():
+        norm.weight.normal_(1.0, 0.3, generator=None)
+        norm.bias.normal_(0.0, 0.5)
+    u = torch.randn(shape[0], shape[1], *up, generator=gen).to(DEV) if up else None
+
+    def ref(dtype):
+        n = torch.nn.GroupNorm(groups, shape[1]).to(DEV, dtype)
+        n.load_state_dict({k: v.to(dtype) for k, v in norm.state_dict().items()})
+        r = n(x.to(dtype))
+        if relu:
+            r = torch.relu(r)
+        if u is not None:
+            r = r + torch.nn.functional.interpolate(u.to(dtype), size=shape[-2:], mode="bilinear", align_corners=False)
+        return r
+    with torch.no_grad():
+        n0 = pkg.launch_count()
+        got = pkg.group_norm(x, norm, relu=relu, up=u)
+        assert pkg.launch_count() - n0 == 2
+        want64, want32 = ref(torch.float64), ref(torch.float32)
+    err = (got.double() - want64).abs().max().item()
+    err32 = (want32.double() - want64).abs().max().item()
+    assert err <= 2 * err32 + 1e-6, (err, err32)
+    with torch.no_grad():                       # deterministic (no atomics)
+        assert torch.equal(got, pkg.group_norm(x, norm, relu=relu, up=u))
+
+
+def test_group_norm_unsupported_shapes_fall_back_in_the_mirror(pkg):
+    norm = torch.nn.GroupNorm(4, 8).to(DEV)
+    x = torch.randn(1, 8, 5, 7, device=DEV)                 # H*W not a multiple of 4
+    assert not pkg.ops.group_norm_supported(x, norm)
+    with pytest.raises(RuntimeError, match="group_norm needs"):
+        pkg.group_norm(x, norm)
+    conv = pkg.pixel_decoder._ConvNormAct(8, 8, kernel_size=1, norm=norm, activation=torch.nn.functional.relu).to(DEV)
+    with torch.no_grad():
+        a = conv(x, fused_norm=True)
+        b = torch.relu(norm(torch.nn.functional.conv2d(x, conv.weight, conv.bias)))
+    assert torch.allclose(a, b, atol=1e-6)

@@ -44,6 +44,9 @@ cudaError_t launch_add_layernorm_bwd(const float *, const float *, const float *
 cudaError_t launch_linear_wgrad(const float *, const float *, float *, float *, long long, int, int, cudaStream_t,
                                 bool *handled);
 cudaError_t launch_transpose(const float *, float *, long long, int, cudaStream_t);
+cudaError_t launch_group_norm(const float *, const float *, const float *, float *, int, int, int, int, int, float, int,
+                              const float *, int, int, double *, cudaStream_t, bool *handled);
+int group_norm_workspace_doubles(int N, int groups);
 cudaError_t launch_debug_indices(const int64_t *, const int64_t *, const float *, const Dims &,
                                  int32_t *, int64_t *, cudaStream_t);
 
@@ -311,6 +314,23 @@ int msda_b200_linear_wgrad_f32(const float *grad_y, const float *x, float *grad_
                                         (cudaStream_t)stream, &handled);
     if (e == cudaSuccess && !handled) return MSDA_ERR_UNSUPPORTED;
     return (int)e;
+}
+
+int msda_b200_group_norm_nchw_f32(const float *x, const float *gamma, const float *beta, float *y, int batch,
+                                  int channels, int height, int width, int groups, float eps, int relu,
+                                  const float *up, int up_h, int up_w, void *workspace, void *stream) {
+    if (!x || !gamma || !beta || !y || !workspace) return MSDA_ERR_NULL_POINTER;
+    if (batch <= 0 || channels <= 0 || height <= 0 || width <= 0 || groups <= 0) return MSDA_ERR_BAD_SHAPE;
+    bool handled = false;
+    cudaError_t e = launch_group_norm(x, gamma, beta, y, batch, channels, height, width, groups, eps, relu, up, up_h,
+                                      up_w, static_cast<double *>(workspace), (cudaStream_t)stream, &handled);
+    if (e == cudaSuccess && !handled) return MSDA_ERR_UNSUPPORTED;
+    return (int)e;
+}
+
+long long msda_b200_group_norm_workspace_bytes(int batch, int groups) {
+    if (batch <= 0 || groups <= 0) return 0;
+    return (long long)group_norm_workspace_doubles(batch, groups) * (long long)sizeof(double);
 }
 
 int msda_b200_transpose_f32(const float *x, float *y, long long rows, int cols, void *stream) {

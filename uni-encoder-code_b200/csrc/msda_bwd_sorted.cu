@@ -721,6 +721,9 @@ cudaError_t launch_bwd_sorted(const float *grad_out, const float *value, const i
                 case 23: return MSDA_SORTED(12, 16, 16, 2, 128, 4096, 4, 4);   // 4 lanes + look-ahead L1 prefetch
                 case 24: return MSDA_SORTED(12, 12, 16, 2, 128, 4096, 4, 0);   // 12 warps, 80 registers
                 case 25: return MSDA_SORTED(12, 8, 8, 4, 64, 2048, 4, 0);      // 64-query tiles, 4 CTAs of 8 warps
+                case 26: return MSDA_SORTED(12, 16, 8, 2, 64, 2048, 4, 4);     // 64-query tiles, 2 CTAs of 16 warps (L1 ~120 KB) + look-ahead
+                case 27: return MSDA_SORTED(12, 16, 8, 2, 64, 2048, 4, 0);     // the same without look-ahead
+                case 28: return MSDA_SORTED(12, 16, 8, 2, 64, 2048, 8, 4);     // 8 lanes, look-ahead, large L1
                 default: return MSDA_SORTED(12, 16, 16, 2, 128, 4096, 4, 0);   // 4 lanes per record (32 bytes each)
             }
         case 16: return MSDA_SORTED(16, 16, 16, 1, 128, 4096, 8, 0);

@@ -315,6 +315,43 @@ def add_layernorm(x, residual, weight, bias, eps=1e-5):
     return y
 
 
+def group_norm_supported(x, norm, up=None) -> bool:
+    """Whether the fused GroupNorm kernel covers `norm(x)` (x: NCHW fp32 CUDA, contiguous)."""
+    ok = (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+          and x.is_contiguous() and x.numel() > 0 and isinstance(norm, torch.nn.GroupNorm) and norm.affine
+          and norm.weight is not None and norm.bias is not None and norm.weight.device == x.device
+          and norm.weight.dtype == torch.float32 and norm.weight.is_contiguous() and norm.bias.is_contiguous()
+          and x.size(1) == norm.num_channels and (x.size(2) * x.size(3)) % 4 == 0 and x.size(3) % 4 == 0
+          and x.data_ptr() % 16 == 0)
+    if ok and up is not None:
+        ok = (up.is_cuda and up.dtype == torch.float32 and up.dim() == 4 and up.is_contiguous()
+              and up.device == x.device and up.shape[:2] == x.shape[:2])
+    return ok
+
+
+def group_norm(x, norm, relu=False, up=None):
+    """``norm(x)`` for an ``nn.GroupNorm`` on an NCHW fp32 CUDA map, optionally followed by ReLU and by
+    ``+ F.interpolate(up, size=x.shape[-2:], mode="bilinear", align_corners=False)`` -- the epilogues of the
+    pixel decoder's input projections and FPN level (msdeformattn.py:233-248, :369-379) -- in two passes
+    over x (statistics, apply) instead of torch's four to six kernels.  Inference only (no backward)."""
+    if not group_norm_supported(x, norm, up):
+        raise RuntimeError("group_norm needs a contiguous NCHW fp32 CUDA map with H*W and W multiples of 4, "
+                           "an affine nn.GroupNorm on the same device and, if given, a contiguous `up` map "
+                           "with the same batch and channels")
+    N, C, H, W = x.shape
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        ws = torch.empty(int(_lib.lib.msda_b200_group_norm_workspace_bytes(N, norm.num_groups)), dtype=torch.uint8,
+                         device=x.device)
+        rc = _lib.lib.msda_b200_group_norm_nchw_f32(
+            x.data_ptr(), norm.weight.data_ptr(), norm.bias.data_ptr(), y.data_ptr(), N, C, H, W, norm.num_groups,
+            float(norm.eps), int(bool(relu)), up.data_ptr() if up is not None else None,
+            up.size(2) if up is not None else 0, up.size(3) if up is not None else 0, ws.data_ptr(),
+            torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(rc, "group_norm")
+    return y
+
+
 def transpose2d(x):
     """``x.t().contiguous()`` for a contiguous fp32 CUDA matrix (operand preparation for the weight-gradient GEMM)."""
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous() and x.numel() > 0):

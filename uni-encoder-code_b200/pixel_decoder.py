@@ -23,6 +23,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from . import ops
 from .modules import CoreFn, MSDeformAttnTransformerEncoderOnly, ShapeCache
 
 
@@ -69,11 +70,20 @@ class _ConvNormAct(nn.Conv2d):
         super().__init__(*args, **kwargs)
         self.norm, self.activation = norm, activation
 
-    def forward(self, x):
+    def forward(self, x, up=None, fused_norm=False):
+        """conv -> norm -> activation (-> + bilinear up-sampling of `up`, the FPN top-down add of
+        msdeformattn.py:372-376).  `fused_norm` (inference, GroupNorm, fp32 CUDA): the norm, the ReLU and
+        the up-sampled add run as one statistics + one apply kernel (ops.group_norm)."""
         x = super().forward(x)
+        if fused_norm and not torch.is_grad_enabled() and self.activation in (None, F.relu) \
+                and ops.group_norm_supported(x, self.norm, up):
+            return ops.group_norm(x, self.norm, relu=self.activation is F.relu, up=up)
         if self.norm is not None:
             x = self.norm(x)
-        return x if self.activation is None else self.activation(x)
+        x = x if self.activation is None else self.activation(x)
+        if up is not None:
+            x = x + F.interpolate(up, size=x.shape[-2:], mode="bilinear", align_corners=False)
+        return x
 
 
 def _norm(kind, channels):
@@ -116,6 +126,7 @@ class MSDeformAttnPixelDecoder(nn.Module):
             dim_feedforward=transformer_dim_feedforward, num_encoder_layers=transformer_enc_layers,
             num_feature_levels=self.transformer_num_feature_levels, core=core, fused=fused, linear=linear)
         self.pe_layer = PositionEmbeddingSine(conv_dim // 2, normalize=True)
+        self.linear = linear
         self.mask_dim = mask_dim
         self.mask_features = nn.Conv2d(conv_dim, mask_dim, kernel_size=1, stride=1, padding=0)
         _c2_xavier_fill(self.mask_features)
@@ -141,9 +152,15 @@ class MSDeformAttnPixelDecoder(nn.Module):
         as msdeformattn.py:336-386 (autocast disabled, inputs promoted to fp32)."""
         with torch.autocast(device_type=next(iter(features.values())).device.type, enabled=False):
             srcs, pos = [], []
+            fused_norm = self.linear == "tf32x3"        # the inference kernels of SURVEY 8f.3 / 8f.4
             for idx, name in enumerate(self.transformer_in_features[::-1]):
                 x = features[name].float()
-                srcs.append(self.input_proj[idx](x))
+                proj = self.input_proj[idx]
+                y = proj[0](x)
+                if fused_norm and not torch.is_grad_enabled() and ops.group_norm_supported(y, proj[1]):
+                    srcs.append(ops.group_norm(y, proj[1]))
+                else:
+                    srcs.append(proj[1](y))
                 pos.append(self.pe_layer(x))
             memory, _, _, _ = self.transformer(srcs, pos)
             n = memory.shape[0]
@@ -151,7 +168,6 @@ class MSDeformAttnPixelDecoder(nn.Module):
             out: List[torch.Tensor] = [z.transpose(1, 2).reshape(n, -1, h, w) for z, (h, w) in
                                        zip(memory.split([h * w for h, w in levels], dim=1), levels)]
             for idx, name in enumerate(self.in_features[:self.num_fpn_levels][::-1]):
-                cur = self.lateral_convs[idx](features[name].float())
-                y = cur + F.interpolate(out[-1], size=cur.shape[-2:], mode="bilinear", align_corners=False)
-                out.append(self.output_convs[idx](y))
+                y = self.lateral_convs[idx](features[name].float(), up=out[-1].contiguous(), fused_norm=fused_norm)
+                out.append(self.output_convs[idx](y, fused_norm=fused_norm))
             return self.mask_features(out[-1]), out[0], out[:self.oneformer_num_feature_levels]
