@@ -57,7 +57,17 @@ def reference_composition(oracle, c):
     ([(7, 9), (5, 3), (4, 4), (2, 2)], 2, 2, 4, True),   # L*P = 16
     ([(9, 13)], 3, 2, 4, True),                          # L*P = 4
 ])
-def test_fused_matches_unfused_composition(pkg, oracle, levels, batch, heads, points, shared_ref):
+@pytest.mark.parametrize("bwd_variant", [0, 20, 2])   # probe-gated default, merging kernel forced, per-row kernel forced
+def test_fused_matches_unfused_composition(pkg, oracle, levels, batch, heads, points, shared_ref, bwd_variant):
+    pkg.set_option("bwd_variant", bwd_variant)
+    try:
+        _fused_matches_unfused_composition(pkg, oracle, levels, batch, heads, points, shared_ref,
+                                           launches=3 if bwd_variant == 0 else 2)
+    finally:
+        pkg.set_option("bwd_variant", 0)
+
+
+def _fused_matches_unfused_composition(pkg, oracle, levels, batch, heads, points, shared_ref, launches):
     c = make_case(pkg, levels, batch, heads, points, shared_ref, seed=21)
     d = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in c.items()}
     value = d["value"].clone().requires_grad_(True)
@@ -67,7 +77,7 @@ def test_fused_matches_unfused_composition(pkg, oracle, levels, batch, heads, po
     out = pkg.MSDeformAttnFusedFunction.apply(value, d["shapes"], d["lsi"], d["ref"], off, logits)
     out.backward(d["grad_out"])
     torch.cuda.synchronize()
-    assert pkg.launch_count() - n0 == 2
+    assert pkg.launch_count() - n0 == launches   # forward + backward (default: merging + per-row kernel behind the probe)
     ref_out, ref_gv, ref_goff, ref_glog = reference_composition(oracle, c)
     assert np.abs(out.detach().double().cpu().numpy() - ref_out).max() <= 2 * FWD_ABS_TOL
     assert rel_err(value.grad.cpu().numpy(), ref_gv.reshape(value.shape)) <= GRAD_REL_TOL
@@ -102,7 +112,7 @@ def test_fused_encoder_matches_reference_golden(pkg):
     memory = m(srcs, pos)[0]
     assert np.abs(memory.detach().double().cpu().numpy() - g["memory"]).max() <= 2e-4
     (memory * torch.from_numpy(g["cotangent"]).float().cuda()).sum().backward()
-    assert pkg.launch_count() - n0 == 4           # 2 layers x (fused forward + fused backward)
+    assert pkg.launch_count() - n0 == 6           # 2 layers x (fused forward + the two gated fused backward kernels)
     ref = g["grad_src2"]
     assert np.abs(srcs[2].grad.double().cpu().numpy() - ref).max() <= 2e-4 * max(1.0, np.abs(ref).max())
 

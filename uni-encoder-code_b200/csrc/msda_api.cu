@@ -28,7 +28,10 @@ cudaError_t launch_fwd_d32_fused(const float *, const int64_t *, const int64_t *
                                  cudaStream_t, bool *handled);
 cudaError_t launch_bwd_d32_fused(const float *, const float *, const int64_t *, const int64_t *,
                                  const float *, long long, const float *, const float *,
-                                 const Dims &, float *, float *, float *, cudaStream_t, bool *handled);
+                                 const Dims &, float *, float *, float *, cudaStream_t, bool *handled, int gate);
+cudaError_t launch_bwd_sorted_fused(const float *, const float *, const int64_t *, const int64_t *,
+                                    const float *, long long, const float *, const float *,
+                                    const Dims &, float *, float *, float *, cudaStream_t, bool *handled, int gate);
 template <typename T>
 cudaError_t launch_fwd_generic(const T *, const int64_t *, const int64_t *, const T *, const T *,
                                const Dims &, T *, cudaStream_t);
@@ -264,10 +267,26 @@ int msda_b200_fused_backward_f32(const float *grad_output, const float *value,
     if (ref_batch_stride != 0 && ref_batch_stride != (long long)num_query * num_levels * 2)
         return MSDA_ERR_BAD_SHAPE;
     bool handled = false;
-    cudaError_t e = launch_bwd_d32_fused(grad_output, value, spatial_shapes, level_start,
-                                         reference_points, ref_batch_stride, sampling_offsets,
-                                         attn_logits, d, grad_value, grad_sampling_offsets,
-                                         grad_attn_logits, (cudaStream_t)stream, &handled);
+    cudaError_t e = cudaSuccess;
+    const int variant = option_value(OPT_BWD_VARIANT);
+    const bool aligned = aligned16(value) && aligned16(grad_output) && aligned16(grad_value) &&
+                         aligned8(sampling_offsets) && aligned8(grad_sampling_offsets) && aligned8(reference_points);
+    if (!aligned) return MSDA_ERR_UNSUPPORTED;
+    // as in msda_b200_backward_f32: merging kernel and per-row kernel behind the same location probe
+    // (here on the raw offsets), or one of them forced by "bwd_variant" (20..39 / 1..8)
+    int gate = GATE_NONE;
+    if ((variant == 0 || (variant >= 20 && variant < 40)) && bwd_sorted_applies(value, grad_value, d)) {
+        e = launch_bwd_sorted_fused(grad_output, value, spatial_shapes, level_start, reference_points,
+                                    ref_batch_stride, sampling_offsets, attn_logits, d, grad_value,
+                                    grad_sampling_offsets, grad_attn_logits, (cudaStream_t)stream, &handled,
+                                    variant == 0 ? GATE_RUN_IF_LOCAL : GATE_NONE);
+        if (variant == 0 && handled) { handled = false; gate = GATE_RUN_IF_SPREAD; }
+    }
+    if (e == cudaSuccess && !handled)
+        e = launch_bwd_d32_fused(grad_output, value, spatial_shapes, level_start,
+                                 reference_points, ref_batch_stride, sampling_offsets,
+                                 attn_logits, d, grad_value, grad_sampling_offsets,
+                                 grad_attn_logits, (cudaStream_t)stream, &handled, gate);
     if (e == cudaSuccess && !handled) return MSDA_ERR_UNSUPPORTED;
     return (int)e;
 }

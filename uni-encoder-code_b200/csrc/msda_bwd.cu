@@ -81,7 +81,7 @@ msda_bwd_d32_kernel(const float *__restrict__ grad_out, const float *__restrict_
     const int drop_pairs = flags >> 1;
     __syncthreads();
     // launched next to the merging kernel (msda_bwd_sorted.cu): the shared probe of the locations decides
-    if (gate == GATE_RUN_IF_SPREAD && probe_points_stay_local(lt, loc, d.N, d.Lq, d.M, d.L, d.P)) return;
+    if (gate == GATE_RUN_IF_SPREAD && probe_points_stay_local<FUSED>(lt, loc, d.N, d.Lq, d.M, d.L, d.P)) return;
 
     const int M = d.M;
     const long long items = (long long)d.N * M * lt.groups;
@@ -330,7 +330,7 @@ cudaError_t launch_bwd_d32(const float *grad_out, const float *value, const int6
 cudaError_t launch_bwd_d32_fused(const float *grad_out, const float *value, const int64_t *shapes,
                                  const int64_t *lstart, const float *ref, long long ref_bstride,
                                  const float *off, const float *logits, const Dims &d, float *gv,
-                                 float *g_off, float *g_logits, cudaStream_t st, bool *handled) {
+                                 float *g_off, float *g_logits, cudaStream_t st, bool *handled, int gate) {
     *handled = true;
     const Producers pr{ref, ref_bstride};
     if (d.D != 32 || (long long)d.S * d.M * 8 >= 0x7fffffffLL) {
@@ -338,7 +338,7 @@ cudaError_t launch_bwd_d32_fused(const float *grad_out, const float *value, cons
         return cudaSuccess;
     }
 #define MSDA_BWD_FUSED(LPV) \
-    launch_bwd_cfg<LPV, 16, 16, 2, 1, 8, true>(grad_out, value, shapes, lstart, off, logits, d, gv, g_off, g_logits, st, pr)
+    launch_bwd_cfg<LPV, 16, 16, 2, 1, 8, true>(grad_out, value, shapes, lstart, off, logits, d, gv, g_off, g_logits, st, pr, gate)
     switch (d.L * d.P) {
         case 4: return MSDA_BWD_FUSED(4);
         case 8: return MSDA_BWD_FUSED(8);

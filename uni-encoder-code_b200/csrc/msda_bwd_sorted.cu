@@ -310,11 +310,15 @@ __device__ __forceinline__ void red_add_f4(float4 *p, const float4 v) {
 // PFV: bit 0 = the first thread that counts a window pixel prefetches its value row into L2,
 //      bit 1 = also every corner outside the windows, bit 2 = the merge loop looks one body ahead
 //      and prefetches the rows of the pixel runs that start there into L1
-template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int TILE_Q, int SLOTS, int GW, int PFV>
+// FUSED: `loc` / `attw` are the raw sampling offsets / attention logits and `grad_loc` / `grad_attw`
+//      receive the gradients with respect to THEM (as in msda_bwd.cu): pass A forms
+//      location = ref + offset / (W, H) and the softmax of the (query, head)'s L*P logits (exchanged
+//      through shared memory), the epilogue applies 1 / (W, H) and the softmax backward.
+template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int TILE_Q, int SLOTS, int GW, int PFV, bool FUSED>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
 msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restrict__ value,
                        const int64_t *__restrict__ shapes, const int64_t *__restrict__ lstart,
-                       const float *__restrict__ loc, const float *__restrict__ attw, const Dims d,
+                       const float *__restrict__ loc, const float *__restrict__ attw, const Producers pr, const Dims d,
                        const int flags, float *__restrict__ grad_value, float *__restrict__ grad_loc,
                        float *__restrict__ grad_attw, const int gate) {
     using Cfg = SortCfg<LP, WARPS, TILE_W, TILE_Q, SLOTS>;
@@ -332,6 +336,12 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
     float4 *go_sm = reinterpret_cast<float4 *>(smem_raw + Cfg::kRecBytes);
     float *dsm = reinterpret_cast<float *>(smem_raw + Cfg::kRecBytes + Cfg::kGoBytes);
     uint32_t *cnt = reinterpret_cast<uint32_t *>(smem_raw + Cfg::kRecBytes + Cfg::kGoBytes + Cfg::kDBytes);
+    // FUSED: softmax weight of every point of the item, pass A -> epilogue (entry s is private to the
+    // thread that owns point s); logits / weighted gradients are exchanged through the record array,
+    // which is free in pass A and after the merge: two disjoint pieces, see the barriers' comments
+    float *aw_sm = reinterpret_cast<float *>(smem_raw + Cfg::kSmem);
+    float *scr_a = reinterpret_cast<float *>(rec), *scr_e = reinterpret_cast<float *>(rec) + Cfg::kPoints;
+    static_assert(!FUSED || (LP % 4 == 0 && 2 * Cfg::kPoints * sizeof(float) <= Cfg::kRecBytes), "softmax scratch");
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -339,7 +349,7 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
     for (int i = tid; i < kSortSlots; i += NT) cnt[i] = 0u;   // invariant: zero outside pass A .. pass B
     __syncthreads();
     // launched next to the per-row reduction kernel: the shared probe of the locations decides
-    if (gate == GATE_RUN_IF_LOCAL && !probe_points_stay_local(lt, loc, d.N, d.Lq, d.M, d.L, d.P)) return;
+    if (gate == GATE_RUN_IF_LOCAL && !probe_points_stay_local<FUSED>(lt, loc, d.N, d.Lq, d.M, d.L, d.P)) return;
 
     const int M = d.M, L = d.L, Lq = d.Lq;
     const long long items = (long long)d.N * M * lt.groups;
@@ -401,6 +411,43 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
                             px[r] = xy.x; py[r] = xy.y;
                             pw[r] = ldg_stream_f1(attw_n + row);
                             live[r] = true;
+                        }
+                    }
+                }
+                if (FUSED) {
+                    // softmax over each (query, head)'s LP logits (mod.py:107-108) and the locations
+                    // ref + offset / (W, H) (mod.py:110-112), with the arithmetic of phase1_records()
+                    // (msda_common.cuh): same max / sum tree, same exact division -> the same bits
+#pragma unroll
+                    for (int r = 0; r < Cfg::kRounds; ++r)
+                        if (live[r]) scr_a[r * NT + tid] = pw[r];
+                    __syncthreads();                                        // logits of the item visible
+#pragma unroll
+                    for (int r = 0; r < Cfg::kRounds; ++r) {
+                        const int s = r * NT + tid;
+                        const int q = s / LP, p = s - q * LP;
+                        if (live[r]) {
+                            const float *row = scr_a + q * LP;
+                            float mx = row[0];
+#pragma unroll
+                            for (int j = 1; j < LP; ++j) mx = fmaxf(mx, row[j]);
+                            float part[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                part[k] = 0.f;
+#pragma unroll
+                                for (int j = 0; j < LP / 4; ++j) part[k] += expf(row[k * (LP / 4) + j] - mx);
+                            }
+                            const float sum = (part[0] + part[1]) + (part[2] + part[3]);
+                            pw[r] = __fdiv_rn(expf(pw[r] - mx), sum);
+                            aw_sm[s] = pw[r];
+                            const int l = lt.level_of[p];
+                            const int qg = tile_query<TILE_W>(tm, q, Lq);
+                            const float2 rp = ldg_stream_f2(reinterpret_cast<const float2 *>(
+                                pr.ref + n * pr.ref_bstride + ((long long)qg * L + l) * 2));
+                            const float2 rc = lt.rcp_wh[l];
+                            px[r] = rp.x + div_by_size(px[r], (float)lt.W[l], rc.x);
+                            py[r] = rp.y + div_by_size(py[r], (float)lt.H[l], rc.y);
                         }
                     }
                 }
@@ -620,28 +667,66 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
                 }
             }
             __syncthreads();                                                // B5: D complete
+            float egx[Cfg::kRounds], egy[Cfg::kRounds], ega[Cfg::kRounds];
 #pragma unroll
             for (int r = 0; r < Cfg::kRounds; ++r) {
                 const int s = r * NT + tid;
-                const int p = s % LP;
+                const int q = s / LP, p = s - q * LP;
+                egx[r] = egy[r] = ega[r] = 0.f;
                 if (elive[r]) {
-                    const int4 lv = lt.hws[lt.level_of[p]];
-                    const Geom<float> gm = decompose(exy[r].x, exy[r].y, lv.x, lv.y);
-                    float gx = 0.f, gy = 0.f, ga = 0.f;
+                    const int l = lt.level_of[p];
+                    const int4 lv = lt.hws[l];
+                    float x = exy[r].x, y = exy[r].y, aw = eaw[r];
+                    if (FUSED) {
+                        const int qg = tile_query<TILE_W>(te, q, Lq);
+                        const float2 rp = ldg_stream_f2(reinterpret_cast<const float2 *>(
+                            pr.ref + n * pr.ref_bstride + ((long long)qg * L + l) * 2));
+                        const float2 rc = lt.rcp_wh[l];
+                        x = rp.x + div_by_size(x, (float)lv.y, rc.x);
+                        y = rp.y + div_by_size(y, (float)lv.x, rc.y);
+                        aw = aw_sm[s];
+                    }
+                    const Geom<float> gm = decompose(x, y, lv.x, lv.y);
                     if (gm.cmask) {
                         const float4 D = reinterpret_cast<const float4 *>(dsm)[s];   // [q][p][corner]
                         const float d0 = (gm.cmask & 1) ? D.x : 0.f, d1 = (gm.cmask & 2) ? D.y : 0.f;
                         const float d2 = (gm.cmask & 4) ? D.z : 0.f, d3 = (gm.cmask & 8) ? D.w : 0.f;
                         const float lh = gm.lh, lw = gm.lw, hh = 1.f - gm.lh, hw = 1.f - gm.lw;
                         // cuh:161: sum_c grad_out[c] * val[c], val = w1 v1 + w2 v2 + w3 v3 + w4 v4
-                        ga = fmaf(hh * hw, d0, fmaf(hh * lw, d1, fmaf(lh * hw, d2, (lh * lw) * d3)));
+                        ega[r] = fmaf(hh * hw, d0, fmaf(hh * lw, d1, fmaf(lh * hw, d2, (lh * lw) * d3)));
                         // cuh:128-156,162-163: W * aw * sum_c g[c] (-hh v1 + hh v2 - lh v3 + lh v4), same for h
-                        gx = (eaw[r] * (float)lv.y) * fmaf(hh, d1 - d0, lh * (d3 - d2));
-                        gy = (eaw[r] * (float)lv.x) * fmaf(hw, d2 - d0, lw * (d3 - d1));
+                        egx[r] = (aw * (float)lv.y) * fmaf(hh, d1 - d0, lh * (d3 - d2));
+                        egy[r] = (aw * (float)lv.x) * fmaf(hw, d2 - d0, lw * (d3 - d1));
                     }
+                    if (FUSED) {
+                        // d location / d offset = 1 / (W, H) (mod.py:110-112)
+                        egx[r] = __fdiv_rn(egx[r], (float)lv.y);
+                        egy[r] = __fdiv_rn(egy[r], (float)lv.x);
+                        scr_e[s] = aw * ega[r];                              // a_j * ga_j of this point
+                    }
+                }
+            }
+            if (FUSED) {
+                __syncthreads();                                            // a_j * ga_j of the item visible
+                // softmax backward: grad_logit_i = a_i * (ga_i - sum_j a_j ga_j) (torch: (grad - sum(grad * out)) * out)
+#pragma unroll
+                for (int r = 0; r < Cfg::kRounds; ++r) {
+                    const int s = r * NT + tid;
+                    if (elive[r]) {
+                        const float *row = scr_e + (s / LP) * LP;
+                        float dot = 0.f;
+#pragma unroll
+                        for (int j = 0; j < LP; ++j) dot += row[j];
+                        ega[r] = aw_sm[s] * (ega[r] - dot);
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < Cfg::kRounds; ++r) {
+                if (elive[r]) {
                     asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};"
-                                 ::"l"(gloc_n + erow[r]), "f"(gx), "f"(gy) : "memory");
-                    stg_stream_f1(gattw_n + erow[r], ga);
+                                 ::"l"(gloc_n + erow[r]), "f"(egx[r]), "f"(egy[r]) : "memory");
+                    stg_stream_f1(gattw_n + erow[r], ega[r]);
                 }
             }
         }
@@ -651,13 +736,14 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
-template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int TILE_Q, int SLOTS, int GW, int PFV>
+template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int TILE_Q, int SLOTS, int GW, int PFV, bool FUSED = false>
 static cudaError_t launch_bwd_sorted_cfg(const float *grad_out, const float *value, const int64_t *shapes,
                                          const int64_t *lstart, const float *loc, const float *attw,
                                          const Dims &d, float *gv, float *gl, float *gw, cudaStream_t stream,
-                                         int gate) {
+                                         int gate, Producers pr = Producers{nullptr, 0}) {
     using Cfg = SortCfg<LP, WARPS, TILE_W, TILE_Q, SLOTS>;
-    auto kern = msda_bwd_sorted_kernel<LP, WARPS, TILE_W, MIN_CTAS, TILE_Q, SLOTS, GW, PFV>;
+    auto kern = msda_bwd_sorted_kernel<LP, WARPS, TILE_W, MIN_CTAS, TILE_Q, SLOTS, GW, PFV, FUSED>;
+    constexpr size_t kSmemBytes = Cfg::kSmem + (FUSED ? (size_t)Cfg::kPoints * sizeof(float) : 0);
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -665,10 +751,10 @@ static cudaError_t launch_bwd_sorted_cfg(const float *grad_out, const float *val
     static std::atomic<int> ctas_per_sm_of[kMaxDevices];
     int per_sm = ctas_per_sm_of[dev].load(std::memory_order_acquire);
     if (per_sm == 0) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
         if (e != cudaSuccess) return e;
         int nb = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, WARPS * 32, Cfg::kSmem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, WARPS * 32, kSmemBytes);
         if (e != cudaSuccess) return e;
         per_sm = nb > 0 ? nb : 1;
         ctas_per_sm_of[dev].store(per_sm, std::memory_order_release);
@@ -680,7 +766,7 @@ static cudaError_t launch_bwd_sorted_cfg(const float *grad_out, const float *val
     if (blocks > items_ub) blocks = items_ub;
     if (blocks < 1) blocks = 1;
     const int flags = option_value(OPT_TILE_ORDER) != 1 ? 1 : 0;
-    kern<<<(unsigned)blocks, WARPS * 32, Cfg::kSmem, stream>>>(grad_out, value, shapes, lstart, loc, attw, d,
+    kern<<<(unsigned)blocks, WARPS * 32, kSmemBytes, stream>>>(grad_out, value, shapes, lstart, loc, attw, pr, d,
                                                               flags, gv, gl, gw, gate);
     note_launch();
     return cudaGetLastError();
@@ -730,6 +816,30 @@ cudaError_t launch_bwd_sorted(const float *grad_out, const float *value, const i
         default: *handled = false; return cudaSuccess;
     }
 #undef MSDA_SORTED
+}
+
+// Fused producers: gradients w.r.t. the raw sampling offsets and attention logits (default shape only).
+cudaError_t launch_bwd_sorted_fused(const float *grad_out, const float *value, const int64_t *shapes,
+                                    const int64_t *lstart, const float *ref, long long ref_bstride,
+                                    const float *off, const float *logits, const Dims &d, float *gv,
+                                    float *g_off, float *g_logits, cudaStream_t stream, bool *handled, int gate) {
+    *handled = true;
+    if (!bwd_sorted_applies(value, gv, d)) {
+        *handled = false;
+        return cudaSuccess;
+    }
+    const Producers pr{ref, ref_bstride};
+#define MSDA_SORTED_FUSED(LPV, C) \
+    launch_bwd_sorted_cfg<LPV, 16, 16, C, 128, 4096, 4, 0, true>(grad_out, value, shapes, lstart, off, logits, d, gv, \
+                                                                 g_off, g_logits, stream, gate, pr)
+    switch (d.L * d.P) {
+        case 4: return MSDA_SORTED_FUSED(4, 2);
+        case 8: return MSDA_SORTED_FUSED(8, 2);
+        case 12: return MSDA_SORTED_FUSED(12, 2);
+        case 16: return MSDA_SORTED_FUSED(16, 1);
+        default: *handled = false; return cudaSuccess;
+    }
+#undef MSDA_SORTED_FUSED
 }
 
 }  // namespace msda

@@ -435,6 +435,9 @@ constexpr int kProbeSamples = 1024;
 constexpr float kProbeMarginPx = 8.f;     // kSortMargin - 1 (msda_bwd_sorted.cu)
 enum { GATE_NONE = 0, GATE_RUN_IF_LOCAL = 1, GATE_RUN_IF_SPREAD = 2 };
 
+// FUSED: `loc` holds the raw sampling offsets, which ARE the distance from the query's own position in
+// pixels of the sampled level (location = ref + offset / (W, H), mod.py:110-112).
+template <bool FUSED = false>
 __device__ __forceinline__ bool probe_points_stay_local(const LevelTable &lt, const float *__restrict__ loc,
                                                         int N, int Lq, int M, int L, int P) {
     __shared__ int probe_in, probe_all;
@@ -451,6 +454,12 @@ __device__ __forceinline__ bool probe_points_stay_local(const LevelTable &lt, co
             const int q = (int)((h >> 4) % (uint32_t)Lq);
             h = h * 1664525u + 1013904223u;
             const int m = (int)((h >> 8) % (uint32_t)M), sp = (int)((h >> 16) % (uint32_t)LP);
+            if (FUSED) {
+                const float2 off = reinterpret_cast<const float2 *>(loc)[(((long long)n * Lq + q) * M + m) * LP + sp];
+                ++n_all;
+                if (fabsf(off.x) <= kProbeMarginPx && fabsf(off.y) <= kProbeMarginPx) ++n_in;
+                continue;
+            }
             int lq = 0;
             while (lq + 1 < L && q >= lt.start[lq + 1]) ++lq;
             const int qy = (q - lt.start[lq]) / lt.W[lq], qx = (q - lt.start[lq]) - qy * lt.W[lq];
