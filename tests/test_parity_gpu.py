@@ -143,6 +143,24 @@ def test_kernel_variants_agree(pkg, oracle, fwd_variant, bwd_variant, tile_order
     check_against(out, gv, gl, gw, *refs, tag=f"variant {fwd_variant}")
 
 
+@pytest.mark.parametrize("levels,batch,heads,points,mode", [
+    ([(9, 13), (17, 5)], 3, 4, 2, "uniform"),                 # LP = 4, odd sizes, no locality: every record a run of one
+    ([(12, 39), (24, 78)], 2, 8, 4, "model"),                 # LP = 8, KITTI-like widths
+    ([(7, 9), (5, 3), (4, 4), (2, 2)], 2, 2, 4, "uniform"),   # LP = 16 (one CTA per SM)
+    ([(40, 50), (20, 25), (10, 13), (5, 7)], 1, 8, 4, "model"),   # four levels: windows over the slot budget are dropped
+    ([(1, 1), (2, 3)], 1, 1, 2, "model"),                     # tiny: fewer records than lane groups
+])
+def test_merging_backward_forced_on_other_shapes(pkg, oracle, levels, batch, heads, points, mode):
+    """bwd_variant 20 (the in-SM merging kernel without the probe) on every L*P it is instantiated for."""
+    inp = pkg.synthetic.make_inputs(levels, batch, heads, 32, points, mode=mode, seed=77)
+    try:
+        pkg.set_option("bwd_variant", 20)
+        out, gv, gl, gw = run_fwd_bwd(pkg, to_dev(inp))
+    finally:
+        pkg.set_option("bwd_variant", 0)
+    check_against(out, gv, gl, gw, *oracle_refs(oracle, inp), tag=f"merging {levels}")
+
+
 def test_random_shapes_match_oracle(pkg, oracle):
     """Seeded random problem shapes (levels, heads, points, batch, query count, location spread)
     through whichever kernel the dispatcher picks (fast path for D=32 and L*P in {4,8,12,16})."""

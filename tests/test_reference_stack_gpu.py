@@ -153,8 +153,8 @@ def test_reference_encoder_training_step_on_the_shim(pkg, ref):
     srcs = [torch.randn(2, 64, h, w, device=DEV) for h, w in levels]
     pos = [torch.randn(2, 64, h, w, device=DEV) * 0.1 for h, w in levels]
     memory = enc(srcs, pos)[0]
-    loss = memory.square().mean()
-    loss.backward()
+    cot = torch.randn_like(memory)          # a fixed random cotangent (mean-square of a LayerNorm output has ~zero gradient)
+    (memory * cot).sum().backward()
     grads = {k: p.grad.clone() for k, p in enc.named_parameters()}
     assert all(torch.isfinite(gr).all() for gr in grads.values())
     mod = importlib.import_module("refmodeling.pixel_decoder.ops.modules.ms_deform_attn")
@@ -169,15 +169,14 @@ def test_reference_encoder_training_step_on_the_shim(pkg, ref):
     try:
         enc.double()
         m2 = enc([s.double() for s in srcs], [p.double() for p in pos])[0]
-        m2.square().mean().backward()
+        (m2 * cot.double()).sum().backward()
     finally:
         mod.MSDeformAttnFunction = real
     assert (m2.float() - memory).abs().max().item() <= 5e-5
     for k, p in enc.named_parameters():
-        # the attention module's own parameters see the op's three gradients directly; level_embed and
-        # the norms are long fp32 sums of cancelling terms (1e-9 in size here): fp32-vs-fp64 noise of torch
         # sampling_offsets: the locations themselves come out of an fp32 Linear here and an fp64 one there;
         # the few samples that round into a different bilinear cell change grad_sampling_loc (floor is
-        # discontinuous), which this sum over all queries picks up at the per-cent level
-        tol = 5e-2 if "sampling_offsets" in k else (2e-3 if "self_attn" in k else 3e-2)
+        # discontinuous), which this sum over all queries picks up at the per-cent level; everything else
+        # is fp32-vs-fp64 rounding of torch's own layers around the op
+        tol = 5e-2 if "sampling_offsets" in k else 2e-3
         assert rel_err(grads[k].cpu().numpy(), p.grad.cpu().numpy()) <= tol, k
