@@ -170,12 +170,8 @@ struct Binned {
 };
 
 // Pass A for one point: geometry, window slots, per-pixel counts.
-// `vrow0` = value row of pixel 0 of this (image, head): the first thread to count a pixel requests
-// its row into L2, so that the merge loop, several microseconds later, does not wait for HBM.
-template <int PF2>
 __device__ __forceinline__ Binned count_point(const LevelTable &lt, const int4 *win, uint32_t *cnt,
-                                              float x, float y, float aw, int p, int kSortSlots,
-                                              const float *vrow0, uint32_t pix_stride_bytes) {
+                                              float x, float y, float aw, int p, int kSortSlots) {
     Binned b;
     b.s01 = b.s23 = kSlotNone | (kSlotNone << 16);
     b.pix0 = 0; b.lh = 0.f; b.lw = 0.f; b.aw = aw;
@@ -196,19 +192,15 @@ __device__ __forceinline__ Binned count_point(const LevelTable &lt, const int4 *
         if (gm.cmask & (1 << k)) {
             const bool inwin = (unsigned)(sx + dx) < (unsigned)ww && (unsigned)(sy + dy) < (unsigned)wh;
             sl[k] = kSlotTail;
-            bool first = PF2 >= 2;                   // outside every window: nobody else asks for this row
             if (inwin) {
                 const int slot = wn.w + (sy + dy) * ww + sx + dx;
 #ifdef MSDA_CHECK_BOUNDS
                 assert(slot >= 0 && slot < kSortSlots);
+#else
+                (void)kSortSlots;
 #endif
-                first = atomicAdd(&cnt[slot], 1u) == 0u;
+                atomicAdd(&cnt[slot], 1u);
                 sl[k] = (uint32_t)slot;
-            }
-            if (PF2 && first) {
-                const char *row = reinterpret_cast<const char *>(vrow0) +
-                                  (size_t)(uint32_t)(b.pix0 + dy * lv.y + dx) * pix_stride_bytes;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
             }
         }
     }
@@ -245,11 +237,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ uint2 lds_u2(uint32_t a) {
     uint2 r;
     asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a) : "memory");
-    return r;
-}
-__device__ __forceinline__ uint4 lds_u4s(uint32_t a) {
-    uint4 r;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a) : "memory");
     return r;
 }
 __device__ __forceinline__ uint32_t lds_u1(uint32_t a) {
@@ -307,14 +294,11 @@ __device__ __forceinline__ void red_add_f4(float4 *p, const float4 v) {
 }
 
 // GW: lanes per record in the merge loop (8: 16 bytes of a row per lane, 4: 32 bytes)
-// PFV: bit 0 = the first thread that counts a window pixel prefetches its value row into L2,
-//      bit 1 = also every corner outside the windows, bit 2 = the merge loop looks one body ahead
-//      and prefetches the rows of the pixel runs that start there into L1
 // FUSED: `loc` / `attw` are the raw sampling offsets / attention logits and `grad_loc` / `grad_attw`
 //      receive the gradients with respect to THEM (as in msda_bwd.cu): pass A forms
 //      location = ref + offset / (W, H) and the softmax of the (query, head)'s L*P logits (exchanged
 //      through shared memory), the epilogue applies 1 / (W, H) and the softmax backward.
-template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int TILE_Q, int SLOTS, int GW, int PFV, bool FUSED>
+template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int TILE_Q, int SLOTS, int GW, bool FUSED>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
 msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restrict__ value,
                        const int64_t *__restrict__ shapes, const int64_t *__restrict__ lstart,
@@ -324,7 +308,6 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
     using Cfg = SortCfg<LP, WARPS, TILE_W, TILE_Q, SLOTS>;
     constexpr int NT = Cfg::kThreads;
     constexpr int kSortTile = Cfg::kSortTile, kSortSlots = Cfg::kSortSlots;
-    constexpr int PF2 = PFV & 3, LOOK = (PFV >> 2) & 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ LevelTable lt;
     __shared__ int4 win[2][kMaxLevels];
@@ -340,8 +323,8 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
     // thread that owns point s); logits / weighted gradients are exchanged through the record array,
     // which is free in pass A and after the merge: two disjoint pieces, see the barriers' comments
     float *aw_sm = reinterpret_cast<float *>(smem_raw + Cfg::kSmem);
-    float *scr_a = reinterpret_cast<float *>(rec), *scr_e = reinterpret_cast<float *>(rec) + Cfg::kPoints;
-    static_assert(!FUSED || (LP % 4 == 0 && 2 * Cfg::kPoints * sizeof(float) <= Cfg::kRecBytes), "softmax scratch");
+    float *scr_a = reinterpret_cast<float *>(rec), *scr_e = scr_a + Cfg::kPoints, *scr_x = scr_a + 2 * Cfg::kPoints;
+    static_assert(!FUSED || (LP % 4 == 0 && 3 * Cfg::kPoints * sizeof(float) <= Cfg::kRecBytes), "softmax scratch");
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -397,12 +380,14 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
             bool live[Cfg::kRounds];
             {
                 float px[Cfg::kRounds], py[Cfg::kRounds], pw[Cfg::kRounds];
+                float2 rp[FUSED ? Cfg::kRounds : 1];           // FUSED: the query's reference point in the point's level
 #pragma unroll
                 for (int r = 0; r < Cfg::kRounds; ++r) {       // all global loads first
                     const int s = r * NT + tid;
                     const int q = s / LP, p = s - q * LP;
                     live[r] = false;
                     px[r] = 0.f; py[r] = 0.f; pw[r] = 0.f;
+                    if (FUSED) rp[r] = make_float2(0.f, 0.f);
                     if (s < Cfg::kPoints) {
                         const int qg = tile_query<TILE_W>(tm, q, Lq);
                         if (qg >= 0) {
@@ -410,6 +395,9 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
                             const float2 xy = ldg_stream_f2(loc_n + row);
                             px[r] = xy.x; py[r] = xy.y;
                             pw[r] = ldg_stream_f1(attw_n + row);
+                            if (FUSED)
+                                rp[r] = ldg_stream_f2(reinterpret_cast<const float2 *>(
+                                    pr.ref + n * pr.ref_bstride + ((long long)qg * L + lt.level_of[p]) * 2));
                             live[r] = true;
                         }
                     }
@@ -422,32 +410,40 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
                     for (int r = 0; r < Cfg::kRounds; ++r)
                         if (live[r]) scr_a[r * NT + tid] = pw[r];
                     __syncthreads();                                        // logits of the item visible
+                    float ex[Cfg::kRounds];
+#pragma unroll
+                    for (int r = 0; r < Cfg::kRounds; ++r) {                // row maximum, own exponential
+                        const int s = r * NT + tid;
+                        ex[r] = 0.f;
+                        if (live[r]) {
+                            const float *row = scr_a + (s / LP) * LP;
+                            float mx = row[0];
+#pragma unroll
+                            for (int j = 1; j < LP; ++j) mx = fmaxf(mx, row[j]);
+                            ex[r] = expf(pw[r] - mx);
+                            scr_x[s] = ex[r];
+                        }
+                    }
+                    __syncthreads();                                        // exponentials of the item visible
 #pragma unroll
                     for (int r = 0; r < Cfg::kRounds; ++r) {
                         const int s = r * NT + tid;
                         const int q = s / LP, p = s - q * LP;
                         if (live[r]) {
-                            const float *row = scr_a + q * LP;
-                            float mx = row[0];
-#pragma unroll
-                            for (int j = 1; j < LP; ++j) mx = fmaxf(mx, row[j]);
-                            float part[4];
+                            const float *row = scr_x + q * LP;
+                            float part[4];                                  // the summation tree of phase1_records()
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 part[k] = 0.f;
 #pragma unroll
-                                for (int j = 0; j < LP / 4; ++j) part[k] += expf(row[k * (LP / 4) + j] - mx);
+                                for (int j = 0; j < LP / 4; ++j) part[k] += row[k * (LP / 4) + j];
                             }
-                            const float sum = (part[0] + part[1]) + (part[2] + part[3]);
-                            pw[r] = __fdiv_rn(expf(pw[r] - mx), sum);
+                            pw[r] = __fdiv_rn(ex[r], (part[0] + part[1]) + (part[2] + part[3]));
                             aw_sm[s] = pw[r];
                             const int l = lt.level_of[p];
-                            const int qg = tile_query<TILE_W>(tm, q, Lq);
-                            const float2 rp = ldg_stream_f2(reinterpret_cast<const float2 *>(
-                                pr.ref + n * pr.ref_bstride + ((long long)qg * L + l) * 2));
                             const float2 rc = lt.rcp_wh[l];
-                            px[r] = rp.x + div_by_size(px[r], (float)lt.W[l], rc.x);
-                            py[r] = rp.y + div_by_size(py[r], (float)lt.H[l], rc.y);
+                            px[r] = rp[r].x + div_by_size(px[r], (float)lt.W[l], rc.x);
+                            py[r] = rp[r].y + div_by_size(py[r], (float)lt.H[l], rc.y);
                         }
                     }
                 }
@@ -457,8 +453,7 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
                     const int p = s % LP;
                     bn[r].s01 = bn[r].s23 = kSlotNone | (kSlotNone << 16);
                     if (live[r])
-                        bn[r] = count_point<PF2>(lt, wn, cnt, px[r], py[r], pw[r], p, Cfg::kSortSlots,
-                                                 value + (n * (long long)d.S * M + m) * 32, (uint32_t)M * 128u);
+                        bn[r] = count_point(lt, wn, cnt, px[r], py[r], pw[r], p, Cfg::kSortSlots);
                 }
             }
             __syncthreads();                                                // B1: counts complete
@@ -555,26 +550,8 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
             // record reads on the same banks.  The wrap is just one more change of pixel.
             const int nb = per / GW;
             int bi = nb > 0 ? gl % nb : 0;
-            const char *v_row0 = reinterpret_cast<const char *>(value) + (size_t)(n * (long long)d.S * M + m) * 128;
             for (int b = 0; b < nb; ++b) {
                 const uint32_t ra = rec_s + (uint32_t)bi * (8u * GW);   // this body's GW records
-                if (LOOK) {
-                    // look one body ahead: the value row of every pixel run that STARTS there is requested
-                    // into L1 now, a whole body before the run's first record needs it
-                    const int bn = (bi + 1 == nb) ? 0 : bi + 1;
-                    const uint32_t rn = rec_s + (uint32_t)bn * (8u * GW);
-                    uint32_t kprev = lds_u1(ra + 8u * (GW - 1)) >> 14;
-#pragma unroll
-                    for (int j = 0; j < GW; j += 2) {
-                        const uint4 two = lds_u4s(rn + 8u * j);
-                        const uint32_t k0 = two.x >> 14, k1 = two.z >> 14;
-                        if (cl == 0 && k0 != kprev && k0 != kNoKey)
-                            asm volatile("prefetch.global.L1 [%0];" ::"l"(v_row0 + (size_t)k0 * row_bytes));
-                        if (cl == 0 && k1 != k0 && k1 != kNoKey)
-                            asm volatile("prefetch.global.L1 [%0];" ::"l"(v_row0 + (size_t)k1 * row_bytes));
-                        kprev = k1;
-                    }
-                }
                 float dp[GW];
 #pragma unroll
                 for (int j = 0; j < GW; ++j) {
@@ -649,6 +626,7 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
             float2 *gloc_n = reinterpret_cast<float2 *>(grad_loc) + n * Lq * (long long)M * LP;
             float *gattw_n = grad_attw + n * Lq * (long long)M * LP;
             float2 exy[Cfg::kRounds];
+            float2 erp[FUSED ? Cfg::kRounds : 1];
             float eaw[Cfg::kRounds];
             uint32_t erow[Cfg::kRounds];
             bool elive[Cfg::kRounds];
@@ -661,9 +639,14 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
                 erow[r] = (uint32_t)(qg * M + m) * (uint32_t)LP + (uint32_t)p;
                 exy[r] = make_float2(0.f, 0.f);
                 eaw[r] = 0.f;
+                if (FUSED) erp[r] = make_float2(0.f, 0.f);
                 if (elive[r]) {
                     exy[r] = ldg_stream_f2(loc_n + erow[r]);
-                    eaw[r] = ldg_stream_f1(attw_n + erow[r]);
+                    if (FUSED)
+                        erp[r] = ldg_stream_f2(reinterpret_cast<const float2 *>(
+                            pr.ref + n * pr.ref_bstride + ((long long)qg * L + lt.level_of[p]) * 2));
+                    else
+                        eaw[r] = ldg_stream_f1(attw_n + erow[r]);
                 }
             }
             __syncthreads();                                                // B5: D complete
@@ -678,12 +661,9 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
                     const int4 lv = lt.hws[l];
                     float x = exy[r].x, y = exy[r].y, aw = eaw[r];
                     if (FUSED) {
-                        const int qg = tile_query<TILE_W>(te, q, Lq);
-                        const float2 rp = ldg_stream_f2(reinterpret_cast<const float2 *>(
-                            pr.ref + n * pr.ref_bstride + ((long long)qg * L + l) * 2));
                         const float2 rc = lt.rcp_wh[l];
-                        x = rp.x + div_by_size(x, (float)lv.y, rc.x);
-                        y = rp.y + div_by_size(y, (float)lv.x, rc.y);
+                        x = erp[r].x + div_by_size(x, (float)lv.y, rc.x);
+                        y = erp[r].y + div_by_size(y, (float)lv.x, rc.y);
                         aw = aw_sm[s];
                     }
                     const Geom<float> gm = decompose(x, y, lv.x, lv.y);
@@ -736,13 +716,13 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
-template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int TILE_Q, int SLOTS, int GW, int PFV, bool FUSED = false>
+template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int TILE_Q, int SLOTS, int GW, bool FUSED = false>
 static cudaError_t launch_bwd_sorted_cfg(const float *grad_out, const float *value, const int64_t *shapes,
                                          const int64_t *lstart, const float *loc, const float *attw,
                                          const Dims &d, float *gv, float *gl, float *gw, cudaStream_t stream,
                                          int gate, Producers pr = Producers{nullptr, 0}) {
     using Cfg = SortCfg<LP, WARPS, TILE_W, TILE_Q, SLOTS>;
-    auto kern = msda_bwd_sorted_kernel<LP, WARPS, TILE_W, MIN_CTAS, TILE_Q, SLOTS, GW, PFV, FUSED>;
+    auto kern = msda_bwd_sorted_kernel<LP, WARPS, TILE_W, MIN_CTAS, TILE_Q, SLOTS, GW, FUSED>;
     constexpr size_t kSmemBytes = Cfg::kSmem + (FUSED ? (size_t)Cfg::kPoints * sizeof(float) : 0);
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -793,26 +773,21 @@ cudaError_t launch_bwd_sorted(const float *grad_out, const float *value, const i
         *handled = false;
         return cudaSuccess;
     }
-    // (warps, tile width, min CTAs per SM, queries per tile, window slots, lanes per record, L2 prefetch)
-#define MSDA_SORTED(LPV, W, TW, C, TQ, SL, GWV, PFV) \
-    launch_bwd_sorted_cfg<LPV, W, TW, C, TQ, SL, GWV, PFV>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, stream, gate)
+    // (warps, tile width, min CTAs per SM, queries per tile, window slots, lanes per record)
+#define MSDA_SORTED(LPV, W, TW, C, TQ, SL, GWV) \
+    launch_bwd_sorted_cfg<LPV, W, TW, C, TQ, SL, GWV>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, stream, gate)
     const int variant = option_value(OPT_BWD_VARIANT);
     switch (LP) {
-        case 4: return MSDA_SORTED(4, 16, 16, 2, 128, 4096, 8, 0);
-        case 8: return MSDA_SORTED(8, 16, 16, 2, 128, 4096, 8, 0);
+        case 4: return MSDA_SORTED(4, 16, 16, 2, 128, 4096, 8);
+        case 8: return MSDA_SORTED(8, 16, 16, 2, 128, 4096, 8);
         case 12:
-            switch (variant) {
-                case 21: return MSDA_SORTED(12, 16, 16, 2, 128, 4096, 8, 0);   // 8 lanes per record
-                case 22: return MSDA_SORTED(12, 16, 16, 2, 128, 4096, 8, 4);   // 8 lanes + look-ahead L1 prefetch
-                case 23: return MSDA_SORTED(12, 16, 16, 2, 128, 4096, 4, 4);   // 4 lanes + look-ahead L1 prefetch
-                case 24: return MSDA_SORTED(12, 12, 16, 2, 128, 4096, 4, 0);   // 12 warps, 80 registers
-                case 25: return MSDA_SORTED(12, 8, 8, 4, 64, 2048, 4, 0);      // 64-query tiles, 4 CTAs of 8 warps
-                case 26: return MSDA_SORTED(12, 16, 8, 2, 64, 2048, 4, 4);     // 64-query tiles, 2 CTAs of 16 warps (L1 ~120 KB) + look-ahead
-                case 27: return MSDA_SORTED(12, 16, 8, 2, 64, 2048, 4, 0);     // the same without look-ahead
-                case 28: return MSDA_SORTED(12, 16, 8, 2, 64, 2048, 8, 4);     // 8 lanes, look-ahead, large L1
-                default: return MSDA_SORTED(12, 16, 16, 2, 128, 4096, 4, 0);   // 4 lanes per record (32 bytes each)
+            switch (variant) {      // tuning variants kept for tools/sweep.py (profiles/r2_sweep.md)
+                case 21: return MSDA_SORTED(12, 16, 16, 2, 128, 4096, 8);   // 8 lanes per record (16 bytes each)
+                case 24: return MSDA_SORTED(12, 12, 16, 2, 128, 4096, 4);   // 12 warps, 80 registers
+                case 25: return MSDA_SORTED(12, 8, 8, 4, 64, 2048, 4);      // 64-query tiles, 4 CTAs of 8 warps
+                default: return MSDA_SORTED(12, 16, 16, 2, 128, 4096, 4);   // 4 lanes per record (32 bytes each)
             }
-        case 16: return MSDA_SORTED(16, 16, 16, 1, 128, 4096, 8, 0);
+        case 16: return MSDA_SORTED(16, 16, 16, 1, 128, 4096, 8);
         default: *handled = false; return cudaSuccess;
     }
 #undef MSDA_SORTED
@@ -830,7 +805,7 @@ cudaError_t launch_bwd_sorted_fused(const float *grad_out, const float *value, c
     }
     const Producers pr{ref, ref_bstride};
 #define MSDA_SORTED_FUSED(LPV, C) \
-    launch_bwd_sorted_cfg<LPV, 16, 16, C, 128, 4096, 4, 0, true>(grad_out, value, shapes, lstart, off, logits, d, gv, \
+    launch_bwd_sorted_cfg<LPV, 16, 16, C, 128, 4096, 4, true>(grad_out, value, shapes, lstart, off, logits, d, gv, \
                                                                  g_off, g_logits, stream, gate, pr)
     switch (d.L * d.P) {
         case 4: return MSDA_SORTED_FUSED(4, 2);
