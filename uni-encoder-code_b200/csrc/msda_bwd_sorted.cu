@@ -49,22 +49,27 @@
 
 namespace msda {
 
-constexpr int kSortTileMax = 128;        // queries per item <= 128: 7 bits of the record word
+constexpr int kSortTileMax = 256;        // queries per item: 7 or 8 bits of the record word
 constexpr int kSortMargin = 9;           // window = tile footprint +- this many pixels
-constexpr uint32_t kNoKey = 0x3ffffu;    // pixel field of an absent record; S < kNoKey (host check)
+constexpr uint32_t kNoKey = 0x3ffffu;    // pixel field of an absent record (7-bit query slot); S < kNoKey (host check)
 constexpr uint32_t kSlotNone = 0xffffu;  // pass A -> pass B: corner does not contribute
 constexpr uint32_t kSlotTail = 0xfffeu;  //                   corner outside every window
 
-// record word: [pixel:18 | query slot:7 | 0 | point*4+corner:6]; (word & 0x3f80) = query slot * 128,
-// the byte offset of the query's grad_output row in shared memory
-__device__ __forceinline__ uint32_t rec_word(uint32_t pix, uint32_t q, uint32_t pc) {
-    return (pix << 14) | (q << 7) | pc;
+// record word: [pixel:18 | query slot:7 | 0 | point*4+corner:6] (tiles of up to 128 queries; 256: pixel:17,
+// query slot:8); (word & kQMask) = query slot * 128, the byte offset of the query's grad_output row in
+// shared memory
+__device__ __forceinline__ uint32_t rec_word(uint32_t pix, uint32_t q, uint32_t pc, int pix_shift) {
+    return (pix << pix_shift) | (q << 7) | pc;
 }
 
 // TILE_Q queries per item (a TILE_W-wide 2-D tile of one level), SLOTS window pixels per item
 template <int LP, int WARPS, int TILE_W, int TILE_Q, int SLOTS>
 struct SortCfg {
     static constexpr int kSortTile = TILE_Q, kSortSlots = SLOTS;
+    static constexpr int kQBits = TILE_Q > 128 ? 8 : 7;
+    static constexpr int kPixShift = 7 + kQBits;                          // record word layout
+    static constexpr uint32_t kQMask = ((1u << kQBits) - 1u) << 7;
+    static constexpr uint32_t kNoPix = 0xffffffffu >> kPixShift;          // pixel field of an absent record
     static constexpr int kThreads = WARPS * 32;
     static constexpr int kTileH = kSortTile / TILE_W;
     static constexpr int kPC = LP * 4;                       // corner records per query
@@ -78,7 +83,7 @@ struct SortCfg {
     static constexpr size_t kSmem = kRecBytes + kGoBytes + kDBytes + kCntBytes;
     static_assert(kPC <= 64 && kSortTile % TILE_W == 0, "record word: 6 bits of point*4+corner");
     static_assert(kSortSlots < (int)kSlotTail, "16-bit slot numbers between the passes");
-    static_assert(TILE_Q <= kSortTileMax, "7-bit query slot");
+    static_assert(TILE_Q <= kSortTileMax, "8-bit query slot");
 };
 
 // where the queries of a tile live
@@ -170,7 +175,9 @@ struct Binned {
 };
 
 // Pass A for one point: geometry, window slots, per-pixel counts.
-__device__ __forceinline__ Binned count_point(const LevelTable &lt, const int4 *win, uint32_t *cnt,
+// `cnt_s`: the counters' 32-bit shared address (kept in a register by the caller: generic pointers
+// make ptxas rebuild the shared-window base at every access)
+__device__ __forceinline__ Binned count_point(const LevelTable &lt, const int4 *win, uint32_t cnt_s,
                                               float x, float y, float aw, int p, int kSortSlots) {
     Binned b;
     b.s01 = b.s23 = kSlotNone | (kSlotNone << 16);
@@ -199,7 +206,7 @@ __device__ __forceinline__ Binned count_point(const LevelTable &lt, const int4 *
 #else
                 (void)kSortSlots;
 #endif
-                atomicAdd(&cnt[slot], 1u);
+                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(cnt_s + 4u * (uint32_t)slot) : "memory");
                 sl[k] = (uint32_t)slot;
             }
         }
@@ -209,25 +216,30 @@ __device__ __forceinline__ Binned count_point(const LevelTable &lt, const int4 *
     return b;
 }
 
-// Pass B for one point: its corner records to their places.
-__device__ __forceinline__ void place_point(const Binned &b, uint32_t *cnt, uint2 *rec, uint32_t *tail_ctr,
-                                            uint32_t n_in, int W, int q, int p, int S, int rec_cap) {
+// Pass B for one point: its corner records to their places.  `wbase` = query slot << 7 | point * 4.
+__device__ __forceinline__ void place_point(const Binned &b, uint32_t cnt_s, uint32_t rec_s, uint32_t *tail_ctr,
+                                            uint32_t n_in, int W, uint32_t wbase, int S, int rec_cap, int pix_shift) {
     const float hh = 1.f - b.lh, hw = 1.f - b.lw;
+    const float wk[4] = {(hh * hw) * b.aw, (hh * b.lw) * b.aw, (b.lh * hw) * b.aw, (b.lh * b.lw) * b.aw};   // bilinear * attention
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int dx = k & 1, dy = k >> 1;
         const uint32_t pair = dy ? b.s23 : b.s01;
         const uint32_t slot = dx ? (pair >> 16) : (pair & 0xffffu);
         if (slot != kSlotNone) {
-            const uint32_t pos = slot != kSlotTail ? atomicAdd(&cnt[slot], 1u) : n_in + atomicAdd(tail_ctr, 1u);
-            const float wk = ((dy ? b.lh : hh) * (dx ? b.lw : hw)) * b.aw;     // bilinear * attention weight
+            uint32_t pos;
+            if (slot != kSlotTail)
+                asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(cnt_s + 4u * slot) : "memory");
+            else
+                pos = n_in + atomicAdd(tail_ctr, 1u);
             const int pix = b.pix0 + dy * W + dx;
 #ifdef MSDA_CHECK_BOUNDS
             assert(pix >= 0 && pix < S && (int)pos < rec_cap);
 #else
             (void)S; (void)rec_cap;
 #endif
-            rec[pos] = make_uint2(rec_word((uint32_t)pix, (uint32_t)q, (uint32_t)(p * 4 + k)), __float_as_uint(wk));
+            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(rec_s + 8u * pos),
+                         "r"(((uint32_t)pix << pix_shift) | wbase | (uint32_t)k), "r"(__float_as_uint(wk[k])) : "memory");
         }
     }
 }
@@ -253,6 +265,16 @@ __device__ __forceinline__ float4 lds_f4(uint32_t a) {
 // 64-bit register pair {lo, hi}
 __device__ __forceinline__ void ffma2_bcast(uint64_t &acc, uint32_t w_bits, uint64_t g) {   // acc += {w, w} * g
     asm("{\n\t.reg .b64 rw;\n\tmov.b64 rw, {%1,%1};\n\tfma.rn.f32x2 %0, rw, %2, %0;\n\t}" : "+l"(acc) : "r"(w_bits), "l"(g));
+}
+// {x, y} = {w, w} * g
+__device__ __forceinline__ void fmul2_bcast_xy(float &x, float &y, uint32_t w_bits, uint64_t g) {
+    asm("{\n\t.reg .b64 rw, ra;\n\tmov.b64 rw, {%2,%2};\n\tmul.rn.f32x2 ra, rw, %3;\n\tmov.b64 {%0,%1}, ra;\n\t}"
+        : "=f"(x), "=f"(y) : "r"(w_bits), "l"(g));
+}
+// {x, y} += {w, w} * g on two adjacent floats of a float4 accumulator (an aligned register pair)
+__device__ __forceinline__ void ffma2_bcast_xy(float &x, float &y, uint32_t w_bits, uint64_t g) {
+    asm("{\n\t.reg .b64 rw, ra;\n\tmov.b64 rw, {%2,%2};\n\tmov.b64 ra, {%0,%1};\n\t"
+        "fma.rn.f32x2 ra, rw, %3, ra;\n\tmov.b64 {%0,%1}, ra;\n\t}" : "+f"(x), "+f"(y) : "r"(w_bits), "l"(g));
 }
 __device__ __forceinline__ void ffma2_p(uint64_t &acc, uint64_t a, uint64_t b) {            // acc += a * b
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
@@ -361,6 +383,8 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
         uint32_t n_in;
         {
             const TileMap tm = tile_of<TILE_W, Cfg::kTileH>(lt, L, g);
+            uint32_t cnt_s = smem_u32(cnt), rec_sa = smem_u32(rec);
+            asm volatile("" : "+r"(cnt_s), "+r"(rec_sa));          // live in registers, not re-derived per access
             // ---- the tile's grad_output rows -> shared memory (read once per record in the merge):
             // asynchronous copies, waited for at the end of pass B; empty query slots are zero-filled ----
             {
@@ -453,7 +477,7 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
                     const int p = s % LP;
                     bn[r].s01 = bn[r].s23 = kSlotNone | (kSlotNone << 16);
                     if (live[r])
-                        bn[r] = count_point(lt, wn, cnt, px[r], py[r], pw[r], p, Cfg::kSortSlots);
+                        bn[r] = count_point(lt, wn, cnt_s, px[r], py[r], pw[r], p, Cfg::kSortSlots);
                 }
             }
             __syncthreads();                                                // B1: counts complete
@@ -500,7 +524,8 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
                 const int s = r * NT + tid;
                 const int q = s / LP, p = s - q * LP;
                 if ((bn[r].s01 & bn[r].s23) != (kSlotNone | (kSlotNone << 16)))
-                    place_point(bn[r], cnt, rec, &tail_ctr, n_in, lt.W[lt.level_of[p]], q, p, d.S, Cfg::kRecs);
+                    place_point(bn[r], cnt_s, rec_sa, &tail_ctr, n_in, lt.W[lt.level_of[p]],
+                                ((uint32_t)q << 7) | (uint32_t)(p * 4), d.S, Cfg::kRecs, Cfg::kPixShift);
             }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
@@ -537,13 +562,21 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
             const size_t lane_off = ((size_t)(n * (long long)d.S * M + m) * 8 + c0) * 16;
             const char *v_lane = reinterpret_cast<const char *>(value) + lane_off;
             char *gv_lane = reinterpret_cast<char *>(grad_value) + lane_off;
-            const uint32_t row_bytes = (uint32_t)M * 128u;
-            uint64_t acc[2 * NCH], v[2 * NCH];                        // channel pairs: packed fp32x2 math
+            uint32_t row_bytes = (uint32_t)M * 128u;
+            // keep the two 64-bit lane bases and the row stride as they are in registers: ptxas otherwise
+            // splits them into a uniform and a per-lane part and re-adds / reloads them at every run start
+            asm volatile("" : "+l"(v_lane), "+l"(gv_lane), "+r"(row_bytes));
+            float4 acc[NCH];                                          // one 16-byte chunk each: leaves as one red.v4
+            uint64_t v[2 * NCH];                                      // channel pairs: packed fp32x2 math
 #pragma unroll
-            for (int h = 0; h < 2 * NCH; ++h) acc[h] = v[h] = 0ull;
+            for (int h = 0; h < NCH; ++h) acc[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int h = 0; h < 2 * NCH; ++h) v[h] = 0ull;
+            constexpr uint32_t kNoKey = Cfg::kNoPix;       // shadows the 7-bit constant: this tile size's layout
             uint32_t cur = kNoKey;
             const uint32_t rec_s = smem_u32(rec) + (uint32_t)i0 * 8u;
-            const uint32_t go_s0 = smem_u32(go_sm) + (uint32_t)c0 * 16u;
+            uint32_t go_s0 = smem_u32(go_sm) + (uint32_t)c0 * 16u, go_s1 = smem_u32(go_sm) + (uint32_t)(c0 ^ 4) * 16u;
+            asm volatile("" : "+r"(go_s0), "+r"(go_s1));
             const uint32_t d_s = smem_u32(dsm);
             // The groups of a warp start at different bodies of their slices (and wrap around): slice
             // starts are multiples of 128 bytes apart, so walking them in step would put every group's
@@ -556,16 +589,16 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
 #pragma unroll
                 for (int j = 0; j < GW; ++j) {
                     const uint2 rr = lds_u2(ra + 8u * j);
-                    const uint32_t key = rr.x >> 14;
-                    const uint32_t ga = go_s0 + (rr.x & 0x3f80u);              // the query's grad_output row
+                    const uint32_t key = rr.x >> Cfg::kPixShift;
+                    const uint32_t qoff = rr.x & Cfg::kQMask;                     // the query's grad_output row
                     uint64_t g[2 * NCH];
-                    lds_2x64(ga, g[0], g[1]);
-                    if (NCH == 2) lds_2x64(ga ^ 64u, g[2], g[3]);
+                    lds_2x64(go_s0 + qoff, g[0], g[1]);
+                    if (NCH == 2) lds_2x64(go_s1 + qoff, g[2], g[3]);
                     if (key != cur) {                    // first record of a pixel (or of the padding)
                         if (cur != kNoKey) {
                             char *p = gv_lane + (size_t)cur * row_bytes;
-                            red_2x64(p, acc[0], acc[1]);
-                            if (NCH == 2) red_2x64(xor64(p), acc[2], acc[3]);
+                            red_add_f4(reinterpret_cast<float4 *>(p), acc[0]);
+                            if (NCH == 2) red_add_f4(reinterpret_cast<float4 *>(xor64(p)), acc[NCH - 1]);
                         }
                         if (key != kNoKey) {
                             const char *p = v_lane + (size_t)key * row_bytes;
@@ -574,7 +607,16 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
                         }
                         cur = key;
 #pragma unroll
-                        for (int h = 0; h < 2 * NCH; ++h) acc[h] = 0ull;
+                        for (int h = 0; h < NCH; ++h) {                          // the run's first term
+                            fmul2_bcast_xy(acc[h].x, acc[h].y, rr.y, g[2 * h]);
+                            fmul2_bcast_xy(acc[h].z, acc[h].w, rr.y, g[2 * h + 1]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < NCH; ++h) {                          // acc += weight * grad_output
+                            ffma2_bcast_xy(acc[h].x, acc[h].y, rr.y, g[2 * h]);
+                            ffma2_bcast_xy(acc[h].z, acc[h].w, rr.y, g[2 * h + 1]);
+                        }
                     }
                     // <value row, grad_output row>: one packed dot product per 16-byte chunk, added at the
                     // end -- the sum does not depend on which chunk a lane happened to load first, so
@@ -582,8 +624,6 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
                     uint64_t d2 = 0ull, d2b = 0ull;
 #pragma unroll
                     for (int h = 0; h < NCH; ++h) {
-                        ffma2_bcast(acc[2 * h], rr.y, g[2 * h]);                 // acc += weight * grad_output
-                        ffma2_bcast(acc[2 * h + 1], rr.y, g[2 * h + 1]);
                         uint64_t t = fmul2_p(v[2 * h], g[2 * h]);
                         ffma2_p(t, v[2 * h + 1], g[2 * h + 1]);
                         if (h == 0) d2 = t; else d2b = t;
@@ -607,14 +647,14 @@ msda_bwd_sorted_kernel(const float *__restrict__ grad_out, const float *__restri
                 }
                 if (i0 + bi * GW + cl < T) {
                     const uint32_t xx = lds_u1(ra + 8u * (uint32_t)cl);
-                    sts_f1(d_s + 4u * (((xx >> 7) & 127u) * (uint32_t)Cfg::kPC + (xx & 63u)), dsum);
+                    sts_f1(d_s + 4u * (((xx & Cfg::kQMask) >> 7) * (uint32_t)Cfg::kPC + (xx & 63u)), dsum);
                 }
                 if (++bi == nb) bi = 0;
             }
             if (cur != kNoKey) {
                 char *p = gv_lane + (size_t)cur * row_bytes;
-                red_2x64(p, acc[0], acc[1]);
-                if (NCH == 2) red_2x64(xor64(p), acc[2], acc[3]);
+                red_add_f4(reinterpret_cast<float4 *>(p), acc[0]);
+                if (NCH == 2) red_add_f4(reinterpret_cast<float4 *>(xor64(p)), acc[NCH - 1]);
             }
         }
 
@@ -785,7 +825,13 @@ cudaError_t launch_bwd_sorted(const float *grad_out, const float *value, const i
                 case 21: return MSDA_SORTED(12, 16, 16, 2, 128, 4096, 8);   // 8 lanes per record (16 bytes each)
                 case 24: return MSDA_SORTED(12, 12, 16, 2, 128, 4096, 4);   // 12 warps, 80 registers
                 case 25: return MSDA_SORTED(12, 8, 8, 4, 64, 2048, 4);      // 64-query tiles, 4 CTAs of 8 warps
-                default: return MSDA_SORTED(12, 16, 16, 2, 128, 4096, 4);   // 4 lanes per record (32 bytes each)
+                case 27:
+                    if (d.S < 0x1ffff) return MSDA_SORTED(12, 32, 16, 1, 256, 4096, 8);
+                    return MSDA_SORTED(12, 16, 16, 2, 128, 4096, 4);
+                case 26:                                                    // 256-query tiles (16 x 16), one CTA of 32 warps:
+                    if (d.S < 0x1ffff) return MSDA_SORTED(12, 32, 16, 1, 256, 4096, 4);   // -2 % at configs[1], +2 % at 1024x2048
+                    return MSDA_SORTED(12, 16, 16, 2, 128, 4096, 4);
+                default: return MSDA_SORTED(12, 16, 16, 2, 128, 4096, 4);   // 128-query tiles, 2 CTAs of 16 warps, 4 lanes per record
             }
         case 16: return MSDA_SORTED(16, 16, 16, 1, 128, 4096, 8);
         default: *handled = false; return cudaSuccess;
