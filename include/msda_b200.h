@@ -120,6 +120,25 @@ int msda_b200_fused_forward_f32(const float *value, const int64_t *spatial_shape
                                 const float *attn_logits, int batch, int spatial_size,
                                 int num_heads, int channels, int num_levels, int num_query,
                                 int num_point, float *output, void *stream);
+/* The fused forward with the raw projections read in place from wider rows: query r's offsets start at
+ * sampling_offsets + r * offsets_row_stride and its logits at attn_logits + r * logits_row_stride (floats;
+ * offsets_row_stride even).  One [rows, 3*M*L*P] GEMM (sampling_offsets and attention_weights weights
+ * stacked, ops/modules/ms_deform_attn.py:105-106) then feeds the kernel without a split copy:
+ * sampling_offsets = y, attn_logits = y + 2*M*L*P, both strides 3*M*L*P.
+ * offsets_table / logits_table (both or neither; NULL = none): per-QUERY tables with num_query rows laid
+ * out with the same row strides, shared by the batch and added to the raw values of query q of every image
+ * before the softmax / location arithmetic.  The encoder layer projects `src + pos` (with_pos_embed,
+ * msdeformattn.py:123-124, :133); `pos` is the same for every image and every call, so
+ * (src + pos) W^T + b = src W^T + (pos W^T + b): the host computes the second term once per layer
+ * (num_query x 3*M*L*P), the GEMM runs on `src`, and the `src + pos` pass over the activations disappears. */
+int msda_b200_fused_forward_strided_f32(const float *value, const int64_t *spatial_shapes,
+                                        const int64_t *level_start, const float *reference_points,
+                                        long long ref_batch_stride, const float *sampling_offsets,
+                                        int offsets_row_stride, const float *attn_logits,
+                                        int logits_row_stride, const float *offsets_table,
+                                        const float *logits_table, int batch, int spatial_size,
+                                        int num_heads, int channels, int num_levels, int num_query,
+                                        int num_point, float *output, void *stream);
 int msda_b200_fused_backward_f32(const float *grad_output, const float *value,
                                  const int64_t *spatial_shapes, const int64_t *level_start,
                                  const float *reference_points, long long ref_batch_stride,
@@ -170,17 +189,25 @@ int msda_b200_add_layernorm_backward_f32(const float *grad_y, const float *x, co
 /*
  * GroupNorm over an NCHW fp32 map with the pixel decoder's epilogues fused in (SURVEY 8f.4;
  * msdeformattn.py:233-248, :286-300, :369-379):
- *     y = group_norm(x, groups, gamma, beta, eps)            torch.nn.functional.group_norm semantics
+ *     y = group_norm(x + channel_bias[c], groups, gamma, beta, eps)    torch.nn.functional.group_norm semantics;
+ *                     channel_bias (may be NULL) is the bias of the convolution that produced x, when that
+ *                     convolution ran without it (torch adds a convolution's bias in a separate pass)
  *     if relu:        y = max(y, 0)
  *     if up != NULL:  y += bilinear up-sampling of up[N, C, up_h, up_w] to H x W, align_corners=False
  * `workspace` must hold msda_b200_group_norm_workspace_bytes(N, groups) bytes (per-group partial sums;
  * its contents are meaningless before and after the call).  Needs H*W and W to be multiples of 4 and
  * 16-byte aligned x / y; MSDA_ERR_UNSUPPORTED otherwise.  Inference only (no backward).
  */
-int msda_b200_group_norm_nchw_f32(const float *x, const float *gamma, const float *beta, float *y, int batch,
-                                  int channels, int height, int width, int groups, float eps, int relu,
-                                  const float *up, int up_h, int up_w, void *workspace, void *stream);
+int msda_b200_group_norm_nchw_f32(const float *x, const float *channel_bias, const float *gamma,
+                                  const float *beta, float *y, int batch, int channels, int height,
+                                  int width, int groups, float eps, int relu, const float *up, int up_h,
+                                  int up_w, void *workspace, void *stream);
 long long msda_b200_group_norm_workspace_bytes(int batch, int groups);
+/* x[n, c, :] += bias[c] in place over an NCHW fp32 map (plane = H*W, a multiple of 4; 16-byte aligned x):
+ * the bias of the decoder's last 1x1 convolution (mask_features, msdeformattn.py:268-275, :381) at the
+ * memory roofline instead of torch's broadcasting add. */
+int msda_b200_add_channel_bias_nchw_f32(float *x, const float *bias, int batch, int channels,
+                                        long long plane, void *stream);
 
 /*
  * Weight and bias gradient of the same Linear (torch autograd semantics), 3 x TF32 on the tensor cores

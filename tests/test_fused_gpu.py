@@ -131,3 +131,99 @@ def test_fused_rejects_unsupported_shapes_and_module_falls_back(pkg):
         a = attn(q, ref, q, d["shapes"], d["lsi"])
         b = attn_unfused(q, ref, q, d["shapes"], d["lsi"])
     assert torch.equal(a, b)
+
+
+def test_packed_projection_forward_is_bit_identical_to_separate_tensors(pkg):
+    """msda_b200_fused_forward_strided_f32: offsets and logits read in place from one [N, Lq, 3*M*L*P]
+    projection output give exactly the result of the packed tensors."""
+    levels = [(16, 32), (8, 16), (4, 8)]
+    c = make_case(pkg, levels, 2, 8, 4, True, seed=11)
+    d = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in c.items()}
+    N, Lq = d["off"].shape[:2]
+    proj = torch.cat((d["off"].reshape(N, Lq, -1), d["logits"].reshape(N, Lq, -1)), -1).contiguous()
+    want = pkg.ms_deform_attn_fused_forward(d["value"], d["shapes"], d["lsi"], d["ref"], d["off"], d["logits"])
+    n0 = pkg.launch_count()
+    got = pkg.ops.ms_deform_attn_fused_forward_packed(d["value"], d["shapes"], d["lsi"], d["ref"], proj,
+                                                      len(levels), 4)
+    assert pkg.launch_count() - n0 == 1
+    assert torch.equal(got, want)
+    # a per-query table added inside the kernel == the same table added to every image beforehand
+    table = torch.randn(Lq, proj.shape[-1], device=DEV) * 0.5
+    shifted = proj + table[None]
+    want_t = pkg.ops.ms_deform_attn_fused_forward_packed(d["value"], d["shapes"], d["lsi"], d["ref"],
+                                                         shifted.contiguous(), len(levels), 4)
+    got_t = pkg.ops.ms_deform_attn_fused_forward_packed(d["value"], d["shapes"], d["lsi"], d["ref"], proj,
+                                                        len(levels), 4, query_table=table)
+    assert torch.equal(got_t, want_t)
+    with pytest.raises(RuntimeError, match="query_table must be"):
+        pkg.ops.ms_deform_attn_fused_forward_packed(d["value"], d["shapes"], d["lsi"], d["ref"], proj,
+                                                    len(levels), 4, query_table=table[:-1])
+    with pytest.raises(RuntimeError, match="projections must be"):
+        pkg.ops.ms_deform_attn_fused_forward_packed(d["value"], d["shapes"], d["lsi"], d["ref"], proj[..., :-1],
+                                                    len(levels), 4)
+    # the C ABI: odd offsets stride / too narrow rows are shape errors
+    lib = pkg._lib.lib
+    args = lambda so, sl: (d["value"].data_ptr(), d["shapes"].data_ptr(), d["lsi"].data_ptr(), d["ref"].data_ptr(),
+                           0 if d["ref"].shape[0] == 1 and N > 1 else Lq * 3 * 2, proj.data_ptr(), so,
+                           proj.data_ptr(), sl, None, None, N, d["value"].shape[1], 8, 32, 3, Lq, 4,
+                           want.data_ptr(), None)
+    assert lib.msda_b200_fused_forward_strided_f32(*args(289, 288)) == -2
+    assert lib.msda_b200_fused_forward_strided_f32(*args(190, 288)) == -2
+    assert lib.msda_b200_fused_forward_strided_f32(*args(288, 95)) == -2
+    one_table = list(args(288, 288))
+    one_table[9] = table.data_ptr()                       # offsets table without a logits table
+    assert lib.msda_b200_fused_forward_strided_f32(*one_table) == -1
+
+
+def test_encoder_with_shared_position_embedding_folds_src_plus_pos_into_the_query_gemm(pkg):
+    """Inference kernels (fused=True, linear="tf32x3") with a position embedding shared by the batch (batch
+    stride 0, what the pixel decoder passes): `src + pos` is never formed -- the two query projections run as one
+    GEMM on `src`, and the fused kernel adds the cached `pos W^T + b` row of each query -- and the result agrees with the
+    same weights on the unfolded path (per-image copy of the embedding) and with torch's fp32 GEMMs."""
+    torch.manual_seed(21)
+    levels = [(8, 16), (16, 32), (32, 64)]
+    kw = dict(d_model=256, nhead=8, num_encoder_layers=2, dim_feedforward=1024, dropout=0.0,
+              num_feature_levels=3, enc_n_points=4)
+    a = pkg.modules.MSDeformAttnTransformerEncoderOnly(**kw).to(DEV).eval()
+    for m in a.modules():
+        if isinstance(m, pkg.modules.MSDeformAttn):
+            torch.nn.init.normal_(m.sampling_offsets.weight, std=0.02)
+            torch.nn.init.normal_(m.attention_weights.weight, std=0.05)
+            torch.nn.init.normal_(m.attention_weights.bias, std=0.05)
+    b = pkg.modules.MSDeformAttnTransformerEncoderOnly(fused=True, linear="tf32x3", **kw).to(DEV).eval()
+    b.load_state_dict(a.state_dict())
+    srcs = [torch.randn(3, 256, h, w, device=DEV) for h, w in levels]
+    one = [torch.randn(1, 256, h, w, device=DEV) for h, w in levels]
+    shared = [p.expand(3, -1, -1, -1) for p in one]                  # batch stride 0
+    copies = [p.expand(3, -1, -1, -1).contiguous() for p in one]     # same values, one copy per image
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            want = a(srcs, copies)[0]
+            n0 = pkg.launch_count()
+            unfolded = b(srcs, copies)[0]
+            n1 = pkg.launch_count()
+            folded = b(srcs, shared)[0]
+            n2 = pkg.launch_count()
+            again = b(srcs, shared)[0]
+            n3 = pkg.launch_count()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    per_layer_unfolded = 1 + 6 * 2 + 2          # MSDA forward, 6 x (weight split + GEMM), 2 x add + LayerNorm
+    per_layer_folded = 1 + 5 * 2 + 2            # offsets and logits are ONE GEMM
+    assert n1 - n0 == 2 * per_layer_unfolded
+    assert n2 - n1 == 2 * (per_layer_folded + 2)            # first call: + the pos W^T + b table (split + GEMM)
+    assert n3 - n2 == 2 * per_layer_folded                  # afterwards the table is cached
+    assert torch.equal(folded, again)
+    assert (folded - unfolded).abs().max().item() <= 2e-5, (folded - unfolded).abs().max().item()
+    assert (folded - want).abs().max().item() <= 5e-5, (folded - want).abs().max().item()
+    # the table follows its inputs: an in-place change of a projection weight or of the level embedding rebuilds it
+    with torch.no_grad():
+        b.encoder.layers[0].self_attn.attention_weights.bias.add_(0.25)
+        b.level_embed.add_(0.1)
+        a.load_state_dict(b.state_dict())
+        want2 = a(srcs, copies)[0]
+        folded2 = b(srcs, shared)[0]
+    assert (folded2 - want2).abs().max().item() <= 5e-5
+    assert (folded2 - folded).abs().max().item() > 1e-3

@@ -376,3 +376,47 @@ def test_group_norm_unsupported_shapes_fall_back_in_the_mirror(pkg):
         a = conv(x, fused_norm=True)
         b = torch.relu(norm(torch.nn.functional.conv2d(x, conv.weight, conv.bias)))
     assert torch.allclose(a, b, atol=1e-6)
+
+
+@pytest.mark.parametrize("shape,groups", [((2, 64, 12, 20), 32), ((3, 256, 8, 16), 32), ((1, 32, 4, 4), 8)])
+def test_group_norm_with_the_convolution_bias_folded_in(pkg, shape, groups):
+    """ops.group_norm(x, norm, channel_bias=b) == norm(x + b[None, :, None, None]) (fp64 reference)."""
+    torch.manual_seed(sum(shape))
+    x = torch.randn(*shape, device=DEV) * 2.0 + 0.5
+    cb = torch.randn(shape[1], device=DEV) * 3.0
+    norm = torch.nn.GroupNorm(groups, shape[1]).to(DEV)
+    with torch.no_grad():
+        norm.weight.normal_()
+        norm.bias.normal_()
+        want = F.group_norm((x + cb.view(1, -1, 1, 1)).double(), groups, norm.weight.double(), norm.bias.double(), norm.eps)
+        n0 = pkg.launch_count()
+        got = pkg.group_norm(x, norm, channel_bias=cb)
+        assert pkg.launch_count() - n0 == 2
+        assert (got.double() - want).abs().max().item() <= 1e-5
+        relu = pkg.group_norm(x, norm, relu=True, channel_bias=cb)
+        assert (relu.double() - want.clamp_min(0)).abs().max().item() <= 1e-5
+    with pytest.raises(RuntimeError, match="channel_bias must be"):
+        pkg.group_norm(x, norm, channel_bias=cb[:-1])
+
+
+def test_add_channel_bias_in_place(pkg):
+    x = torch.randn(3, 40, 6, 10, device=DEV)
+    b = torch.randn(40, device=DEV)
+    want = x + b.view(1, -1, 1, 1)
+    n0 = pkg.launch_count()
+    got = pkg.ops.add_channel_bias_(x, b)
+    assert pkg.launch_count() - n0 == 1 and got.data_ptr() == x.data_ptr()
+    assert torch.equal(got, want)
+    assert not pkg.ops.channel_bias_supported(torch.randn(1, 4, 3, 3, device=DEV), torch.randn(4, device=DEV))
+    with pytest.raises(RuntimeError, match="add_channel_bias_ needs"):
+        pkg.ops.add_channel_bias_(torch.randn(1, 4, 3, 3, device=DEV), torch.randn(4, device=DEV))
+    big = torch.randn(2, 8, 256, 512, device=DEV)
+    bb = torch.randn(8, device=DEV)
+    assert torch.equal(pkg.ops.add_channel_bias_(big.clone(), bb), big + bb.view(1, -1, 1, 1))
+
+
+def test_transpose_into_destination(pkg):
+    x = torch.randn(333, 64, device=DEV)
+    dst = torch.empty(64, 333, device=DEV)
+    got = pkg.ops.transpose2d(x, out=dst)
+    assert got.data_ptr() == dst.data_ptr() and torch.equal(dst, x.t())

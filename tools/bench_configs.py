@@ -144,6 +144,18 @@ def main():
                      for k, (c, st) in shapes.items()}
             with torch.no_grad():
                 ms = timed(lambda: dec.forward_features(feats), args.steps)
+                # the same call replayed from one CUDA graph (the mirror's forward has no host sync, so it
+                # records; tests/test_pixel_decoder.py::test_forward_features_is_cuda_graph_capturable)
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    dec.forward_features(feats)
+                torch.cuda.current_stream().wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    dec.forward_features(feats)
+                ms_graph = timed(graph.replay, args.steps)
+                del graph
                 ev = pkg.ops.enable_timing(True)
                 for _ in range(args.steps):
                     dec.forward_features(feats)
@@ -151,7 +163,7 @@ def main():
                 pkg.ops.enable_timing(False)
             S = sum(h * w for h, w in syn.pyramid(Himg, Wimg))
             q = batch * S
-            emit({"config": int(cfg), "what": name, "ms": ms, "msda_ms_6_layers": f_ms, "msda_share": f_ms / ms,
+            emit({"config": int(cfg), "what": name, "ms": ms, "ms_cuda_graph": ms_graph, "msda_ms_6_layers": f_ms, "msda_share": f_ms / ms,
                   "queries_per_layer_per_gpu": q, "images_per_s": world * batch / ms * 1e3,
                   "msda_algorithmic_GBs": 6 * q * 3200 / f_ms / 1e6, "msda_frac_of_measured_hbm": 6 * q * 3200 / f_ms / 1e6 / peak})
             del dec, feats

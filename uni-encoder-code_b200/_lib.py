@@ -28,13 +28,15 @@ SYMBOLS = {
     "msda_b200_backward_f64": (_I, [_P] * 6 + _DIMS + [_P, _P, _P, _P]),
     "msda_b200_debug_indices_f32": (_I, [_P] * 3 + _DIMS + [_P, _P, _P]),
     "msda_b200_fused_forward_f32": (_I, [_P] * 4 + [ctypes.c_longlong, _P, _P] + _DIMS + [_P, _P]),
+    "msda_b200_fused_forward_strided_f32": (_I, [_P] * 4 + [ctypes.c_longlong, _P, _I, _P, _I, _P, _P] + _DIMS + [_P, _P]),
     "msda_b200_fused_backward_f32": (_I, [_P] * 5 + [ctypes.c_longlong, _P, _P] + _DIMS + [_P, _P, _P, _P]),
     "msda_b200_linear_f32": (_I, [_P] * 4 + [_I] * 4 + [_P, _P]),
     "msda_b200_add_layernorm_f32": (_I, [_P] * 5 + [ctypes.c_longlong, _I, ctypes.c_float, _P]),
     "msda_b200_add_layernorm_backward_f32": (_I, [_P] * 7 + [ctypes.c_longlong, _I, ctypes.c_float, _P]),
     "msda_b200_linear_wgrad_f32": (_I, [_P] * 4 + [ctypes.c_longlong, _I, _I, _P]),
     "msda_b200_transpose_f32": (_I, [_P, _P, ctypes.c_longlong, _I, _P]),
-    "msda_b200_group_norm_nchw_f32": (_I, [_P] * 4 + [_I] * 5 + [ctypes.c_float, _I, _P, _I, _I, _P, _P]),
+    "msda_b200_group_norm_nchw_f32": (_I, [_P] * 5 + [_I] * 5 + [ctypes.c_float, _I, _P, _I, _I, _P, _P]),
+    "msda_b200_add_channel_bias_nchw_f32": (_I, [_P, _P, _I, _I, ctypes.c_longlong, _P]),
     "msda_b200_group_norm_workspace_bytes": (ctypes.c_longlong, [_I, _I]),
     "msda_b200_set_option": (_I, [ctypes.c_char_p, _I]),
     "msda_b200_get_option": (_I, [ctypes.c_char_p, ctypes.POINTER(_I)]),

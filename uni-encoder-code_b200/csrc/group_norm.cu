@@ -35,19 +35,25 @@ namespace {
 constexpr int kGnSplit = 16;       // CTAs per (image, group) chunk in the statistics pass
 constexpr int kGnThreads = 512;
 
+// CBIAS: a per-channel constant (the bias of the convolution that produced x, left out of that
+// convolution's epilogue) is added to x on the fly: group_norm(x + cbias[c])
+template <bool CBIAS>
 __global__ void __launch_bounds__(kGnThreads)
-group_stats_kernel(const float *__restrict__ x, double *__restrict__ partial, long long chunk /* elements */) {
+group_stats_kernel(const float *__restrict__ x, double *__restrict__ partial, long long chunk /* elements */,
+                   const float *__restrict__ cbias, int groups, int cpg, unsigned hw4 /* float4 per channel plane */) {
     // blockIdx.x = (image * groups + group), blockIdx.y = part
     const float *base = x + (long long)blockIdx.x * chunk;
     const long long chunk4 = chunk >> 2;
     const long long per = (chunk4 + gridDim.y - 1) / gridDim.y;
     const long long beg = (long long)blockIdx.y * per, end = min(beg + per, chunk4);
-    const float K = __ldg(base);
+    const float *cb = CBIAS ? cbias + (blockIdx.x % (unsigned)groups) * cpg : nullptr;   // the group's first channel
+    const float K = __ldg(base) + (CBIAS ? __ldg(cb) : 0.f);
     float s = 0.f, q = 0.f;
     const float4 *b4 = reinterpret_cast<const float4 *>(base);
     for (long long i = beg + threadIdx.x; i < end; i += kGnThreads) {
         const float4 v = ldg_stream_f4(b4 + i);
-        const float a = v.x - K, b = v.y - K, c = v.z - K, d = v.w - K;
+        const float Kc = CBIAS ? K - __ldg(cb + (unsigned)i / hw4) : K;      // (x + b_c) - K
+        const float a = v.x - Kc, b = v.y - Kc, c = v.z - Kc, d = v.w - Kc;
         s += (a + b) + (c + d);
         q = fmaf(a, a, fmaf(b, b, fmaf(c, c, fmaf(d, d, q))));
     }
@@ -83,7 +89,8 @@ template <bool RELU, bool UP>
 __global__ void __launch_bounds__(256)
 group_apply_kernel(const float *__restrict__ x, const double *__restrict__ partial, const float *__restrict__ gamma,
                    const float *__restrict__ beta, float *__restrict__ y, int C, int H, int W, int cpg, float eps,
-                   const float *__restrict__ up, int uh, int uw, float sh, float sw) {
+                   const float *__restrict__ up, int uh, int uw, float sh, float sw,
+                   const float *__restrict__ cbias) {
     // blockIdx.x = image * C + channel (one plane), blockIdx.y = part of the plane
     const int plane = blockIdx.x, c = plane % C, ng = plane / cpg;      // ng = image * groups + group
     __shared__ float s_scale, s_shift;
@@ -92,15 +99,16 @@ group_apply_kernel(const float *__restrict__ x, const double *__restrict__ parti
         const double *p = partial + (long long)ng * kGnSplit * 2;
         for (int k = 0; k < kGnSplit; ++k) { a += p[2 * k]; b += p[2 * k + 1]; }
         const double n = (double)cpg * H * W;
-        const double K = (double)__ldg(x + (long long)ng * cpg * H * W);
-        const double mean_k = a / n;                                     // mean of (x - K)
+        const int g0 = (ng % (C / cpg)) * cpg;                           // the group's first channel
+        const double K = (double)(__ldg(x + (long long)ng * cpg * H * W) + (cbias ? __ldg(cbias + g0) : 0.f));
+        const double mean_k = a / n;                                     // mean of (x + cbias - K)
         double var = b / n - mean_k * mean_k;
         var = var < 0.0 ? 0.0 : var;
         const float mean = (float)(mean_k + K);
         const float rstd = (float)(1.0 / sqrt(var + (double)eps));
         const float sc = rstd * gamma[c];
         s_scale = sc;
-        s_shift = beta[c] - mean * sc;
+        s_shift = beta[c] + ((cbias ? __ldg(cbias + c) : 0.f) - mean) * sc;
     }
     __syncthreads();
     const float sc = s_scale, sf = s_shift;
@@ -140,9 +148,9 @@ group_apply_kernel(const float *__restrict__ x, const double *__restrict__ parti
 }  // namespace
 
 // workspace: N * groups * kGnSplit * 2 doubles
-cudaError_t launch_group_norm(const float *x, const float *gamma, const float *beta, float *y, int N, int C, int H,
-                              int W, int groups, float eps, int relu, const float *up, int uh, int uw,
-                              double *workspace, cudaStream_t stream, bool *handled) {
+cudaError_t launch_group_norm(const float *x, const float *cbias, const float *gamma, const float *beta, float *y,
+                              int N, int C, int H, int W, int groups, float eps, int relu, const float *up, int uh,
+                              int uw, double *workspace, cudaStream_t stream, bool *handled) {
     *handled = false;
     const long long hw = (long long)H * W;
     if (groups <= 0 || C % groups != 0 || (hw & 3) || (W & 3) || hw > 0x7fffffffLL ||
@@ -150,10 +158,15 @@ cudaError_t launch_group_norm(const float *x, const float *gamma, const float *b
         return cudaSuccess;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15u) return cudaSuccess;
     if (up != nullptr && (uh <= 0 || uw <= 0)) return cudaSuccess;
-    *handled = true;
     const int cpg = C / groups;
     const long long chunk = (long long)cpg * hw;
-    group_stats_kernel<<<dim3((unsigned)(N * groups), kGnSplit), kGnThreads, 0, stream>>>(x, workspace, chunk);
+    if (cbias != nullptr && chunk > 0x7fffffffLL) return cudaSuccess;    // 32-bit channel lookup in the statistics pass
+    *handled = true;
+    const dim3 sgrid((unsigned)(N * groups), kGnSplit);
+    if (cbias != nullptr)
+        group_stats_kernel<true><<<sgrid, kGnThreads, 0, stream>>>(x, workspace, chunk, cbias, groups, cpg, (unsigned)(hw >> 2));
+    else
+        group_stats_kernel<false><<<sgrid, kGnThreads, 0, stream>>>(x, workspace, chunk, nullptr, groups, cpg, 1u);
     note_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -163,7 +176,7 @@ cudaError_t launch_group_norm(const float *x, const float *gamma, const float *b
     if (parts > 64) parts = 64;
     const dim3 grid((unsigned)(N * C), (unsigned)parts);
     const float sh = up ? (float)uh / (float)H : 0.f, sw = up ? (float)uw / (float)W : 0.f;
-#define GN_APPLY(R, U) group_apply_kernel<R, U><<<grid, 256, 0, stream>>>(x, workspace, gamma, beta, y, C, H, W, cpg, eps, up, uh, uw, sh, sw)
+#define GN_APPLY(R, U) group_apply_kernel<R, U><<<grid, 256, 0, stream>>>(x, workspace, gamma, beta, y, C, H, W, cpg, eps, up, uh, uw, sh, sw, cbias)
     if (up != nullptr) { if (relu) GN_APPLY(true, true); else GN_APPLY(false, true); }
     else { if (relu) GN_APPLY(true, false); else GN_APPLY(false, false); }
 #undef GN_APPLY
@@ -172,5 +185,35 @@ cudaError_t launch_group_norm(const float *x, const float *gamma, const float *b
 }
 
 int group_norm_workspace_doubles(int N, int groups) { return N * groups * kGnSplit * 2; }
+
+// x[n, c, :, :] += bias[c] in place (the bias of a convolution run without one), 128-bit accesses
+namespace {
+__global__ void __launch_bounds__(256)
+channel_bias_kernel(float4 *__restrict__ x, const float *__restrict__ bias, int C, long long hw4) {
+    const int plane = blockIdx.x;
+    const float b = __ldg(bias + plane % C);
+    const long long per = (hw4 + gridDim.y - 1) / gridDim.y;
+    const long long beg = (long long)blockIdx.y * per, end = min(beg + per, hw4);
+    float4 *p = x + (long long)plane * hw4;
+    for (long long i = beg + threadIdx.x; i < end; i += 256) {
+        float4 v = ldg_stream_f4(p + i);
+        v.x += b; v.y += b; v.z += b; v.w += b;
+        p[i] = v;
+    }
+}
+}  // namespace
+
+cudaError_t launch_channel_bias(float *x, const float *bias, int N, int C, long long hw, cudaStream_t stream,
+                                bool *handled) {
+    *handled = false;
+    if ((hw & 3) || (long long)N * C > 0x7fffffffLL || (reinterpret_cast<uintptr_t>(x) & 15u)) return cudaSuccess;
+    *handled = true;
+    int parts = (int)((hw / 4 + 8191) / 8192);
+    parts = parts < 1 ? 1 : parts > 64 ? 64 : parts;
+    channel_bias_kernel<<<dim3((unsigned)(N * C), (unsigned)parts), 256, 0, stream>>>(
+        reinterpret_cast<float4 *>(x), bias, C, hw >> 2);
+    note_launch();
+    return cudaGetLastError();
+}
 
 }  // namespace msda

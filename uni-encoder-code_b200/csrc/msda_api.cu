@@ -25,7 +25,8 @@ cudaError_t launch_bwd_sorted(const float *, const float *, const int64_t *, con
 bool bwd_sorted_applies(const float *value, const float *grad_value, const Dims &);
 cudaError_t launch_fwd_d32_fused(const float *, const int64_t *, const int64_t *, const float *,
                                  long long, const float *, const float *, const Dims &, float *,
-                                 cudaStream_t, bool *handled);
+                                 cudaStream_t, bool *handled, int off_qstride = 0, int logit_qstride = 0,
+                                 const float *off_table = nullptr, const float *logit_table = nullptr);
 cudaError_t launch_bwd_d32_fused(const float *, const float *, const int64_t *, const int64_t *,
                                  const float *, long long, const float *, const float *,
                                  const Dims &, float *, float *, float *, cudaStream_t, bool *handled, int gate);
@@ -47,8 +48,9 @@ cudaError_t launch_add_layernorm_bwd(const float *, const float *, const float *
 cudaError_t launch_linear_wgrad(const float *, const float *, float *, float *, long long, int, int, cudaStream_t,
                                 bool *handled);
 cudaError_t launch_transpose(const float *, float *, long long, int, cudaStream_t);
-cudaError_t launch_group_norm(const float *, const float *, const float *, float *, int, int, int, int, int, float, int,
-                              const float *, int, int, double *, cudaStream_t, bool *handled);
+cudaError_t launch_group_norm(const float *, const float *, const float *, const float *, float *, int, int, int, int,
+                              int, float, int, const float *, int, int, double *, cudaStream_t, bool *handled);
+cudaError_t launch_channel_bias(float *, const float *, int, int, long long, cudaStream_t, bool *handled);
 int group_norm_workspace_doubles(int N, int groups);
 cudaError_t launch_debug_indices(const int64_t *, const int64_t *, const float *, const Dims &,
                                  int32_t *, int64_t *, cudaStream_t);
@@ -231,12 +233,14 @@ int msda_b200_backward_f64(const double *grad_output, const double *value,
                                            grad_sampling_loc, grad_attn_weight, (cudaStream_t)stream);
 }
 
-int msda_b200_fused_forward_f32(const float *value, const int64_t *spatial_shapes,
-                                const int64_t *level_start, const float *reference_points,
-                                long long ref_batch_stride, const float *sampling_offsets,
-                                const float *attn_logits, int batch, int spatial_size, int num_heads,
-                                int channels, int num_levels, int num_query, int num_point,
-                                float *output, void *stream) {
+int msda_b200_fused_forward_strided_f32(const float *value, const int64_t *spatial_shapes,
+                                        const int64_t *level_start, const float *reference_points,
+                                        long long ref_batch_stride, const float *sampling_offsets,
+                                        int offsets_row_stride, const float *attn_logits,
+                                        int logits_row_stride, const float *offsets_table,
+                                        const float *logits_table, int batch, int spatial_size, int num_heads,
+                                        int channels, int num_levels, int num_query, int num_point,
+                                        float *output, void *stream) {
     if (!value || !spatial_shapes || !level_start || !reference_points || !sampling_offsets ||
         !attn_logits || !output)
         return MSDA_ERR_NULL_POINTER;
@@ -244,12 +248,34 @@ int msda_b200_fused_forward_f32(const float *value, const int64_t *spatial_shape
     if (int rc = check_dims(d)) return rc;
     if (ref_batch_stride != 0 && ref_batch_stride != (long long)num_query * num_levels * 2)
         return MSDA_ERR_BAD_SHAPE;
+    const long long packed = (long long)num_heads * num_levels * num_point;
+    if (offsets_row_stride < 2 * packed || logits_row_stride < packed || (offsets_row_stride & 1))
+        return MSDA_ERR_BAD_SHAPE;
+    if ((offsets_table != nullptr) != (logits_table != nullptr)) return MSDA_ERR_NULL_POINTER;
+    if (!aligned16(value) || !aligned16(output) || !aligned8(sampling_offsets) || !aligned8(reference_points) ||
+        !aligned8(offsets_table))
+        return MSDA_ERR_UNSUPPORTED;
     bool handled = false;
     cudaError_t e = launch_fwd_d32_fused(value, spatial_shapes, level_start, reference_points,
                                          ref_batch_stride, sampling_offsets, attn_logits, d, output,
-                                         (cudaStream_t)stream, &handled);
+                                         (cudaStream_t)stream, &handled, offsets_row_stride, logits_row_stride,
+                                         offsets_table, logits_table);
     if (e == cudaSuccess && !handled) return MSDA_ERR_UNSUPPORTED;
     return (int)e;
+}
+
+int msda_b200_fused_forward_f32(const float *value, const int64_t *spatial_shapes,
+                                const int64_t *level_start, const float *reference_points,
+                                long long ref_batch_stride, const float *sampling_offsets,
+                                const float *attn_logits, int batch, int spatial_size, int num_heads,
+                                int channels, int num_levels, int num_query, int num_point,
+                                float *output, void *stream) {
+    return msda_b200_fused_forward_strided_f32(value, spatial_shapes, level_start, reference_points,
+                                               ref_batch_stride, sampling_offsets,
+                                               2 * num_heads * num_levels * num_point, attn_logits,
+                                               num_heads * num_levels * num_point, nullptr, nullptr, batch, spatial_size,
+                                               num_heads, channels, num_levels, num_query, num_point, output,
+                                               stream);
 }
 
 int msda_b200_fused_backward_f32(const float *grad_output, const float *value,
@@ -335,14 +361,25 @@ int msda_b200_linear_wgrad_f32(const float *grad_y, const float *x, float *grad_
     return (int)e;
 }
 
-int msda_b200_group_norm_nchw_f32(const float *x, const float *gamma, const float *beta, float *y, int batch,
-                                  int channels, int height, int width, int groups, float eps, int relu,
-                                  const float *up, int up_h, int up_w, void *workspace, void *stream) {
+int msda_b200_group_norm_nchw_f32(const float *x, const float *channel_bias, const float *gamma, const float *beta,
+                                  float *y, int batch, int channels, int height, int width, int groups, float eps,
+                                  int relu, const float *up, int up_h, int up_w, void *workspace, void *stream) {
     if (!x || !gamma || !beta || !y || !workspace) return MSDA_ERR_NULL_POINTER;
     if (batch <= 0 || channels <= 0 || height <= 0 || width <= 0 || groups <= 0) return MSDA_ERR_BAD_SHAPE;
     bool handled = false;
-    cudaError_t e = launch_group_norm(x, gamma, beta, y, batch, channels, height, width, groups, eps, relu, up, up_h,
-                                      up_w, static_cast<double *>(workspace), (cudaStream_t)stream, &handled);
+    cudaError_t e = launch_group_norm(x, channel_bias, gamma, beta, y, batch, channels, height, width, groups, eps,
+                                      relu, up, up_h, up_w, static_cast<double *>(workspace), (cudaStream_t)stream,
+                                      &handled);
+    if (e == cudaSuccess && !handled) return MSDA_ERR_UNSUPPORTED;
+    return (int)e;
+}
+
+int msda_b200_add_channel_bias_nchw_f32(float *x, const float *bias, int batch, int channels, long long plane,
+                                        void *stream) {
+    if (!x || !bias) return MSDA_ERR_NULL_POINTER;
+    if (batch <= 0 || channels <= 0 || plane <= 0) return MSDA_ERR_BAD_SHAPE;
+    bool handled = false;
+    cudaError_t e = launch_channel_bias(x, bias, batch, channels, plane, (cudaStream_t)stream, &handled);
     if (e == cudaSuccess && !handled) return MSDA_ERR_UNSUPPORTED;
     return (int)e;
 }

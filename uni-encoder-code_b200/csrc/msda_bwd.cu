@@ -249,7 +249,7 @@ static cudaError_t launch_bwd_cfg(const float *grad_out, const float *value, con
                                   const int64_t *lstart, const float *loc, const float *attw,
                                   const Dims &d, float *grad_value, float *grad_loc,
                                   float *grad_attw, cudaStream_t stream,
-                                  Producers pr = Producers{nullptr, 0}, int gate = GATE_NONE) {
+                                  Producers pr = Producers{nullptr, 0, 0, 0, nullptr, nullptr}, int gate = GATE_NONE) {
     using Cfg = BwdCfg<LP, WARPS, TILE_W, QPW>;
     auto kern = msda_bwd_d32_kernel<LP, WARPS, TILE_W, MIN_CTAS, BATCH, QPW, FUSED>;
     // the opt-in shared-memory size is a per-device function attribute: set it (and query the
@@ -292,7 +292,7 @@ static cudaError_t launch_bwd_lp(const float *grad_out, const float *value, cons
     //            queries per warp)
 #define MSDA_BWD(W, TW, C, B, Q) \
     launch_bwd_cfg<LP, W, TW, C, B, Q>(grad_out, value, shapes, lstart, loc, attw, d, gv, gl, gw, st, \
-                                       Producers{nullptr, 0}, gate)
+                                       Producers{nullptr, 0, 0, 0, nullptr, nullptr}, gate)
     switch (option_value(OPT_BWD_VARIANT)) {
         case 1: return MSDA_BWD(8, 8, 4, 1, 8);     //  8 warps, tile  8x8
         case 3: return MSDA_BWD(32, 16, 1, 1, 8);   // 32 warps, tile 16x16, one CTA per SM

@@ -760,7 +760,7 @@ template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int TILE_Q, int SLOTS, in
 static cudaError_t launch_bwd_sorted_cfg(const float *grad_out, const float *value, const int64_t *shapes,
                                          const int64_t *lstart, const float *loc, const float *attw,
                                          const Dims &d, float *gv, float *gl, float *gw, cudaStream_t stream,
-                                         int gate, Producers pr = Producers{nullptr, 0}) {
+                                         int gate, Producers pr = Producers{nullptr, 0, 0, 0, nullptr, nullptr}) {
     using Cfg = SortCfg<LP, WARPS, TILE_W, TILE_Q, SLOTS>;
     auto kern = msda_bwd_sorted_kernel<LP, WARPS, TILE_W, MIN_CTAS, TILE_Q, SLOTS, GW, FUSED>;
     constexpr size_t kSmemBytes = Cfg::kSmem + (FUSED ? (size_t)Cfg::kPoints * sizeof(float) : 0);

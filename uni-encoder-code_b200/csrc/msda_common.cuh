@@ -319,6 +319,14 @@ __device__ __forceinline__ float div_by_size(float a, float b, float rb) {
 struct Producers {
     const float *ref;          // FUSED only
     long long ref_bstride;     // elements between images in `ref` (0: shared by the batch)
+    // FUSED forward only: floats between consecutive queries' rows of the raw offsets / logits (0: packed,
+    // M*L*P*2 and M*L*P) -- lets both live in one [rows, M*L*P*3] projection output
+    int off_qstride;
+    int logit_qstride;
+    // FUSED forward only: per-QUERY additive tables (same row strides, Lq rows, shared by the batch), or null:
+    // the position-embedding part of the two query projections, (src + pos) W^T = src W^T + pos W^T
+    const float *off_table;
+    const float *logit_table;
 };
 
 template <bool FUSED, int LP, int QPW, int PLANE, bool WITH_AUX>
@@ -330,16 +338,45 @@ __device__ __forceinline__ void phase1_records(const LevelTable &lt, uint2 *rec,
     constexpr int kRounds = (QPW * LP + 31) / 32;
     float2 xy[kRounds];
     float aw[kRounds];          // attention weight; FUSED: the raw logit until the softmax below
+    float2 txy[FUSED ? kRounds : 1];   // FUSED with tables: the table entries, added once ALL loads are in flight
+    float taw[FUSED ? kRounds : 1];
+    const long long tab_li = FUSED ? n * Lq * (long long)((pr.off_qstride != 0 ? pr.off_qstride : M * LP * 2) >> 1) : 0;
+    const long long tab_ai = FUSED ? n * Lq * (long long)(pr.logit_qstride != 0 ? pr.logit_qstride : M * LP) : 0;
 #pragma unroll
     for (int r = 0; r < kRounds; ++r) {          // all global loads first
         const int s = r * 32 + lane;
         const int qi = s / LP, sp = s - qi * LP;
         xy[r] = make_float2(0.f, 0.f);
         aw[r] = 0.f;
+        if (FUSED) {
+            txy[r] = make_float2(0.f, 0.f);
+            taw[r] = 0.f;
+        }
         if (qi < cnt) {                           // also false for the padding lanes of the last round
             const long long qrow = (n * Lq + q0 + qi) * M + m;
-            xy[r] = ldg_stream_f2(reinterpret_cast<const float2 *>(loc) + qrow * LP + sp);
-            aw[r] = ldg_stream_f1(attw + qrow * LP + sp);
+            long long li = qrow * LP + sp, ai = li;
+            if (FUSED && pr.off_qstride != 0) {
+                const long long q = n * Lq + q0 + qi;
+                li = q * (pr.off_qstride >> 1) + m * LP + sp;
+                ai = q * pr.logit_qstride + m * LP + sp;
+            }
+            xy[r] = ldg_stream_f2(reinterpret_cast<const float2 *>(loc) + li);
+            aw[r] = ldg_stream_f1(attw + ai);
+            if (FUSED && pr.off_table != nullptr) {
+                // the tables have Lq rows with the projections' row strides: entry = the projection's index
+                // minus the image's n * Lq rows (tab_li / tab_ai below).  Reused by every image, but by one warp
+                // per image: kept out of L1 (whose lines phase 2's value rows live on), served by L2
+                txy[r] = ldg_stream_f2(reinterpret_cast<const float2 *>(pr.off_table) + (li - tab_li));
+                taw[r] = ldg_stream_f1(pr.logit_table + (ai - tab_ai));
+            }
+        }
+    }
+    if (FUSED && pr.off_table != nullptr) {
+#pragma unroll
+        for (int r = 0; r < kRounds; ++r) {
+            xy[r].x += txy[r].x;
+            xy[r].y += txy[r].y;
+            aw[r] += taw[r];
         }
     }
     if (FUSED) {

@@ -129,7 +129,7 @@ msda_fwd_d32_kernel(const float *__restrict__ value, const int64_t *__restrict__
 template <int LP, int WARPS, int TILE_W, int MIN_CTAS, int QPW, bool FUSED = false>
 static cudaError_t launch_fwd_cfg(const float *value, const int64_t *shapes, const int64_t *lstart,
                                   const float *loc, const float *attw, const Dims &d,
-                                  float *out, cudaStream_t stream, Producers pr = Producers{nullptr, 0}) {
+                                  float *out, cudaStream_t stream, Producers pr = Producers{nullptr, 0, 0, 0, nullptr, nullptr}) {
     using Cfg = FwdCfg<LP, WARPS, TILE_W, QPW>;
     auto kern = msda_fwd_d32_kernel<LP, WARPS, TILE_W, MIN_CTAS, QPW, FUSED>;
     // the opt-in shared-memory size is a per-device function attribute: set it (and query the
@@ -208,9 +208,17 @@ cudaError_t launch_fwd_d32(const float *value, const int64_t *shapes, const int6
 cudaError_t launch_fwd_d32_fused(const float *value, const int64_t *shapes, const int64_t *lstart,
                                  const float *ref, long long ref_bstride, const float *off,
                                  const float *logits, const Dims &d, float *out, cudaStream_t stream,
-                                 bool *handled) {
+                                 bool *handled, int off_qstride, int logit_qstride, const float *off_table,
+                                 const float *logit_table) {
     *handled = true;
-    const Producers pr{ref, ref_bstride};
+    const int lp = d.L * d.P;
+    if (off_qstride == d.M * lp * 2 && logit_qstride == d.M * lp) off_qstride = logit_qstride = 0;   // packed
+    const Producers pr{ref, ref_bstride, off_qstride, logit_qstride, off_table, logit_table};
+    if ((off_qstride != 0) != (logit_qstride != 0) || (off_qstride & 1) || off_qstride < 0 || logit_qstride < 0 ||
+        (off_table != nullptr) != (logit_table != nullptr)) {
+        *handled = false;
+        return cudaSuccess;
+    }
     if (d.D != 32 || (long long)d.S * d.M * 8 >= 0x7fffffffLL) {
         *handled = false;
         return cudaSuccess;

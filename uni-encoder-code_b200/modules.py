@@ -198,6 +198,53 @@ class MSDeformAttn(nn.Module):
                          weights.contiguous(), self.im2col_step)
         return _linear(self.output_proj, out, self.linear)
 
+    # ---- inference with a position embedding shared by the batch ----
+    def can_fold_pos(self, src, pos, reference_points, padding_mask=None) -> bool:
+        """Whether `forward_shared_pos` applies: inference kernels on, no mask, 2-d reference points, and
+        `pos` [N or 1, S, C] holding the same rows for every image (batch stride 0, as the pixel decoder's
+        sine embedding + level embedding is)."""
+        return (self.fused and self.linear == "tf32x3" and self._core is _cuda_core
+                and not torch.is_grad_enabled() and padding_mask is None and pos is not None
+                and pos.dim() == 3 and (pos.size(0) == 1 or pos.stride(0) == 0)
+                and pos.shape[1:] == src.shape[1:] and pos[0].is_contiguous()
+                and src.is_cuda and src.dtype == torch.float32 and src.is_contiguous()
+                and pos.dtype == torch.float32 and pos.device == src.device
+                and reference_points.dim() == 4 and reference_points.size(-1) == 2
+                and not reference_points.requires_grad
+                and self.d_model // self.n_heads == 32 and self.n_levels * self.n_points in (4, 8, 12, 16)
+                and ops.linear_tf32x3_supported(src, self.sampling_offsets.weight)
+                and self.sampling_offsets.bias is not None and self.attention_weights.bias is not None)
+
+    def _query_projection(self, pos_rows):
+        """(stacked weight [3*M*L*P, C] of sampling_offsets and attention_weights, table [S, 3*M*L*P] =
+        pos_rows @ weight^T + stacked bias), rebuilt when a parameter or the embedding changes."""
+        params = (self.sampling_offsets.weight, self.sampling_offsets.bias,
+                  self.attention_weights.weight, self.attention_weights.bias)
+        key = tuple((t.data_ptr(), _version_of(t)) for t in params + (pos_rows,)) + (tuple(pos_rows.shape),)
+        if getattr(self, "_qproj_key", None) != key:
+            weight = torch.cat((params[0], params[2]), 0).contiguous()
+            bias = torch.cat((params[1], params[3]), 0).contiguous()
+            # the table keeps `pos_rows` referenced so that its memory cannot be handed to other data
+            self._qproj = (weight, ops.linear_tf32x3(pos_rows, weight, bias), pos_rows)
+            self._qproj_key = key
+        return self._qproj[0], self._qproj[1]
+
+    def forward_shared_pos(self, src, pos, reference_points, input_spatial_shapes, input_level_start_index):
+        """`forward(src + pos, reference_points, src, ...)` without forming `src + pos`: the two query
+        projections run as ONE GEMM on `src`; the fused kernel reads offsets and logits in place from its
+        [N, S, 3*M*L*P] output and adds the cached `pos @ W^T + b` row of the query
+        ((src + pos) W^T + b = src W^T + (pos W^T + b))."""
+        value = self.project_value(src)
+        weight, table = self._query_projection(pos[0])
+        proj = ops.linear_tf32x3(src, weight, None)
+        ref = reference_points
+        if ref.stride(0) == 0:
+            ref = ref[:1]
+        out = ops.ms_deform_attn_fused_forward_packed(value, input_spatial_shapes, input_level_start_index,
+                                                      ref.contiguous(), proj, self.n_levels, self.n_points,
+                                                      query_table=table)
+        return _linear(self.output_proj, out, self.linear)
+
 
 def _activation(name):
     return {"relu": F.relu, "gelu": F.gelu, "glu": F.glu}[name]
@@ -229,8 +276,11 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
                          self.linear)
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
-        q = src if pos is None else src + pos
-        attn = self.self_attn(q, reference_points, src, spatial_shapes, level_start_index, padding_mask)
+        if self.self_attn.can_fold_pos(src, pos, reference_points, padding_mask):
+            attn = self.self_attn.forward_shared_pos(src, pos, reference_points, spatial_shapes, level_start_index)
+        else:
+            q = src if pos is None else src + pos
+            attn = self.self_attn(q, reference_points, src, spatial_shapes, level_start_index, padding_mask)
         return self.forward_ffn(_add_norm(self.norm1, src, self.dropout1(attn), self.linear))
 
 
@@ -332,6 +382,13 @@ class MSDeformAttnTransformerEncoderOnly(nn.Module):
         nn.init.normal_(self.level_embed)
 
     def _level_pos(self, pos_embeds):
+        if not torch.is_grad_enabled() and all(p.size(0) == 1 or p.stride(0) == 0 for p in pos_embeds):
+            # one embedding for the whole batch (the pixel decoder's mask-free sine embedding): keep ONE copy
+            # of the rows and broadcast it, so that callers can tell (batch stride 0)
+            n = pos_embeds[0].size(0)
+            rows = torch.cat([p[:1].flatten(2).transpose(1, 2) + self.level_embed[i].view(1, 1, -1)
+                              for i, p in enumerate(pos_embeds)], 1)
+            return rows.expand(n, -1, -1)
         return torch.cat([p.flatten(2).transpose(1, 2) + self.level_embed[i].view(1, 1, -1)
                           for i, p in enumerate(pos_embeds)], 1)
 

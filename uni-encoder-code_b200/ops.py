@@ -218,6 +218,54 @@ def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, refer
     return output
 
 
+def ms_deform_attn_fused_forward_packed(value, spatial_shapes, level_start_index, reference_points,
+                                        projections, n_levels, n_points, query_table=None):
+    """The fused forward reading the raw offsets and logits in place from ONE projection output
+    ``projections`` [N, Lq, 3*M*L*P] = [sampling_offsets (2*M*L*P) | attn_logits (M*L*P)] per query -- the
+    stacked ``sampling_offsets`` / ``attention_weights`` Linear (ops/modules/ms_deform_attn.py:105-106) run
+    as one GEMM (msda_b200_fused_forward_strided_f32).  ``query_table`` [Lq, 3*M*L*P] (optional) is added to
+    the rows of every image inside the kernel: the part of the projection that depends on the query's
+    position only (``pos @ W^T + b`` when the projection input is ``src + pos``).  Inference only."""
+    N, S, M, D = value.shape
+    L, P = int(n_levels), int(n_points)
+    width = 3 * M * L * P
+    if projections.dim() != 3 or projections.size(0) != N or projections.size(2) != width:
+        raise RuntimeError(f"projections must be [N, Lq, {width}]")
+    Lq = projections.size(1)
+    off = projections[..., :2 * M * L * P]
+    logits = projections[..., 2 * M * L * P:]
+    named = [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+             ("reference_points", reference_points), ("projections", projections)]
+    if query_table is not None:
+        named.append(("query_table", query_table))
+        if tuple(query_table.shape) != (Lq, width) or query_table.dtype != torch.float32:
+            raise RuntimeError(f"query_table must be a float32 [Lq, {width}] tensor")
+    if not value.is_cuda:
+        raise RuntimeError("Not implemented on the CPU")
+    for name, t in named:
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name} tensor has to be contiguous")
+        if not t.is_cuda or t.device != value.device:
+            raise RuntimeError(f"{name} must be a CUDA tensor on {value.device}")
+    if not fused_supported(value, reference_points, off.view(N, Lq, M, L, P, 2), logits) \
+            or tuple(reference_points.shape[1:]) != (Lq, L, 2) or spatial_shapes.size(0) != L \
+            or projections.dtype != torch.float32 or reference_points.dtype != torch.float32:
+        raise RuntimeError("fused MSDA covers fp32, 32 channels per head, L*P in {4,8,12,16}, 2-d "
+                           "reference points only; compose the unfused op for other shapes")
+    rs = 0 if reference_points.size(0) == 1 and N > 1 else Lq * L * 2
+    with torch.cuda.device(value.device):
+        output = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+        with _timed("forward"):
+            rc = _lib.lib.msda_b200_fused_forward_strided_f32(
+                value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                reference_points.data_ptr(), rs, off.data_ptr(), width, logits.data_ptr(), width,
+                query_table.data_ptr() if query_table is not None else None,
+                query_table[:, 2 * M * L * P:].data_ptr() if query_table is not None else None,
+                N, S, M, D, L, Lq, P, output.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "ms_deform_attn_fused_forward_packed")
+    return output
+
+
 def ms_deform_attn_fused_backward(value, spatial_shapes, level_start_index, reference_points,
                                   sampling_offsets, attn_logits, grad_output):
     """[grad_value, grad_sampling_offsets, grad_attn_logits] (msda_b200_fused_backward_f32)."""
@@ -329,8 +377,9 @@ def group_norm_supported(x, norm, up=None) -> bool:
     return ok
 
 
-def group_norm(x, norm, relu=False, up=None):
-    """``norm(x)`` for an ``nn.GroupNorm`` on an NCHW fp32 CUDA map, optionally followed by ReLU and by
+def group_norm(x, norm, relu=False, up=None, channel_bias=None):
+    """``norm(x)`` (``norm(x + channel_bias[None, :, None, None])`` when the producing convolution ran without
+    its bias) for an ``nn.GroupNorm`` on an NCHW fp32 CUDA map, optionally followed by ReLU and by
     ``+ F.interpolate(up, size=x.shape[-2:], mode="bilinear", align_corners=False)`` -- the epilogues of the
     pixel decoder's input projections and FPN level (msdeformattn.py:233-248, :369-379) -- in two passes
     over x (statistics, apply) instead of torch's four to six kernels.  Inference only (no backward)."""
@@ -339,12 +388,17 @@ def group_norm(x, norm, relu=False, up=None):
                            "an affine nn.GroupNorm on the same device and, if given, a contiguous `up` map "
                            "with the same batch and channels")
     N, C, H, W = x.shape
+    if channel_bias is not None and not (channel_bias.is_cuda and channel_bias.device == x.device
+                                         and channel_bias.dtype == torch.float32 and channel_bias.is_contiguous()
+                                         and channel_bias.shape == (C,)):
+        raise RuntimeError("channel_bias must be a contiguous fp32 [C] tensor on x's device")
     y = torch.empty_like(x)
     with torch.cuda.device(x.device):
         ws = torch.empty(int(_lib.lib.msda_b200_group_norm_workspace_bytes(N, norm.num_groups)), dtype=torch.uint8,
                          device=x.device)
         rc = _lib.lib.msda_b200_group_norm_nchw_f32(
-            x.data_ptr(), norm.weight.data_ptr(), norm.bias.data_ptr(), y.data_ptr(), N, C, H, W, norm.num_groups,
+            x.data_ptr(), channel_bias.data_ptr() if channel_bias is not None else None,
+            norm.weight.data_ptr(), norm.bias.data_ptr(), y.data_ptr(), N, C, H, W, norm.num_groups,
             float(norm.eps), int(bool(relu)), up.data_ptr() if up is not None else None,
             up.size(2) if up is not None else 0, up.size(3) if up is not None else 0, ws.data_ptr(),
             torch.cuda.current_stream(x.device).cuda_stream)
@@ -352,11 +406,35 @@ def group_norm(x, norm, relu=False, up=None):
     return y
 
 
-def transpose2d(x):
-    """``x.t().contiguous()`` for a contiguous fp32 CUDA matrix (operand preparation for the weight-gradient GEMM)."""
+def channel_bias_supported(x, bias) -> bool:
+    return (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+            and x.is_contiguous() and x.numel() > 0 and (x.size(2) * x.size(3)) % 4 == 0 and x.data_ptr() % 16 == 0
+            and isinstance(bias, torch.Tensor) and bias.device == x.device and bias.dtype == torch.float32
+            and bias.is_contiguous() and bias.shape == (x.size(1),))
+
+
+def add_channel_bias_(x, bias):
+    """``x += bias[None, :, None, None]`` in place on a contiguous NCHW fp32 CUDA map (the bias of a convolution
+    that ran without one: torch's own broadcast add runs at less than half of the memory roofline)."""
+    if not channel_bias_supported(x, bias):
+        raise RuntimeError("add_channel_bias_ needs a contiguous NCHW fp32 CUDA map with H*W % 4 == 0 and a [C] bias")
+    with torch.cuda.device(x.device):
+        rc = _lib.lib.msda_b200_add_channel_bias_nchw_f32(x.data_ptr(), bias.data_ptr(), x.size(0), x.size(1),
+                                                          x.size(2) * x.size(3),
+                                                          torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(rc, "add_channel_bias_")
+    return x
+
+
+def transpose2d(x, out=None):
+    """``x.t().contiguous()`` for a contiguous fp32 CUDA matrix (operand preparation for the weight-gradient GEMM;
+    the [pixels, C] -> [C, pixels] turn of the encoder memory); ``out``: a contiguous [cols, rows] destination."""
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous() and x.numel() > 0):
         raise RuntimeError("transpose2d needs a contiguous 2-d fp32 CUDA tensor")
-    y = torch.empty(x.size(1), x.size(0), dtype=x.dtype, device=x.device)
+    if out is not None and not (out.is_cuda and out.device == x.device and out.dtype == torch.float32
+                                and out.is_contiguous() and out.numel() == x.numel()):
+        raise RuntimeError("transpose2d: out must be a contiguous fp32 tensor of x's size on x's device")
+    y = torch.empty(x.size(1), x.size(0), dtype=x.dtype, device=x.device) if out is None else out
     with torch.cuda.device(x.device):
         rc = _lib.lib.msda_b200_transpose_f32(x.data_ptr(), y.data_ptr(), x.size(0), x.size(1),
                                               torch.cuda.current_stream(x.device).cuda_stream)

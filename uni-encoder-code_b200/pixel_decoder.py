@@ -156,11 +156,17 @@ class MSDeformAttnPixelDecoder(nn.Module):
             for idx, name in enumerate(self.transformer_in_features[::-1]):
                 x = features[name].float()
                 proj = self.input_proj[idx]
-                y = proj[0](x)
-                if fused_norm and not torch.is_grad_enabled() and ops.group_norm_supported(y, proj[1]):
-                    srcs.append(ops.group_norm(y, proj[1]))
+                if fused_norm and not torch.is_grad_enabled():
+                    # the convolution runs without its bias (torch adds it in a separate pass over the map);
+                    # the GroupNorm kernels add it on the fly
+                    y = F.conv2d(x, proj[0].weight, None, proj[0].stride, proj[0].padding, proj[0].dilation,
+                                 proj[0].groups)
+                    if ops.group_norm_supported(y, proj[1]):
+                        srcs.append(ops.group_norm(y, proj[1], channel_bias=proj[0].bias))
+                    else:
+                        srcs.append(proj[1](y if proj[0].bias is None else y + proj[0].bias.view(1, -1, 1, 1)))
                 else:
-                    srcs.append(proj[1](y))
+                    srcs.append(proj[1](proj[0](x)))
                 pos.append(self.pe_layer(x))
             memory, _, _, _ = self.transformer(srcs, pos)
             n = memory.shape[0]
@@ -168,6 +174,33 @@ class MSDeformAttnPixelDecoder(nn.Module):
             out: List[torch.Tensor] = [z.transpose(1, 2).reshape(n, -1, h, w) for z, (h, w) in
                                        zip(memory.split([h * w for h, w in levels], dim=1), levels)]
             for idx, name in enumerate(self.in_features[:self.num_fpn_levels][::-1]):
-                y = self.lateral_convs[idx](features[name].float(), up=out[-1].contiguous(), fused_norm=fused_norm)
+                y = self.lateral_convs[idx](features[name].float(), up=self._nchw(out[-1], memory, fused_norm),
+                                            fused_norm=fused_norm)
                 out.append(self.output_convs[idx](y, fused_norm=fused_norm))
-            return self.mask_features(out[-1]), out[0], out[:self.oneformer_num_feature_levels]
+            return self._mask_features(out[-1], fused_norm), out[0], out[:self.oneformer_num_feature_levels]
+
+    @staticmethod
+    def _nchw(view, memory, fused_norm):
+        """Contiguous NCHW copy of a level of the encoder memory (`view` = [N, C, H, W] strided over the
+        [N, S, C] memory): one [pixels, C] -> [C, pixels] transpose kernel per image in inference."""
+        if view.is_contiguous():
+            return view
+        n, c, h, w = view.shape
+        if not (fused_norm and not torch.is_grad_enabled() and view.is_cuda and view.dtype == torch.float32
+                and view.stride(1) == 1 and view.stride(3) == c and view.stride(2) == w * c):
+            return view.contiguous()
+        dst = torch.empty((n, c, h, w), dtype=view.dtype, device=view.device)
+        for i in range(n):
+            # view[i] is the transpose of the contiguous [h*w, c] block of rows of image i
+            rows = torch.as_strided(view, (h * w, c), (c, 1), view[i].storage_offset())
+            ops.transpose2d(rows, out=dst[i])
+        return dst
+
+    def _mask_features(self, x, fused_norm):
+        conv = self.mask_features
+        if fused_norm and not torch.is_grad_enabled() and conv.bias is not None:
+            y = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+            if ops.channel_bias_supported(y, conv.bias):
+                return ops.add_channel_bias_(y, conv.bias)
+            return y + conv.bias.view(1, -1, 1, 1)
+        return conv(x)
