@@ -160,7 +160,7 @@ int msda_b200_fused_backward_f32(const float *grad_output, const float *value,
  * weight is then split inside the kernel (for a one-shot "weight", e.g. the transposed activations of a
  * weight-gradient GEMM).  When the output has few tiles and in_features is very large the reduction is
  * spread over several CTAs per tile (split-K: y is zero-filled and accumulated with reductions).  Requires
- * in_features % 32 == 0, out_features % 4 == 0 and 16-byte aligned x / weight / workspace;
+ * in_features % 32 == 0, out_features % 4 == 0 and 16-byte aligned x / weight / workspace / y;
  * MSDA_ERR_UNSUPPORTED otherwise.
  */
 int msda_b200_linear_f32(const float *x, const float *weight, const float *bias, float *y,

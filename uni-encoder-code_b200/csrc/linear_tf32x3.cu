@@ -16,12 +16,13 @@
 // epilogue: one third of the accumulations into the main one.
 //
 // Two kernels in this file (msda_b200_set_option("linear_variant", v) overrides the choice):
-//   * linear_tf32x3_atmem_kernel -- the default for in_features < 512: A operand (x_hi, x_lo) in tensor
-//     memory, see the comment above it;
-//   * linear_tf32x3_kernel -- both operands in shared memory; used with four accumulators {main, main', small,
-//     small'} for in_features >= 512 (the truncating accumulation: error at the fp32 SIMT level needs fewer
-//     MMAs per accumulator), with the weight split inside the kernel when no workspace is given, and split-K
-//     (reductions into the zero-filled output) when the output has few tiles and a very long reduction.
+//   * linear_tf32x3_atmem_kernel -- the default: A operand (x_hi, x_lo) in tensor memory, see the comment
+//     above it; reductions longer than 256 are accumulated in chunks of 256 that the epilogue warps add up
+//     in registers (the truncating accumulation: error at the fp32 SIMT level needs few MMAs per accumulator);
+//   * linear_tf32x3_kernel -- both operands in shared memory; with the weight split inside the kernel when no
+//     workspace is given, and split-K (reductions into the zero-filled output) when the output has few tiles
+//     and a very long reduction; with four accumulators {main, main', small, small'} it was the long-reduction
+//     kernel before the chunked accumulation ("linear_variant" 2).
 //
 // Structure of linear_tf32x3_kernel (persistent: one CTA per SM walks 128 x BN output tiles, BN = 128 or 96;
 // 14 warps):
@@ -39,6 +40,14 @@
 //            32 x 32 transposes through shared memory and 128-byte row-segment stores (or reductions).
 #include "tc_common.cuh"
 
+#ifdef MSDA_PROFILE_KNOBS
+// cycle counters of the pipeline roles (profiling build only; summed over the grid, see tools/whatif_linear_atmem.py)
+__device__ unsigned long long g_lin_dbg[16];
+#define LIN_DBG(...) __VA_ARGS__
+#else
+#define LIN_DBG(...)
+#endif
+
 namespace msda {
 
 using namespace tc;
@@ -48,6 +57,7 @@ namespace {
 constexpr int kSplitWarps = 4;    // warps 2-5
 constexpr int kEpiWarps = 8;      // warps 6-13: two per TMEM lane quarter, alternating 32-column blocks
 constexpr int kThreads = 64 + 32 * (kSplitWarps + kEpiWarps);
+constexpr int kAccChunk = 8;      // k-blocks per accumulation chunk of the A-in-tensor-memory kernel
 
 template <int BN, int STAGES, int NBUF, int NACC>
 struct LinCfg {
@@ -337,12 +347,15 @@ struct LinCfgT {
     static_assert(2 * BN + kStages * 64 <= 512 && kStageBytes % 1024 == 0, "tile shape");
 };
 
-template <int BN>
+template <int BN, bool CHUNKED>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_tf32x3_atmem_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wh,
                            const __grid_constant__ CUtensorMap map_wl, const float *__restrict__ bias,
-                           float *__restrict__ y, int M, int N, int K, int relu) {
+                           float *__restrict__ y, int M, int N, int K, int relu, int kb_chunk, int whatif) {
     using Cfg = LinCfgT<BN>;
+    // timing experiments for profiles/ (results WRONG; profiling build only, msda_b200_set_option("whatif_linear", bits))
+    const bool dbg_no_mma2 = whatif & 1, dbg_no_split = whatif & 2, dbg_no_store = whatif & 4, dbg_no_mma1 = whatif & 8,
+               dbg_narrow = whatif & 16, dbg_alt = whatif & 32, dbg_no_wlo = whatif & 64, dbg_no_w = whatif & 128;
     constexpr int STAGES = Cfg::kStages;
     extern __shared__ uint8_t smem_dyn[];
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -355,6 +368,8 @@ linear_tf32x3_atmem_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(base_ptr + Cfg::kRingBytes + Cfg::kEpiBytes + 8 * (3 * STAGES + 2));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    LIN_DBG(__shared__ volatile long long ts_issue[Cfg::kStages]; __shared__ volatile long long ts_commit[Cfg::kStages];
+            long long d0 = 0, d1 = 0, d2 = 0, d3 = 0; const long long t_start = clock64();)
     const int kblocks = K / kBK;
     const int k_rot = (int)(blockIdx.x % (unsigned)kblocks);
     const int n_tiles = (N + BN - 1) / BN;
@@ -388,25 +403,35 @@ linear_tf32x3_atmem_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
                 for (int kb = 0; kb < kblocks; ++kb, ++g) {
                     const int kk = (kb + k_rot) % kblocks;
                     const int s = g % STAGES;
+                    LIN_DBG(const long long w0 = clock64();)
                     mbar_wait(empty(s), ((g / STAGES) & 1) ^ 1);
+                    LIN_DBG(const long long w1 = clock64(); d0 += w1 - w0; d1 += 1; if (g >= STAGES) d2 += w1 - ts_commit[s]; ts_issue[s] = w1;)
                     const uint32_t st = base + s * Cfg::kStageBytes;
-                    mbar_arrive_expect_tx(full(s), Cfg::kStageBytes);
+                    mbar_arrive_expect_tx(full(s), Cfg::kStageBytes - (dbg_no_w ? 2 : dbg_no_wlo ? 1 : 0) * Cfg::kWBytes);
                     tma_load_2d(st, &map_x, full(s), kk * kBK, m0);
-                    tma_load_2d(st + Cfg::kXBytes, &map_wh, full(s), kk * kBK, n0);
-                    tma_load_2d(st + Cfg::kXBytes + Cfg::kWBytes, &map_wl, full(s), kk * kBK, n0);
+                    if (!dbg_no_w) tma_load_2d(st + Cfg::kXBytes, &map_wh, full(s), kk * kBK, n0);
+                    if (!dbg_no_w && !dbg_no_wlo) tma_load_2d(st + Cfg::kXBytes + Cfg::kWBytes, &map_wl, full(s), kk * kBK, n0);
                 }
             }
+            LIN_DBG(atomicAdd(&g_lin_dbg[0], d0); atomicAdd(&g_lin_dbg[1], d1); atomicAdd(&g_lin_dbg[12], d2);)
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc(kBM, BN), idesc2 = umma_idesc(kBM, 2 * BN);
-            uint32_t g = 0, it = 0;
-            for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
-                mbar_wait(acc_empty, (it & 1) ^ 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t g = 0, it = 0;                                       // it: accumulation chunks so far
+            for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+                int kc = 0;                                                // position in the accumulation chunk
                 for (int kb = 0; kb < kblocks; ++kb, ++g) {
+                    if (kc == 0) {
+                        LIN_DBG(const long long w0 = clock64();)
+                        mbar_wait(acc_empty, (it & 1) ^ 1);
+                        LIN_DBG(d2 += clock64() - w0;)
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
                     const int s = g % STAGES;
+                    LIN_DBG(const long long w2 = clock64();)
                     mbar_wait(ready(s), (g / STAGES) & 1);                 // A slot written (implies the W tiles landed)
+                    LIN_DBG(const long long w3 = clock64(); d0 += w3 - w2;)
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t wh = base + s * Cfg::kStageBytes + Cfg::kXBytes;
                     const uint32_t a_hi = tmem_base + Cfg::kACol + s * 64, a_lo = a_hi + 32;
@@ -414,13 +439,21 @@ linear_tf32x3_atmem_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
                     for (int k = 0; k < kBK / kUmmaK; ++k) {
                         const uint32_t ko = k * kUmmaK * 4;
                         // x_hi * [W_hi; W_lo]^T -> {main, small};  x_lo * W_hi^T -> small
-                        umma_tf32_ts(tmem_base, a_hi + k * kUmmaK, umma_desc(wh + ko), idesc2, (kb | k) != 0);
-                        umma_tf32_ts(tmem_base + BN, a_lo + k * kUmmaK, umma_desc(wh + ko), idesc, 1);
+                        if (!dbg_no_mma1)
+                            umma_tf32_ts(tmem_base, a_hi + k * kUmmaK, umma_desc(wh + ko), dbg_narrow ? idesc : idesc2, (kc | k) != 0);
+                        if (!dbg_no_mma2)     // dbg_alt: into the main accumulator (no dependence on the double-width MMA's small half)
+                            umma_tf32_ts(tmem_base + (dbg_alt ? 0 : BN), a_lo + k * kUmmaK, umma_desc(wh + ko), idesc, 1);
                     }
                     umma_commit(empty(s));                                // smem stage AND TMEM A slot reusable
+                    LIN_DBG(const long long w4 = clock64(); d1 += w4 - w3; ts_commit[s] = w4;)
+                    if (++kc == kb_chunk || kb == kblocks - 1) {
+                        umma_commit(acc_full);                             // this chunk's sums are complete
+                        ++it;
+                        kc = 0;
+                    }
                 }
-                umma_commit(acc_full);
             }
+            LIN_DBG(atomicAdd(&g_lin_dbg[5], d0); atomicAdd(&g_lin_dbg[6], d1); atomicAdd(&g_lin_dbg[7], d2);)
         }
     } else if (warp < 2 + kSplitWarps) {
         // ---- A warps: rows 32*(warp%4) .. +31 of the X tile -> TMEM (x_hi = raw words, x_lo) ----
@@ -429,7 +462,9 @@ linear_tf32x3_atmem_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
         for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
             for (int kb = 0; kb < kblocks; ++kb, ++g) {
                 const int s = g % STAGES;
+                LIN_DBG(const long long w0 = clock64();)
                 mbar_wait(full(s), (g / STAGES) & 1);
+                LIN_DBG(const long long w1 = clock64(); d0 += w1 - w0; d2 += w1 - ts_issue[s];)
                 const uint8_t *xrow = base_ptr + s * Cfg::kStageBytes + row * 128;
                 uint32_t hi[32], lo[32];
 #pragma unroll
@@ -439,63 +474,113 @@ linear_tf32x3_atmem_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
                 }
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                    lo[j] = to_tf32(__uint_as_float(hi[j]) - __uint_as_float(hi[j] & 0xffffe000u));
+                    lo[j] = dbg_no_split ? hi[j] : to_tf32(__uint_as_float(hi[j]) - __uint_as_float(hi[j] & 0xffffe000u));
                 const uint32_t a_hi = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::kACol + s * 64;
                 tmem_st32(a_hi, hi);
                 tmem_st32(a_hi + 32, lo);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 mbar_arrive(ready(s));
+                LIN_DBG(d1 += clock64() - w1;)
             }
         }
+        LIN_DBG(if (warp == 2 && lane == 0) { atomicAdd(&g_lin_dbg[2], d0); atomicAdd(&g_lin_dbg[3], d1); atomicAdd(&g_lin_dbg[4], d2); })
     } else {
         const int q = warp & 3;
-        float *tile = reinterpret_cast<float *>(base_ptr + Cfg::kRingBytes) + (warp - 2 - kSplitWarps) * 32 * 33;
-        uint32_t it = 0;
-        for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+        float4 *tile4 = reinterpret_cast<float4 *>(base_ptr + Cfg::kRingBytes) + (warp - 2 - kSplitWarps) * 32 * 8;
+        uint32_t it = 0;                                                  // accumulation chunks so far
+        for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
             const int m0 = (int)(t / n_tiles) * kBM, n0 = (int)(t % n_tiles) * BN;
             const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16);
-            mbar_wait(acc_full, it & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             // this warp's 32-column blocks: c = part, part + kEpiWarps/4, ...  All of them are read from TMEM
             // (and main + small added) before anything else, so the accumulators go back to the MMA warp after
             // a few hundred cycles; the transposes and stores then overlap with the next tile's MMAs
             constexpr int kStep = kEpiWarps / 4, kMaxBlk = (BN / 32 + kStep - 1) / kStep;
             const int part = (warp - 2 - kSplitWarps) >> 2;
             float sum[kMaxBlk][32];
+            if (!CHUNKED) {
+                LIN_DBG(const long long w0 = clock64();)
+                mbar_wait(acc_full, it & 1);
+                LIN_DBG(d3 = clock64(); d0 += d3 - w0;)
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int i = 0; i < kMaxBlk; ++i) {
-                const int c = part + i * kStep;
-                if (c < BN / 32) {
-                    uint32_t v[32], u[32];
-                    tmem_ld32(acc + (uint32_t)(c * 32), v);
-                    tmem_ld32(acc + (uint32_t)(BN + c * 32), u);
+                for (int i = 0; i < kMaxBlk; ++i) {
+                    const int c = part + i * kStep;
+                    if (c < BN / 32) {
+                        uint32_t v[32], u[32];
+                        tmem_ld32(acc + (uint32_t)(c * 32), v);
+                        tmem_ld32(acc + (uint32_t)(BN + c * 32), u);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) sum[i][j] = __uint_as_float(v[j]) + __uint_as_float(u[j]);
+                        for (int j = 0; j < 32; ++j) sum[i][j] = __uint_as_float(v[j]) + __uint_as_float(u[j]);
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(acc_empty);
+                LIN_DBG(const long long w5 = clock64(); d1 += w5 - d3; d3 = w5;)
+                ++it;
+            } else {
+                // long reductions are accumulated in chunks of kb_chunk k-blocks: the tensor core adds every
+                // MMA into the accumulator with truncation, so the error of one accumulator grows with its
+                // number of MMAs; each chunk starts from fresh accumulators and the chunks are added here in
+                // fp32 registers (round to nearest) -- the error stays at the level of a 256-deep reduction
+#pragma unroll
+                for (int i = 0; i < kMaxBlk; ++i)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sum[i][j] = 0.f;
+                for (int kb0 = 0; kb0 < kblocks; kb0 += kb_chunk, ++it) {
+                    mbar_wait(acc_full, it & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < kMaxBlk; ++i) {
+                        const int c = part + i * kStep;
+                        if (c < BN / 32) {
+                            uint32_t v[32];                                // main, then small
+                            tmem_ld32(acc + (uint32_t)(c * 32), v);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) sum[i][j] += __uint_as_float(v[j]);
+                            tmem_ld32(acc + (uint32_t)(BN + c * 32), v);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) sum[i][j] += __uint_as_float(v[j]);
+                        }
+                    }
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(acc_empty);
                 }
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(acc_empty);
+            // 32 x 32 blocks go through shared memory to turn "lane = row" into row segments: 128-bit accesses both
+            // ways, chunk c of row r at position c ^ (r % 8) (no padding, no bank conflicts), then one 128-bit global
+            // store per lane = four 128-byte row segments per instruction -- a quarter of the instructions of a
+            // scalar loop, which matters beyond the epilogue: these warps share issue slots with the single thread
+            // that feeds the tensor core
+            const int sub = lane >> 3, ch = lane & 7;                    // row within a group of 4, 16-byte chunk
 #pragma unroll
             for (int i = 0; i < kMaxBlk; ++i) {
                 const int c = part + i * kStep;
                 if (c >= BN / 32) continue;
-                const int col = n0 + c * 32;
-                const float b = (bias != nullptr && col + lane < N) ? bias[col + lane] : 0.f;
+                const int col = n0 + c * 32 + ch * 4;                     // this lane's 4 columns in the store loop
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bias != nullptr && col < N) b4 = make_float4(bias[col], bias[col + 1], bias[col + 2], bias[col + 3]);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = sum[i][j];
+                for (int j = 0; j < 8; ++j)
+                    tile4[lane * 8 + (j ^ (lane & 7))] = make_float4(sum[i][4 * j], sum[i][4 * j + 1], sum[i][4 * j + 2], sum[i][4 * j + 3]);
                 __syncwarp();
-#pragma unroll 8
-                for (int r = 0; r < 32; ++r) {
-                    const int rr = m0 + q * 32 + r;
-                    float o = tile[r * 33 + lane] + b;
-                    if (relu) o = fmaxf(o, 0.f);
-                    if (rr < M && col + lane < N) y[(long long)rr * N + col + lane] = o;
+                float *yrow = y + (long long)(m0 + q * 32 + sub) * N + col;
+#pragma unroll
+                for (int r4 = 0; r4 < 8; ++r4) {
+                    const int r = r4 * 4 + sub;
+                    float4 o = tile4[r * 8 + (ch ^ (r & 7))];
+                    o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+                    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    if (m0 + q * 32 + r < M && col < N && !dbg_no_store)
+                        *reinterpret_cast<float4 *>(yrow + (long long)r4 * 4 * N) = o;
                 }
                 __syncwarp();
             }
+            LIN_DBG(if (!CHUNKED) d2 += clock64() - d3;)
         }
+        LIN_DBG(if (warp == 2 + kSplitWarps && lane == 0) { atomicAdd(&g_lin_dbg[8], d0); atomicAdd(&g_lin_dbg[9], d1); atomicAdd(&g_lin_dbg[10], d2); })
     }
+    LIN_DBG(if (threadIdx.x == 0) atomicAdd(&g_lin_dbg[11], clock64() - t_start);)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1)
@@ -570,11 +655,11 @@ cudaError_t launch_linear(const float *x, const float *w, const float *bias, flo
     return cudaGetLastError();
 }
 
-template <int BN>
+template <int BN, bool CHUNKED>
 cudaError_t launch_linear_atmem(const float *x, const float *w, const float *bias, float *y, int M, int N, int K,
                                 int relu, float *workspace, cudaStream_t stream) {
     using Cfg = LinCfgT<BN>;
-    auto kern = linear_tf32x3_atmem_kernel<BN>;
+    auto kern = linear_tf32x3_atmem_kernel<BN, CHUNKED>;
     static std::atomic<bool> attr_set[msda::kMaxDevices];
     {
         cudaError_t e = cudaSuccess;
@@ -596,7 +681,10 @@ cudaError_t launch_linear_atmem(const float *x, const float *w, const float *bia
     note_launch();
     const long long tiles = (long long)((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
     const long long grid = tiles < sm_count() ? tiles : sm_count();
-    kern<<<(unsigned)grid, kThreads, Cfg::kSmem, stream>>>(mx, mwh, mwl, bias, y, M, N, K, relu);
+    // accumulation chunks of 8 k-blocks (256 of the reduction) -- see the epilogue
+    kern<<<(unsigned)grid, kThreads, Cfg::kSmem, stream>>>(mx, mwh, mwl, bias, y, M, N, K, relu,
+                                                           CHUNKED ? kAccChunk : K / kBK,
+                                                           whatif_value(OPT_WHATIF_LINEAR));
     note_launch();
     return cudaGetLastError();
 }
@@ -608,7 +696,8 @@ cudaError_t launch_linear_tf32x3(const float *x, const float *w, const float *bi
                                  int relu, float *workspace, cudaStream_t stream, bool *handled) {
     *handled = true;
     if (M <= 0 || N <= 0 || K <= 0 || K % kBK != 0 || N % 4 != 0 ||
-        (reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(workspace)) % 16 != 0 ||
+        (reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(workspace) |
+         reinterpret_cast<uintptr_t>(y)) % 16 != 0 ||
         ((long long)K * 4) % 16 != 0) {
         *handled = false;
         return cudaSuccess;
@@ -622,15 +711,19 @@ cudaError_t launch_linear_tf32x3(const float *x, const float *w, const float *bi
         if (narrow) return launch_linear<96, 3, 1, 4, true>(x, w, bias, y, M, N, K, relu, workspace, stream);
         return launch_linear<128, 3, 1, 4, true>(x, w, bias, y, M, N, K, relu, workspace, stream);
     }
-    // default for in_features < 512: A operand in tensor memory (fastest; {main, small} accumulators)
-    if (variant == 4 || (variant == 0 && K < 512)) {
-        if (narrow) return launch_linear_atmem<96>(x, w, bias, y, M, N, K, relu, workspace, stream);
-        return launch_linear_atmem<128>(x, w, bias, y, M, N, K, relu, workspace, stream);
+    // default: A operand in tensor memory (fastest; {main, small} accumulators, drained into registers every
+    // 256 of the reduction so that the truncating accumulation never sees more than 64 MMAs per accumulator)
+    if (variant == 4 || variant == 0) {
+        if (K / kBK > kAccChunk) {
+            if (narrow) return launch_linear_atmem<96, true>(x, w, bias, y, M, N, K, relu, workspace, stream);
+            return launch_linear_atmem<128, true>(x, w, bias, y, M, N, K, relu, workspace, stream);
+        }
+        if (narrow) return launch_linear_atmem<96, false>(x, w, bias, y, M, N, K, relu, workspace, stream);
+        return launch_linear_atmem<128, false>(x, w, bias, y, M, N, K, relu, workspace, stream);
     }
-    // long reductions: the truncating accumulation makes the error grow with the number of MMAs per
-    // accumulator, so from in_features = 512 on the products are spread over four accumulators (one set:
-    // the epilogue is not overlapped, ~15 % slower) -- error at the level of an fp32 SIMT GEMM again
-    if (variant == 2 || (variant == 0 && K >= 512)) {
+    // both operands in shared memory, the products spread over four accumulators (one set: the epilogue is
+    // not overlapped) -- the long-reduction kernel before the chunked accumulation above
+    if (variant == 2) {
         if (narrow) return launch_linear<96, 3, 1, 4, false>(x, w, bias, y, M, N, K, relu, workspace, stream);
         return launch_linear<128, 3, 1, 4, false>(x, w, bias, y, M, N, K, relu, workspace, stream);
     }
@@ -639,3 +732,13 @@ cudaError_t launch_linear_tf32x3(const float *x, const float *w, const float *bi
 }
 
 }  // namespace msda
+
+#ifdef MSDA_PROFILE_KNOBS
+// profiling build only: read (and clear) the pipeline cycle counters
+extern "C" int msda_b200_debug_linear_counters(unsigned long long *out16) {
+    cudaError_t e = cudaMemcpyFromSymbol(out16, g_lin_dbg, sizeof(g_lin_dbg));
+    if (e != cudaSuccess) return (int)e;
+    unsigned long long zero[16] = {};
+    return (int)cudaMemcpyToSymbol(g_lin_dbg, zero, sizeof(zero));
+}
+#endif
