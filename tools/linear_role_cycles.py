@@ -11,6 +11,8 @@ pkg = load_package(); lib = pkg._lib.lib; dev = "cuda:0"
 raw = ctypes.CDLL(pkg._lib.LIB_PATH)
 raw.msda_b200_debug_linear_counters.argtypes = [ctypes.c_void_p]
 M = 344064
+knob = int(sys.argv[1]) if len(sys.argv) > 1 else 0      # whatif_linear bits (tools/whatif_linear_atmem.py)
+pkg.set_option("whatif_linear", knob)
 for N, K in ((256, 256), (1024, 256)):
     x = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev) / K ** 0.5; b = torch.randn(N, device=dev)
     y = torch.empty(M, N, device=dev); ws = torch.empty(2 * N * K, device=dev)

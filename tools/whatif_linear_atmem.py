@@ -9,7 +9,7 @@ sys.path.insert(0, ROOT)
 from __graft_entry__ import load_package
 pkg = load_package(); lib = pkg._lib.lib; dev = "cuda:0"
 M = 344064
-for N, K in ((256, 256), (1024, 256), (256, 1024)):
+for N, K in ((256, 256),):
     x = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev) / K ** 0.5; b = torch.randn(N, device=dev)
     y = torch.empty(M, N, device=dev); ws = torch.empty(2 * N * K, device=dev)
     st = torch.cuda.current_stream().cuda_stream
@@ -17,6 +17,17 @@ for N, K in ((256, 256), (1024, 256), (256, 1024)):
                        (8, "no x_hi MMA"), (16, "x_hi MMA single width"), (1 + 16, "one single-width MMA per k-step"),
                        (32, "x_lo MMA into main (no shared accumulator half)"), (1 + 8, "no MMAs"),
                        (1 + 8 + 4, "no MMAs, no stores"), (2 + 4, "no split arithmetic, no stores"),
+                       (256, "no X loads"), (128 + 256, "no loads (barrier traffic only)"),
+                       (1 + 8 + 4 + 128 + 256, "no loads, no MMAs, no stores"),
+                       (1 + 8 + 4 + 512, "no MMAs, no stores, no tcgen05.st"),
+                       (1 + 8 + 4 + 512 + 1024, "no MMAs, no stores, no tcgen05.st, no LDS"),
+                       (1 + 8 + 4 + 128 + 256 + 512 + 1024, "barriers only"),
+                       (1 + 8 + 4 + 128 + 256 + 512 + 1024 + 4096, "barriers only, no epilogue transposes"),
+                       (1 + 8 + 4 + 128 + 256 + 512 + 1024 + 2048, "barriers only, plain arrives instead of tcgen05.commit"),
+                       (1 + 8 + 4 + 128 + 256 + 512 + 1024 + 2048 + 4096, "barriers only, plain arrives, no epilogue transposes"),
+                       (4096, "no epilogue transposes / stores"),
+                       (8192, "mbarrier.test_wait polling instead of try_wait"),
+                       (8192 + 1 + 8 + 4 + 128 + 256 + 512 + 1024, "barriers only, polling"),
                        (64, "no W_lo loads"), (128, "no W loads"), (128 + 4, "no W loads, no stores"),
                        (128 + 1 + 8 + 4, "no W loads, no MMAs, no stores")):
         pkg.set_option("whatif_linear", knob)

@@ -347,15 +347,26 @@ struct LinCfgT {
     static_assert(2 * BN + kStages * 64 <= 512 && kStageBytes % 1024 == 0, "tile shape");
 };
 
-template <int BN, bool CHUNKED>
+template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_tf32x3_atmem_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wh,
                            const __grid_constant__ CUtensorMap map_wl, const float *__restrict__ bias,
                            float *__restrict__ y, int M, int N, int K, int relu, int kb_chunk, int whatif) {
     using Cfg = LinCfgT<BN>;
-    // timing experiments for profiles/ (results WRONG; profiling build only, msda_b200_set_option("whatif_linear", bits))
+    // timing experiments for profiles/ (results WRONG; profiling build only, msda_b200_set_option("whatif_linear", bits);
+    // compile-time false in the shipped library)
+#ifdef MSDA_PROFILE_KNOBS
     const bool dbg_no_mma2 = whatif & 1, dbg_no_split = whatif & 2, dbg_no_store = whatif & 4, dbg_no_mma1 = whatif & 8,
-               dbg_narrow = whatif & 16, dbg_alt = whatif & 32, dbg_no_wlo = whatif & 64, dbg_no_w = whatif & 128;
+               dbg_narrow = whatif & 16, dbg_alt = whatif & 32, dbg_no_wlo = whatif & 64, dbg_no_w = whatif & 128, dbg_no_x = whatif & 256,
+               dbg_no_sttm = whatif & 512, dbg_no_lds = whatif & 1024, dbg_plain_arrive = whatif & 2048,
+               dbg_no_epi = whatif & 4096, dbg_poll = whatif & 8192;
+#else
+    constexpr bool dbg_no_mma2 = false, dbg_no_split = false, dbg_no_store = false, dbg_no_mma1 = false, dbg_narrow = false,
+                   dbg_alt = false, dbg_no_wlo = false, dbg_no_w = false, dbg_no_x = false, dbg_no_sttm = false,
+                   dbg_no_lds = false, dbg_plain_arrive = false, dbg_no_epi = false, dbg_poll = false;
+    (void)whatif;
+#endif
+    auto WAIT = [&](uint32_t bar, uint32_t parity) { if (dbg_poll) mbar_wait_poll(bar, parity); else mbar_wait(bar, parity); };
     constexpr int STAGES = Cfg::kStages;
     extern __shared__ uint8_t smem_dyn[];
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -367,7 +378,9 @@ linear_tf32x3_atmem_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
     const uint32_t acc_full = bars + 8u * 3 * STAGES, acc_empty = acc_full + 8u;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(base_ptr + Cfg::kRingBytes + Cfg::kEpiBytes + 8 * (3 * STAGES + 2));
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the warp index through a shuffle: the compiler then KNOWS it is warp-uniform and keeps the role loops' addresses
+    // and descriptors in uniform registers
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     LIN_DBG(__shared__ volatile long long ts_issue[Cfg::kStages]; __shared__ volatile long long ts_commit[Cfg::kStages];
             long long d0 = 0, d1 = 0, d2 = 0, d3 = 0; const long long t_start = clock64();)
     const int kblocks = K / kBK;
@@ -378,11 +391,11 @@ linear_tf32x3_atmem_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full(s), 1);
-            mbar_init(ready(s), 32 * kSplitWarps);
+            mbar_init(ready(s), kSplitWarps);               // one arrival per warp (lane 0, after __syncwarp)
             mbar_init(empty(s), 1);
         }
         mbar_init(acc_full, 1);
-        mbar_init(acc_empty, 32 * kEpiWarps);
+        mbar_init(acc_empty, kEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -393,7 +406,7 @@ linear_tf32x3_atmem_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -404,11 +417,12 @@ linear_tf32x3_atmem_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
                     const int kk = (kb + k_rot) % kblocks;
                     const int s = g % STAGES;
                     LIN_DBG(const long long w0 = clock64();)
-                    mbar_wait(empty(s), ((g / STAGES) & 1) ^ 1);
+                    WAIT(empty(s), ((g / STAGES) & 1) ^ 1);
                     LIN_DBG(const long long w1 = clock64(); d0 += w1 - w0; d1 += 1; if (g >= STAGES) d2 += w1 - ts_commit[s]; ts_issue[s] = w1;)
                     const uint32_t st = base + s * Cfg::kStageBytes;
-                    mbar_arrive_expect_tx(full(s), Cfg::kStageBytes - (dbg_no_w ? 2 : dbg_no_wlo ? 1 : 0) * Cfg::kWBytes);
-                    tma_load_2d(st, &map_x, full(s), kk * kBK, m0);
+                    mbar_arrive_expect_tx(full(s), Cfg::kStageBytes - (dbg_no_w ? 2 : dbg_no_wlo ? 1 : 0) * Cfg::kWBytes -
+                                                       (dbg_no_x ? Cfg::kXBytes : 0));
+                    if (!dbg_no_x) tma_load_2d(st, &map_x, full(s), kk * kBK, m0);
                     if (!dbg_no_w) tma_load_2d(st + Cfg::kXBytes, &map_wh, full(s), kk * kBK, n0);
                     if (!dbg_no_w && !dbg_no_wlo) tma_load_2d(st + Cfg::kXBytes + Cfg::kWBytes, &map_wl, full(s), kk * kBK, n0);
                 }
@@ -416,71 +430,88 @@ linear_tf32x3_atmem_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
             LIN_DBG(atomicAdd(&g_lin_dbg[0], d0); atomicAdd(&g_lin_dbg[1], d1); atomicAdd(&g_lin_dbg[12], d2);)
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(kBM, BN), idesc2 = umma_idesc(kBM, 2 * BN);
-            uint32_t g = 0, it = 0;                                       // it: accumulation chunks so far
-            for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-                int kc = 0;                                                // position in the accumulation chunk
-                for (int kb = 0; kb < kblocks; ++kb, ++g) {
-                    if (kc == 0) {
-                        LIN_DBG(const long long w0 = clock64();)
-                        mbar_wait(acc_empty, (it & 1) ^ 1);
-                        LIN_DBG(d2 += clock64() - w0;)
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    }
-                    const int s = g % STAGES;
-                    LIN_DBG(const long long w2 = clock64();)
-                    mbar_wait(ready(s), (g / STAGES) & 1);                 // A slot written (implies the W tiles landed)
-                    LIN_DBG(const long long w3 = clock64(); d0 += w3 - w2;)
+        // The whole warp walks the loop (warp-uniform control flow, everything in uniform registers); one elected lane
+        // issues.  A tcgen05.mma is accepted only when the previous one is nearly done (measured: the issue of a
+        // k-block's 8 MMAs takes their execution time), so every instruction BETWEEN two issues is tensor-core idle
+        // time: the descriptors of a k-block differ from the stage's first one by constants.
+        constexpr uint32_t idesc = umma_idesc(kBM, BN), idesc2 = umma_idesc(kBM, 2 * BN);
+        const bool leader = elect_one();
+        uint32_t g = 0, it = 0;                                           // it: accumulation chunks so far
+        LIN_DBG(long long w3 = 0;)
+        for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+            int kc = 0;                                                    // position in the accumulation chunk
+            for (int kb = 0; kb < kblocks; ++kb, ++g) {
+                if (kc == 0) {
+                    LIN_DBG(const long long w0 = clock64();)
+                    WAIT(acc_empty, (it & 1) ^ 1);
+                    LIN_DBG(d2 += clock64() - w0;)
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t wh = base + s * Cfg::kStageBytes + Cfg::kXBytes;
-                    const uint32_t a_hi = tmem_base + Cfg::kACol + s * 64, a_lo = a_hi + 32;
+                }
+                const int s = g % STAGES;
+                LIN_DBG(const long long w2 = clock64();)
+                WAIT(ready(s), (g / STAGES) & 1);                          // A slot written (implies the W tiles landed)
+                LIN_DBG(w3 = clock64(); d0 += w3 - w2;)
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t dw = umma_desc(base + s * Cfg::kStageBytes + Cfg::kXBytes);
+                const uint32_t a_hi = tmem_base + Cfg::kACol + s * 64, a_lo = a_hi + 32;
+                if (leader) {
 #pragma unroll
                     for (int k = 0; k < kBK / kUmmaK; ++k) {
-                        const uint32_t ko = k * kUmmaK * 4;
+                        const uint64_t db = dw + (uint64_t)((k * kUmmaK * 4) >> 4);   // + 32 bytes per k-step (address field, no carry)
                         // x_hi * [W_hi; W_lo]^T -> {main, small};  x_lo * W_hi^T -> small
                         if (!dbg_no_mma1)
-                            umma_tf32_ts(tmem_base, a_hi + k * kUmmaK, umma_desc(wh + ko), dbg_narrow ? idesc : idesc2, (kc | k) != 0);
+                            umma_tf32_ts(tmem_base, a_hi + k * kUmmaK, db, dbg_narrow ? idesc : idesc2, (kc | k) != 0);
                         if (!dbg_no_mma2)     // dbg_alt: into the main accumulator (no dependence on the double-width MMA's small half)
-                            umma_tf32_ts(tmem_base + (dbg_alt ? 0 : BN), a_lo + k * kUmmaK, umma_desc(wh + ko), idesc, 1);
+                            umma_tf32_ts(tmem_base + (dbg_alt ? 0 : BN), a_lo + k * kUmmaK, db, idesc, 1);
                     }
-                    umma_commit(empty(s));                                // smem stage AND TMEM A slot reusable
-                    LIN_DBG(const long long w4 = clock64(); d1 += w4 - w3; ts_commit[s] = w4;)
-                    if (++kc == kb_chunk || kb == kblocks - 1) {
+                    if (dbg_plain_arrive) mbar_arrive(empty(s)); else
+                    umma_commit(empty(s));                                 // smem stage AND TMEM A slot reusable
+                }
+                LIN_DBG(const long long w4 = clock64(); d1 += w4 - w3; if (leader) ts_commit[s] = w4;)
+                if (++kc == kb_chunk || kb == kblocks - 1) {
+                    if (leader) {
+                        if (dbg_plain_arrive) mbar_arrive(acc_full); else
                         umma_commit(acc_full);                             // this chunk's sums are complete
-                        ++it;
-                        kc = 0;
                     }
+                    ++it;
+                    kc = 0;
                 }
             }
-            LIN_DBG(atomicAdd(&g_lin_dbg[5], d0); atomicAdd(&g_lin_dbg[6], d1); atomicAdd(&g_lin_dbg[7], d2);)
         }
+        LIN_DBG(if (leader) { atomicAdd(&g_lin_dbg[5], d0); atomicAdd(&g_lin_dbg[6], d1); atomicAdd(&g_lin_dbg[7], d2); })
     } else if (warp < 2 + kSplitWarps) {
         // ---- A warps: rows 32*(warp%4) .. +31 of the X tile -> TMEM (x_hi = raw words, x_lo) ----
+        // (two warps per lane quarter on alternate k-blocks were tried: the 576-thread CTA's 96-register cap
+        //  spills the epilogue, 0.218 -> 0.242 ms at 256 x 256)
         const int q = warp & 3, row = q * 32 + lane;
         uint32_t g = 0;
         for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
             for (int kb = 0; kb < kblocks; ++kb, ++g) {
                 const int s = g % STAGES;
                 LIN_DBG(const long long w0 = clock64();)
-                mbar_wait(full(s), (g / STAGES) & 1);
+                WAIT(full(s), (g / STAGES) & 1);
                 LIN_DBG(const long long w1 = clock64(); d0 += w1 - w0; d2 += w1 - ts_issue[s];)
                 const uint8_t *xrow = base_ptr + s * Cfg::kStageBytes + row * 128;
                 uint32_t hi[32], lo[32];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {                              // 128-byte swizzle: chunk j sits at j ^ (row % 8)
-                    const uint4 v = *reinterpret_cast<const uint4 *>(xrow + ((j ^ (row & 7)) << 4));
+                    const uint4 v = dbg_no_lds ? make_uint4(j, g, s, row) : *reinterpret_cast<const uint4 *>(xrow + ((j ^ (row & 7)) << 4));
                     hi[4 * j + 0] = v.x; hi[4 * j + 1] = v.y; hi[4 * j + 2] = v.z; hi[4 * j + 3] = v.w;
                 }
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                     lo[j] = dbg_no_split ? hi[j] : to_tf32(__uint_as_float(hi[j]) - __uint_as_float(hi[j] & 0xffffe000u));
                 const uint32_t a_hi = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::kACol + s * 64;
-                tmem_st32(a_hi, hi);
-                tmem_st32(a_hi + 32, lo);
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                if (!dbg_no_sttm) {
+                    tmem_st32(a_hi, hi);
+                    tmem_st32(a_hi + 32, lo);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                } else if (hi[3] == 0x12345u && lo[7] == 0x54321u) {
+                    y[0] = 1.f;                                            // keeps the loads and the split alive
+                }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                mbar_arrive(ready(s));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ready(s));
                 LIN_DBG(d1 += clock64() - w1;)
             }
         }
@@ -498,54 +529,37 @@ linear_tf32x3_atmem_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
             constexpr int kStep = kEpiWarps / 4, kMaxBlk = (BN / 32 + kStep - 1) / kStep;
             const int part = (warp - 2 - kSplitWarps) >> 2;
             float sum[kMaxBlk][32];
-            if (!CHUNKED) {
+            // long reductions are accumulated in chunks of kb_chunk k-blocks: the tensor core adds every MMA
+            // into the accumulator with truncation, so the error of one accumulator grows with its number of
+            // MMAs; each chunk starts from fresh accumulators and the chunks are added here in fp32 registers
+            // (round to nearest) -- the error stays at the level of a 256-deep reduction
+#pragma unroll
+            for (int i = 0; i < kMaxBlk; ++i)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sum[i][j] = 0.f;
+            LIN_DBG(d3 = clock64();)
+            for (int kb0 = 0; kb0 < kblocks; kb0 += kb_chunk, ++it) {
                 LIN_DBG(const long long w0 = clock64();)
-                mbar_wait(acc_full, it & 1);
-                LIN_DBG(d3 = clock64(); d0 += d3 - w0;)
+                WAIT(acc_full, it & 1);
+                LIN_DBG(const long long w1 = clock64(); d0 += w1 - w0;)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                 for (int i = 0; i < kMaxBlk; ++i) {
                     const int c = part + i * kStep;
                     if (c < BN / 32) {
-                        uint32_t v[32], u[32];
+                        uint32_t v[32];                                    // main, then small
                         tmem_ld32(acc + (uint32_t)(c * 32), v);
-                        tmem_ld32(acc + (uint32_t)(BN + c * 32), u);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) sum[i][j] = __uint_as_float(v[j]) + __uint_as_float(u[j]);
+                        for (int j = 0; j < 32; ++j) sum[i][j] += __uint_as_float(v[j]);
+                        tmem_ld32(acc + (uint32_t)(BN + c * 32), v);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) sum[i][j] += __uint_as_float(v[j]);
                     }
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                mbar_arrive(acc_empty);
-                LIN_DBG(const long long w5 = clock64(); d1 += w5 - d3; d3 = w5;)
-                ++it;
-            } else {
-                // long reductions are accumulated in chunks of kb_chunk k-blocks: the tensor core adds every
-                // MMA into the accumulator with truncation, so the error of one accumulator grows with its
-                // number of MMAs; each chunk starts from fresh accumulators and the chunks are added here in
-                // fp32 registers (round to nearest) -- the error stays at the level of a 256-deep reduction
-#pragma unroll
-                for (int i = 0; i < kMaxBlk; ++i)
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) sum[i][j] = 0.f;
-                for (int kb0 = 0; kb0 < kblocks; kb0 += kb_chunk, ++it) {
-                    mbar_wait(acc_full, it & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-                    for (int i = 0; i < kMaxBlk; ++i) {
-                        const int c = part + i * kStep;
-                        if (c < BN / 32) {
-                            uint32_t v[32];                                // main, then small
-                            tmem_ld32(acc + (uint32_t)(c * 32), v);
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) sum[i][j] += __uint_as_float(v[j]);
-                            tmem_ld32(acc + (uint32_t)(BN + c * 32), v);
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) sum[i][j] += __uint_as_float(v[j]);
-                        }
-                    }
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    mbar_arrive(acc_empty);
-                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty);
+                LIN_DBG(d3 = clock64(); d1 += d3 - w1;)
             }
             // 32 x 32 blocks go through shared memory to turn "lane = row" into row segments: 128-bit accesses both
             // ways, chunk c of row r at position c ^ (r % 8) (no padding, no bank conflicts), then one 128-bit global
@@ -556,7 +570,7 @@ linear_tf32x3_atmem_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
 #pragma unroll
             for (int i = 0; i < kMaxBlk; ++i) {
                 const int c = part + i * kStep;
-                if (c >= BN / 32) continue;
+                if (c >= BN / 32 || dbg_no_epi) continue;
                 const int col = n0 + c * 32 + ch * 4;                     // this lane's 4 columns in the store loop
                 float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (bias != nullptr && col < N) b4 = make_float4(bias[col], bias[col + 1], bias[col + 2], bias[col + 3]);
@@ -576,7 +590,7 @@ linear_tf32x3_atmem_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
                 }
                 __syncwarp();
             }
-            LIN_DBG(if (!CHUNKED) d2 += clock64() - d3;)
+            LIN_DBG(d2 += clock64() - d3;)
         }
         LIN_DBG(if (warp == 2 + kSplitWarps && lane == 0) { atomicAdd(&g_lin_dbg[8], d0); atomicAdd(&g_lin_dbg[9], d1); atomicAdd(&g_lin_dbg[10], d2); })
     }
@@ -655,11 +669,11 @@ cudaError_t launch_linear(const float *x, const float *w, const float *bias, flo
     return cudaGetLastError();
 }
 
-template <int BN, bool CHUNKED>
+template <int BN>
 cudaError_t launch_linear_atmem(const float *x, const float *w, const float *bias, float *y, int M, int N, int K,
                                 int relu, float *workspace, cudaStream_t stream) {
     using Cfg = LinCfgT<BN>;
-    auto kern = linear_tf32x3_atmem_kernel<BN, CHUNKED>;
+    auto kern = linear_tf32x3_atmem_kernel<BN>;
     static std::atomic<bool> attr_set[msda::kMaxDevices];
     {
         cudaError_t e = cudaSuccess;
@@ -683,8 +697,7 @@ cudaError_t launch_linear_atmem(const float *x, const float *w, const float *bia
     const long long grid = tiles < sm_count() ? tiles : sm_count();
     // accumulation chunks of 8 k-blocks (256 of the reduction) -- see the epilogue
     kern<<<(unsigned)grid, kThreads, Cfg::kSmem, stream>>>(mx, mwh, mwl, bias, y, M, N, K, relu,
-                                                           CHUNKED ? kAccChunk : K / kBK,
-                                                           whatif_value(OPT_WHATIF_LINEAR));
+                                                           kAccChunk, whatif_value(OPT_WHATIF_LINEAR));
     note_launch();
     return cudaGetLastError();
 }
@@ -714,12 +727,8 @@ cudaError_t launch_linear_tf32x3(const float *x, const float *w, const float *bi
     // default: A operand in tensor memory (fastest; {main, small} accumulators, drained into registers every
     // 256 of the reduction so that the truncating accumulation never sees more than 64 MMAs per accumulator)
     if (variant == 4 || variant == 0) {
-        if (K / kBK > kAccChunk) {
-            if (narrow) return launch_linear_atmem<96, true>(x, w, bias, y, M, N, K, relu, workspace, stream);
-            return launch_linear_atmem<128, true>(x, w, bias, y, M, N, K, relu, workspace, stream);
-        }
-        if (narrow) return launch_linear_atmem<96, false>(x, w, bias, y, M, N, K, relu, workspace, stream);
-        return launch_linear_atmem<128, false>(x, w, bias, y, M, N, K, relu, workspace, stream);
+        if (narrow) return launch_linear_atmem<96>(x, w, bias, y, M, N, K, relu, workspace, stream);
+        return launch_linear_atmem<128>(x, w, bias, y, M, N, K, relu, workspace, stream);
     }
     // both operands in shared memory, the products spread over four accumulators (one set: the epilogue is
     // not overlapped) -- the long-reduction kernel before the chunked accumulation above

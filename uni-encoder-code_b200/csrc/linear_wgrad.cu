@@ -56,7 +56,8 @@ linear_wgrad_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_con
     const uint32_t acc_full = bars + 8u * 3 * kStages, acc_empty = acc_full + 8u;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(base_ptr + Cfg::kRingBytes + Cfg::kEpiBytes + 8 * (3 * kStages + 2));
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the warp index through a shuffle: provably warp-uniform, so the role loops stay in uniform registers
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int kblocks_all = (int)((rows + kBK - 1) / kBK);
     const int n_tiles = (out_f + kBM - 1) / kBM, k_tiles = (in_f + BN - 1) / BN;
     // work items: (row chunk, output tile), output tile fastest -- the items that read the same rows of grad_y
@@ -91,7 +92,7 @@ linear_wgrad_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_con
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0) {
         // ---- TMA producer: plain tiles of grad_y and x, 32 rows each ----
@@ -111,31 +112,34 @@ linear_wgrad_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_con
             }
         }
     } else if (warp == 1) {
-        // ---- MMA issuer ----
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(kBM, BN), idesc2 = umma_idesc(kBM, 2 * BN);
-            uint32_t g = 0, it = 0;
-            for (long long t = blockIdx.x; t < items; t += gridDim.x, ++it) {
-                int n0, k0, kb0, nkb;
-                decode(t, n0, k0, kb0, nkb);
-                mbar_wait(acc_empty, (it & 1) ^ 1);
+        // ---- MMA issuer: the whole warp walks the loop (warp-uniform control flow keeps the descriptors in uniform
+        //      registers: the 8 tcgen05.mma of a k-block issue back to back -- an MMA is accepted only when the previous
+        //      one is nearly done, so instructions between two issues are tensor-core idle time); one elected lane issues
+        constexpr uint32_t idesc = umma_idesc(kBM, BN), idesc2 = umma_idesc(kBM, 2 * BN);
+        const bool leader = elect_one();
+        uint32_t g = 0, it = 0;
+        for (long long t = blockIdx.x; t < items; t += gridDim.x, ++it) {
+            int n0, k0, kb0, nkb;
+            decode(t, n0, k0, kb0, nkb);
+            mbar_wait(acc_empty, (it & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int kb = 0; kb < nkb; ++kb, ++g) {
+                const int s = g % kStages;
+                mbar_wait(ready(s), (g / kStages) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                for (int kb = 0; kb < nkb; ++kb, ++g) {
-                    const int s = g % kStages;
-                    mbar_wait(ready(s), (g / kStages) & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t bh = base + s * Cfg::kStageBytes + Cfg::kYBytes + Cfg::kXBytes;
-                    const uint32_t a_hi = tmem_base + Cfg::kACol + s * 64, a_lo = a_hi + 32;
+                const uint64_t db0 = umma_desc(base + s * Cfg::kStageBytes + Cfg::kYBytes + Cfg::kXBytes);
+                const uint32_t a_hi = tmem_base + Cfg::kACol + s * 64, a_lo = a_hi + 32;
+                if (leader) {
 #pragma unroll
                     for (int k = 0; k < kBK / kUmmaK; ++k) {
-                        const uint32_t ko = k * kUmmaK * 4;
-                        umma_tf32_ts(tmem_base, a_hi + k * kUmmaK, umma_desc(bh + ko), idesc2, (kb | k) != 0);
-                        umma_tf32_ts(tmem_base + BN, a_lo + k * kUmmaK, umma_desc(bh + ko), idesc, 1);
+                        const uint64_t db = db0 + (uint64_t)((k * kUmmaK * 4) >> 4);   // + 32 bytes per k-step (address field)
+                        umma_tf32_ts(tmem_base, a_hi + k * kUmmaK, db, idesc2, (kb | k) != 0);
+                        umma_tf32_ts(tmem_base + BN, a_lo + k * kUmmaK, db, idesc, 1);
                     }
                     umma_commit(empty(s));
                 }
-                umma_commit(acc_full);
             }
+            if (leader) umma_commit(acc_full);
         }
     } else if (warp < 2 + kOpWarps) {
         // ---- operand warps ----

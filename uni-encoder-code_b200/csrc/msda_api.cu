@@ -127,7 +127,7 @@ long long msda_b200_launch_count(void) { return g_launches.load(std::memory_orde
 
 int msda_b200_set_option(const char *name, int value) {
     const int i = option_index(name);
-    if (i < 0 || value < 0 || value > 4096) return MSDA_ERR_BAD_OPTION;
+    if (i < 0 || value < 0 || value > 65535) return MSDA_ERR_BAD_OPTION;
     g_options[i].store(value, std::memory_order_relaxed);
     return MSDA_OK;
 }
