@@ -384,7 +384,6 @@ linear_tf32x3_atmem_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
     LIN_DBG(__shared__ volatile long long ts_issue[Cfg::kStages]; __shared__ volatile long long ts_commit[Cfg::kStages];
             long long d0 = 0, d1 = 0, d2 = 0, d3 = 0; const long long t_start = clock64();)
     const int kblocks = K / kBK;
-    const int k_rot = (int)(blockIdx.x % (unsigned)kblocks);
     const int n_tiles = (N + BN - 1) / BN;
     const long long tiles = (long long)((M + kBM - 1) / kBM) * n_tiles;
 
@@ -414,7 +413,8 @@ linear_tf32x3_atmem_kernel(const __grid_constant__ CUtensorMap map_x, const __gr
             for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
                 const int m0 = (int)(t / n_tiles) * kBM, n0 = (int)(t % n_tiles) * BN;
                 for (int kb = 0; kb < kblocks; ++kb, ++g) {
-                    const int kk = (kb + k_rot) % kblocks;
+                    const int kk = kb;      // the same k order for every tile: a row's result does not depend on which
+                                            // CTA computed it (row-range sharding reproduces the unsharded bits)
                     const int s = g % STAGES;
                     LIN_DBG(const long long w0 = clock64();)
                     WAIT(empty(s), ((g / STAGES) & 1) ^ 1);

@@ -229,14 +229,20 @@ class MSDeformAttn(nn.Module):
             self._qproj_key = key
         return self._qproj[0], self._qproj[1]
 
-    def forward_shared_pos(self, src, pos, reference_points, input_spatial_shapes, input_level_start_index):
+    def forward_shared_pos(self, src, pos, reference_points, input_spatial_shapes, input_level_start_index,
+                           value=None):
         """`forward(src + pos, reference_points, src, ...)` without forming `src + pos`: the two query
         projections run as ONE GEMM on `src`; the fused kernel reads offsets and logits in place from its
         [N, S, 3*M*L*P] output and adds the cached `pos @ W^T + b` row of the query
-        ((src + pos) W^T + b = src W^T + (pos W^T + b))."""
-        value = self.project_value(src)
+        ((src + pos) W^T + b = src W^T + (pos W^T + b)).  `value`: a callable returning the projected value
+        [N, S, M, D] (query-range sharding: `src` holds this rank's rows only and the value rows of the other
+        ranks are still in flight while the query GEMM runs); default: `project_value(src)`."""
+        if value is None:
+            value = self.project_value(src)
         weight, table = self._query_projection(pos[0])
         proj = ops.linear_tf32x3(src, weight, None)
+        if callable(value):
+            value = value()
         ref = reference_points
         if ref.stride(0) == 0:
             ref = ref[:1]

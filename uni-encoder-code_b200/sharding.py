@@ -18,7 +18,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 import torch.distributed as dist
 
-from .modules import MSDeformAttnTransformerEncoderOnly, reference_points_for
+from .modules import MSDeformAttnTransformerEncoderOnly, _add_norm, _linear, reference_points_for
 
 
 def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
@@ -103,14 +103,25 @@ class QueryShardedEncoder:
         a, b = shard_range(S, self.rank, self.world)
         ref = reference_points_for(levels, src.device)[:, a:b].expand(src.shape[0], -1, -1, -1)
         x, p = src[:, a:b], pos[:, a:b]
+        x = x.contiguous()
         for layer in m.encoder.layers:
             attn = layer.self_attn
-            gather = RowGather(attn.value_proj(x), sizes, self.group)      # in flight ...
-            loc, w = attn.sampling_inputs(x + p, ref, shapes)              # ... while the local rows' producers run
-            value = gather.result()
-            value = value.view(value.shape[0], S, attn.n_heads, attn.d_model // attn.n_heads)
-            out = attn._core(value, shapes, lsi, loc.contiguous(), w.contiguous(), attn.im2col_step)
-            x = layer.forward_ffn(layer.norm1(x + layer.dropout1(attn.output_proj(out))))
+            gather = RowGather(_linear(attn.value_proj, x, attn.linear), sizes, self.group)      # in flight ...
+
+            def full_value(gather=gather, attn=attn):
+                v = gather.result()
+                return v.view(v.shape[0], S, attn.n_heads, attn.d_model // attn.n_heads)
+
+            if attn.can_fold_pos(x, p, ref):
+                # ... while the stacked query projection of the local rows runs; the same kernels, the same
+                # per-row arithmetic as the unsharded encoder: results are bit-identical
+                out = attn.forward_shared_pos(x, p, ref, shapes, lsi, value=full_value)
+            else:
+                loc, w = attn.sampling_inputs(x + p, ref, shapes)          # ... while the local rows' producers run
+                out = _linear(attn.output_proj,
+                              attn._core(full_value(), shapes, lsi, loc.contiguous(), w.contiguous(), attn.im2col_step),
+                              attn.linear)
+            x = layer.forward_ffn(_add_norm(layer.norm1, x, layer.dropout1(out), layer.linear))
         return all_gather_rows(x, sizes, self.group), shapes, lsi
 
     __call__ = forward
