@@ -227,3 +227,30 @@ def test_encoder_with_shared_position_embedding_folds_src_plus_pos_into_the_quer
         folded2 = b(srcs, shared)[0]
     assert (folded2 - want2).abs().max().item() <= 5e-5
     assert (folded2 - folded).abs().max().item() > 1e-3
+
+
+@pytest.mark.parametrize("levels,points,shared_ref,lq", [
+    ([(12, 20), (6, 10)], 4, True, None),           # L*P = 8
+    ([(16, 16), (8, 8), (4, 4), (2, 2)], 4, False, None),   # L*P = 16, per-image reference points
+    ([(9, 13)], 4, True, None),                     # L*P = 4, odd sizes
+    ([(16, 32), (8, 16), (4, 8)], 4, True, 301),    # fewer queries than pixels (decoder-style / a rank's row range)
+])
+def test_packed_projection_with_table_on_other_shapes(pkg, levels, points, shared_ref, lq):
+    """Strided offsets / logits + per-query table against the packed tensors with the table added beforehand,
+    over the level / point counts the fused kernels are instantiated for, per-image reference points and Lq != S."""
+    c = make_case(pkg, levels, 2, 8, points, shared_ref, seed=5 + len(levels))
+    d = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in c.items()}
+    L = len(levels)
+    if lq is not None:
+        d["off"], d["logits"], d["ref"] = d["off"][:, :lq].contiguous(), d["logits"][:, :lq].contiguous(), d["ref"][:, :lq].contiguous()
+    N, Lq = d["off"].shape[:2]
+    proj = torch.cat((d["off"].reshape(N, Lq, -1), d["logits"].reshape(N, Lq, -1)), -1).contiguous()
+    table = torch.randn(Lq, proj.shape[-1], device=DEV) * 0.3
+    shifted = (proj + table[None]).contiguous()
+    width = 2 * 8 * L * points
+    want = pkg.ms_deform_attn_fused_forward(d["value"], d["shapes"], d["lsi"], d["ref"],
+                                            shifted[..., :width].reshape(N, Lq, 8, L, points, 2).contiguous(),
+                                            shifted[..., width:].reshape(N, Lq, 8, L * points).contiguous())
+    got = pkg.ops.ms_deform_attn_fused_forward_packed(d["value"], d["shapes"], d["lsi"], d["ref"], proj, L, points,
+                                                      query_table=table)
+    assert torch.equal(got, want)
