@@ -1,0 +1,13 @@
+#!/usr/bin/env python
+"""Markdown table from a tools/sweep.py jsonl: python tools/sweep_table.py sweep.jsonl"""
+import json
+import sys
+
+PEAK = 6540.8
+print("| workload | locations | bwd_variant | forward ms | backward ms | backward % of HBM |")
+print("|---|---|---|---:|---:|---:|")
+for line in open(sys.argv[1]):
+    r = json.loads(line)
+    q = r.get("queries") or r.get("queries_per_step") or 0
+    pct = f"{q * 5376 / r['bwd_ms'] / 1e6 / PEAK * 100:.1f}" if q else ""
+    print(f"| {r['workload']} | {r['mode']} | {r['variant']} | {r['fwd_ms']:.3f} | {r['bwd_ms']:.3f} | {pct} |")
