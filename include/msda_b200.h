@@ -195,7 +195,7 @@ int msda_b200_add_layernorm_backward_f32(const float *grad_y, const float *x, co
  *     if relu:        y = max(y, 0)
  *     if up != NULL:  y += bilinear up-sampling of up[N, C, up_h, up_w] to H x W, align_corners=False
  * `workspace` must hold msda_b200_group_norm_workspace_bytes(N, groups) bytes (per-group partial sums;
- * its contents are meaningless before and after the call).  Needs H*W and W to be multiples of 4 and
+ * its contents are meaningless before and after the call).  Needs H*W (and, with `up`, W) to be a multiple of 4 and
  * 16-byte aligned x / y; MSDA_ERR_UNSUPPORTED otherwise.  Inference only (no backward).
  */
 int msda_b200_group_norm_nchw_f32(const float *x, const float *channel_bias, const float *gamma,

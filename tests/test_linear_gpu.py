@@ -332,6 +332,8 @@ def test_linear_and_wgrad_random_shapes(pkg):
     ((3, 256, 24, 40), 32, False, (12, 20)),     # lateral: GroupNorm + up-sampled add (x2)
     ((1, 64, 10, 28), 8, True, (7, 9)),          # odd up-sampling ratio, 8 channels per group
     ((2, 256, 96, 160), 32, False, (48, 80)),    # larger map: several parts per plane
+    ((2, 64, 12, 39), 32, False, None),          # KITTI pyramid: W not a multiple of 4 (H*W is)
+    ((1, 256, 24, 78), 32, True, None),
 ])
 def test_group_norm_kernel_matches_torch(pkg, shape, groups, relu, up):
     """ops.group_norm == F.group_norm [+ ReLU] [+ F.interpolate(bilinear, align_corners=False)] against
@@ -369,6 +371,9 @@ def test_group_norm_unsupported_shapes_fall_back_in_the_mirror(pkg):
     norm = torch.nn.GroupNorm(4, 8).to(DEV)
     x = torch.randn(1, 8, 5, 7, device=DEV)                 # H*W not a multiple of 4
     assert not pkg.ops.group_norm_supported(x, norm)
+    wide = torch.randn(1, 8, 4, 6, device=DEV)              # W % 4 != 0: fine alone, not with the up-sampled add
+    assert pkg.ops.group_norm_supported(wide, norm)
+    assert not pkg.ops.group_norm_supported(wide, norm, torch.randn(1, 8, 2, 3, device=DEV))
     with pytest.raises(RuntimeError, match="group_norm needs"):
         pkg.group_norm(x, norm)
     conv = pkg.pixel_decoder._ConvNormAct(8, 8, kernel_size=1, norm=norm, activation=torch.nn.functional.relu).to(DEV)

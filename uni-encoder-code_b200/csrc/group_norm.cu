@@ -153,7 +153,8 @@ cudaError_t launch_group_norm(const float *x, const float *cbias, const float *g
                               int uw, double *workspace, cudaStream_t stream, bool *handled) {
     *handled = false;
     const long long hw = (long long)H * W;
-    if (groups <= 0 || C % groups != 0 || (hw & 3) || (W & 3) || hw > 0x7fffffffLL ||
+    // planes are walked as float4 (H*W % 4 == 0); only the up-sampled add needs 4 outputs of one row (W % 4 == 0)
+    if (groups <= 0 || C % groups != 0 || (hw & 3) || (up != nullptr && (W & 3)) || hw > 0x7fffffffLL ||
         (long long)N * C > 0x7fffffffLL || (long long)N * groups > 0x7fffffffLL)
         return cudaSuccess;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15u) return cudaSuccess;

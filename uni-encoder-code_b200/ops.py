@@ -369,11 +369,11 @@ def group_norm_supported(x, norm, up=None) -> bool:
           and x.is_contiguous() and x.numel() > 0 and isinstance(norm, torch.nn.GroupNorm) and norm.affine
           and norm.weight is not None and norm.bias is not None and norm.weight.device == x.device
           and norm.weight.dtype == torch.float32 and norm.weight.is_contiguous() and norm.bias.is_contiguous()
-          and x.size(1) == norm.num_channels and (x.size(2) * x.size(3)) % 4 == 0 and x.size(3) % 4 == 0
+          and x.size(1) == norm.num_channels and (x.size(2) * x.size(3)) % 4 == 0
           and x.data_ptr() % 16 == 0)
     if ok and up is not None:
         ok = (up.is_cuda and up.dtype == torch.float32 and up.dim() == 4 and up.is_contiguous()
-              and up.device == x.device and up.shape[:2] == x.shape[:2])
+              and up.device == x.device and up.shape[:2] == x.shape[:2] and x.size(3) % 4 == 0)
     return ok
 
 
@@ -384,7 +384,7 @@ def group_norm(x, norm, relu=False, up=None, channel_bias=None):
     pixel decoder's input projections and FPN level (msdeformattn.py:233-248, :369-379) -- in two passes
     over x (statistics, apply) instead of torch's four to six kernels.  Inference only (no backward)."""
     if not group_norm_supported(x, norm, up):
-        raise RuntimeError("group_norm needs a contiguous NCHW fp32 CUDA map with H*W and W multiples of 4, "
+        raise RuntimeError("group_norm needs a contiguous NCHW fp32 CUDA map with H*W (and, with `up`, W) a multiple of 4, "
                            "an affine nn.GroupNorm on the same device and, if given, a contiguous `up` map "
                            "with the same batch and channels")
     N, C, H, W = x.shape
