@@ -203,6 +203,17 @@ int msda_b200_group_norm_nchw_f32(const float *x, const float *channel_bias, con
                                   int width, int groups, float eps, int relu, const float *up, int up_h,
                                   int up_w, void *workspace, void *stream);
 long long msda_b200_group_norm_workspace_bytes(int batch, int groups);
+/* The same GroupNorm (+ channel_bias, + ReLU) of x[N, C, plane] written as ROWS,
+ *     y_rows[n * image_stride + pixel * row_stride + c],
+ * the `[N, pixels, C]` layout the deformable encoder consumes (`src.flatten(2).transpose(1, 2)` followed by the
+ * concatenation of the levels, msdeformattn.py:72-79, :87): with y_rows = the level's first row of the
+ * concatenated [N, S, C] tensor, row_stride = C and image_stride = S * C every input projection lands in place
+ * and torch's transposing `cat` disappears.  channels % 32 == 0, plane % 4 == 0, strides % 4 == 0,
+ * 16-byte aligned x / y_rows; MSDA_ERR_UNSUPPORTED otherwise.  Same workspace as above. */
+int msda_b200_group_norm_nchw_to_rows_f32(const float *x, const float *channel_bias, const float *gamma,
+                                          const float *beta, float *y_rows, long long row_stride,
+                                          long long image_stride, int batch, int channels, long long plane,
+                                          int groups, float eps, int relu, void *workspace, void *stream);
 /* x[n, c, :] += bias[c] in place over an NCHW fp32 map (plane = H*W, a multiple of 4; 16-byte aligned x):
  * the bias of the decoder's last 1x1 convolution (mask_features, msdeformattn.py:268-275, :381) at the
  * memory roofline instead of torch's broadcasting add. */

@@ -425,3 +425,48 @@ def test_transpose_into_destination(pkg):
     dst = torch.empty(64, 333, device=DEV)
     got = pkg.ops.transpose2d(x, out=dst)
     assert got.data_ptr() == dst.data_ptr() and torch.equal(dst, x.t())
+
+
+@pytest.mark.parametrize("shape,groups,bias", [((2, 64, 12, 20), 32, True), ((3, 256, 8, 16), 32, False),
+                                               ((1, 32, 6, 10), 8, True), ((2, 256, 24, 78), 32, True),
+                                               ((1, 64, 40, 52), 16, False)])
+def test_group_norm_written_as_rows_of_the_concatenated_tensor(pkg, shape, groups, bias):
+    """ops.group_norm_rows writes norm(x + b)[n, c, p] to rows[n, p, c] of a slice of a larger [N, S, C] tensor
+    (the layout `src.flatten(2).transpose(1, 2)` + `cat` produces) and touches nothing else."""
+    torch.manual_seed(sum(shape))
+    N, C, H, W = shape
+    x = torch.randn(*shape, device=DEV) * 1.5 + 0.25
+    cb = torch.randn(C, device=DEV) if bias else None
+    norm = torch.nn.GroupNorm(groups, C).to(DEV)
+    with torch.no_grad():
+        norm.weight.normal_()
+        norm.bias.normal_()
+        ref_in = x if cb is None else x + cb.view(1, -1, 1, 1)
+        want = F.group_norm(ref_in.double(), groups, norm.weight.double(), norm.bias.double(), norm.eps)
+        want = want.flatten(2).transpose(1, 2)                         # [N, H*W, C]
+        S, start = H * W + 96, 64
+        flat = torch.full((N, S, C), -7.0, device=DEV)
+        rows = flat[:, start:start + H * W]
+        assert pkg.ops.group_norm_rows_supported(x, norm, rows)
+        n0 = pkg.launch_count()
+        got = pkg.ops.group_norm_rows(x, norm, rows, channel_bias=cb)
+        assert pkg.launch_count() - n0 == 2 and got.data_ptr() == rows.data_ptr()
+        assert (rows.double() - want).abs().max().item() <= 1e-5
+        assert bool((flat[:, :start] == -7.0).all()) and bool((flat[:, start + H * W:] == -7.0).all())
+        # the same values as the NCHW kernel, bit for bit
+        assert torch.equal(rows, pkg.group_norm(x, norm, channel_bias=cb).flatten(2).transpose(1, 2))
+        relu = pkg.ops.group_norm_rows(x, norm, torch.empty(N, H * W, C, device=DEV), channel_bias=cb, relu=True)
+        assert (relu.double() - want.clamp_min(0)).abs().max().item() <= 1e-5
+    # a wider row stride is fine (rows of a larger tensor); a channel stride other than 1 is not
+    wide = torch.empty(N, H * W, C + 4, device=DEV)[..., :C]
+    with torch.no_grad():
+        assert torch.equal(pkg.ops.group_norm_rows(x, norm, wide, channel_bias=cb), rows)
+    assert not pkg.ops.group_norm_rows_supported(x, norm, torch.empty(N, C, H * W, device=DEV).transpose(1, 2))
+    with pytest.raises(RuntimeError, match="group_norm_rows needs"):
+        pkg.ops.group_norm_rows(x, norm, torch.empty(N, H * W + 1, C, device=DEV))
+
+
+def test_group_norm_rows_needs_32_channel_blocks(pkg):
+    norm = torch.nn.GroupNorm(4, 16).to(DEV)
+    x = torch.randn(1, 16, 4, 4, device=DEV)
+    assert not pkg.ops.group_norm_rows_supported(x, norm, torch.empty(1, 16, 16, device=DEV))

@@ -145,6 +145,69 @@ group_apply_kernel(const float *__restrict__ x, const double *__restrict__ parti
     }
 }
 
+// The same normalisation written as ROWS: y_rows[n][pixel][c] (row = the C channels of one pixel, `row_stride`
+// floats apart, images `image_stride` floats apart) -- the layout the deformable encoder consumes
+// (`src.flatten(2).transpose(1, 2)`, msdeformattn.py:72-79), so that the per-level maps land directly in
+// their slice of the concatenated [N, S, C] tensor and torch's transposing `cat` (one more read and write of
+// every map) disappears.  One CTA = 32 channels x a range of pixels; a warp turns 32 x 32 tiles through shared
+// memory: 128-byte reads along the pixels of one channel, 128-bit stores along the channels of one pixel.
+constexpr int kRowsWarps = 8;
+constexpr int kRowsTilesPerWarp = 4;      // 32-pixel tiles per warp and CTA
+
+__global__ void __launch_bounds__(kRowsWarps * 32)
+group_apply_rows_kernel(const float *__restrict__ x, const double *__restrict__ partial, const float *__restrict__ gamma,
+                        const float *__restrict__ beta, float *__restrict__ y, int C, long long hw, int cpg, float eps,
+                        const float *__restrict__ cbias, long long row_stride, long long image_stride, int relu) {
+    // blockIdx.x = image * (C / 32) + channel block, blockIdx.y = pixel range
+    __shared__ float s_scale[32], s_shift[32];
+    __shared__ float s_tile[kRowsWarps][32 * 33];
+    const int cblocks = C / 32, n = blockIdx.x / cblocks, c0 = (blockIdx.x % cblocks) * 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < 32) {
+        const int c = c0 + threadIdx.x, groups = C / cpg, g = c / cpg;
+        const long long ng = (long long)n * groups + g;
+        double a = 0.0, b = 0.0;
+        const double *p = partial + ng * kGnSplit * 2;
+        for (int k = 0; k < kGnSplit; ++k) { a += p[2 * k]; b += p[2 * k + 1]; }
+        const double cnt = (double)cpg * (double)hw;
+        const double K = (double)(__ldg(x + ng * cpg * hw) + (cbias ? __ldg(cbias + g * cpg) : 0.f));
+        const double mean_k = a / cnt;
+        double var = b / cnt - mean_k * mean_k;
+        var = var < 0.0 ? 0.0 : var;
+        const float mean = (float)(mean_k + K);
+        const float sc = (float)(1.0 / sqrt(var + (double)eps)) * gamma[c];
+        s_scale[threadIdx.x] = sc;
+        s_shift[threadIdx.x] = beta[c] + ((cbias ? __ldg(cbias + c) : 0.f) - mean) * sc;
+    }
+    __syncthreads();
+    float *tile = s_tile[warp];
+    const float *xin = x + ((long long)n * C + c0) * hw;               // channel c0 of image n
+    float *yout = y + (long long)n * image_stride + c0;
+    const int sub = lane >> 3, ch4 = (lane & 7) * 4;
+    const long long first = ((long long)blockIdx.y * kRowsWarps + warp) * kRowsTilesPerWarp;
+    for (int t = 0; t < kRowsTilesPerWarp; ++t) {
+        const long long p0 = (first + t) * 32;
+        if (p0 >= hw) break;
+        const long long p = p0 + lane;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+            const float v = p < hw ? ldg_stream_f1(xin + (long long)j * hw + p) : 0.f;
+            float o = fmaf(v, s_scale[j], s_shift[j]);
+            if (relu) o = fmaxf(o, 0.f);
+            tile[j * 33 + lane] = o;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int pix = i * 4 + sub;
+            const float4 o = make_float4(tile[(ch4 + 0) * 33 + pix], tile[(ch4 + 1) * 33 + pix],
+                                         tile[(ch4 + 2) * 33 + pix], tile[(ch4 + 3) * 33 + pix]);
+            if (p0 + pix < hw) *reinterpret_cast<float4 *>(yout + (p0 + pix) * row_stride + ch4) = o;
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace
 
 // workspace: N * groups * kGnSplit * 2 doubles
@@ -181,6 +244,37 @@ cudaError_t launch_group_norm(const float *x, const float *cbias, const float *g
     if (up != nullptr) { if (relu) GN_APPLY(true, true); else GN_APPLY(false, true); }
     else { if (relu) GN_APPLY(true, false); else GN_APPLY(false, false); }
 #undef GN_APPLY
+    note_launch();
+    return cudaGetLastError();
+}
+
+// GroupNorm of x[N, C, H*W] written as rows: y[n * image_stride + pixel * row_stride + c]
+cudaError_t launch_group_norm_rows(const float *x, const float *cbias, const float *gamma, const float *beta, float *y,
+                                   int N, int C, long long hw, int groups, float eps, int relu, long long row_stride,
+                                   long long image_stride, double *workspace, cudaStream_t stream, bool *handled) {
+    *handled = false;
+    if (groups <= 0 || C % groups != 0 || C % 32 != 0 || (hw & 3) || hw > 0x7fffffffLL || row_stride < C ||
+        (row_stride & 3) || (image_stride & 3) || (long long)N * (C / 32) > 0x7fffffffLL ||
+        (long long)N * groups > 0x7fffffffLL)
+        return cudaSuccess;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15u) return cudaSuccess;
+    const int cpg = C / groups;
+    const long long chunk = (long long)cpg * hw;
+    if (cbias != nullptr && chunk > 0x7fffffffLL) return cudaSuccess;
+    *handled = true;
+    const dim3 sgrid((unsigned)(N * groups), kGnSplit);
+    if (cbias != nullptr)
+        group_stats_kernel<true><<<sgrid, kGnThreads, 0, stream>>>(x, workspace, chunk, cbias, groups, cpg, (unsigned)(hw >> 2));
+    else
+        group_stats_kernel<false><<<sgrid, kGnThreads, 0, stream>>>(x, workspace, chunk, nullptr, groups, cpg, 1u);
+    note_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const long long per_cta = 32LL * kRowsWarps * kRowsTilesPerWarp;
+    const long long parts = (hw + per_cta - 1) / per_cta;
+    if (parts > 65535) { *handled = false; return cudaSuccess; }
+    group_apply_rows_kernel<<<dim3((unsigned)(N * (C / 32)), (unsigned)parts), kRowsWarps * 32, 0, stream>>>(
+        x, workspace, gamma, beta, y, C, hw, cpg, eps, cbias, row_stride, image_stride, relu);
     note_launch();
     return cudaGetLastError();
 }

@@ -51,6 +51,9 @@ cudaError_t launch_transpose(const float *, float *, long long, int, cudaStream_
 cudaError_t launch_group_norm(const float *, const float *, const float *, const float *, float *, int, int, int, int,
                               int, float, int, const float *, int, int, double *, cudaStream_t, bool *handled);
 cudaError_t launch_channel_bias(float *, const float *, int, int, long long, cudaStream_t, bool *handled);
+cudaError_t launch_group_norm_rows(const float *, const float *, const float *, const float *, float *, int, int,
+                                   long long, int, float, int, long long, long long, double *, cudaStream_t,
+                                   bool *handled);
 int group_norm_workspace_doubles(int N, int groups);
 cudaError_t launch_debug_indices(const int64_t *, const int64_t *, const float *, const Dims &,
                                  int32_t *, int64_t *, cudaStream_t);
@@ -370,6 +373,21 @@ int msda_b200_group_norm_nchw_f32(const float *x, const float *channel_bias, con
     cudaError_t e = launch_group_norm(x, channel_bias, gamma, beta, y, batch, channels, height, width, groups, eps,
                                       relu, up, up_h, up_w, static_cast<double *>(workspace), (cudaStream_t)stream,
                                       &handled);
+    if (e == cudaSuccess && !handled) return MSDA_ERR_UNSUPPORTED;
+    return (int)e;
+}
+
+int msda_b200_group_norm_nchw_to_rows_f32(const float *x, const float *channel_bias, const float *gamma,
+                                          const float *beta, float *y_rows, long long row_stride,
+                                          long long image_stride, int batch, int channels, long long plane,
+                                          int groups, float eps, int relu, void *workspace, void *stream) {
+    if (!x || !gamma || !beta || !y_rows || !workspace) return MSDA_ERR_NULL_POINTER;
+    if (batch <= 0 || channels <= 0 || plane <= 0 || groups <= 0 || row_stride < channels || image_stride < 0)
+        return MSDA_ERR_BAD_SHAPE;
+    bool handled = false;
+    cudaError_t e = launch_group_norm_rows(x, channel_bias, gamma, beta, y_rows, batch, channels, plane, groups, eps,
+                                           relu, row_stride, image_stride, static_cast<double *>(workspace),
+                                           (cudaStream_t)stream, &handled);
     if (e == cudaSuccess && !handled) return MSDA_ERR_UNSUPPORTED;
     return (int)e;
 }

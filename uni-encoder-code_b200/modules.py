@@ -398,9 +398,15 @@ class MSDeformAttnTransformerEncoderOnly(nn.Module):
         return torch.cat([p.flatten(2).transpose(1, 2) + self.level_embed[i].view(1, 1, -1)
                           for i, p in enumerate(pos_embeds)], 1)
 
-    def flatten_inputs(self, srcs, pos_embeds):
-        levels = [(int(s.shape[2]), int(s.shape[3])) for s in srcs]
-        src = torch.cat([s.flatten(2).transpose(1, 2) for s in srcs], 1)
+    def flatten_inputs(self, srcs, pos_embeds, src_flat=None, levels=None):
+        """`src_flat` / `levels` (not in the reference): the per-level maps already laid out as the concatenated
+        [N, S, C] rows (the pixel decoder's fused GroupNorm writes them there), `srcs` is then ignored."""
+        if src_flat is None:
+            levels = [(int(s.shape[2]), int(s.shape[3])) for s in srcs]
+            src = torch.cat([s.flatten(2).transpose(1, 2) for s in srcs], 1)
+        else:
+            levels = [(int(h), int(w)) for h, w in levels]
+            src = src_flat
         if torch.is_grad_enabled():
             pos = self._level_pos(pos_embeds)
         else:
@@ -416,8 +422,8 @@ class MSDeformAttnTransformerEncoderOnly(nn.Module):
         shapes, lsi = level_tensors_for(levels, src.device)
         return src, pos, shapes, lsi, levels
 
-    def forward(self, srcs, pos_embeds):
-        src, pos, shapes, lsi, levels = self.flatten_inputs(srcs, pos_embeds)
+    def forward(self, srcs, pos_embeds, src_flat=None, levels=None):
+        src, pos, shapes, lsi, levels = self.flatten_inputs(srcs, pos_embeds, src_flat, levels)
         # masks are all-False in the reference (msdeformattn.py:68-69): valid ratios are exactly 1
         # and the padding mask changes nothing, so neither is materialised
         memory = self.encoder(src, shapes, lsi, None, pos, None, levels=levels)

@@ -406,6 +406,40 @@ def group_norm(x, norm, relu=False, up=None, channel_bias=None):
     return y
 
 
+def group_norm_rows_supported(x, norm, out_rows) -> bool:
+    """Whether `group_norm_rows` covers these tensors: the map as for `group_norm`, channels a multiple of 32, and
+    `out_rows` an fp32 [N, H*W, C] view with unit channel stride (a slice of the concatenated [N, S, C] tensor)."""
+    return (group_norm_supported(x, norm) and x.size(1) % 32 == 0 and isinstance(out_rows, torch.Tensor)
+            and out_rows.is_cuda and out_rows.device == x.device and out_rows.dtype == torch.float32
+            and out_rows.dim() == 3 and tuple(out_rows.shape) == (x.size(0), x.size(2) * x.size(3), x.size(1))
+            and out_rows.stride(2) == 1 and out_rows.stride(1) >= x.size(1) and out_rows.stride(1) % 4 == 0
+            and out_rows.stride(0) % 4 == 0 and out_rows.data_ptr() % 16 == 0)
+
+
+def group_norm_rows(x, norm, out_rows, channel_bias=None, relu=False):
+    """``out_rows[n, p, c] = norm(x + channel_bias)[n, c, p]`` (p = flattened pixel): GroupNorm of an NCHW map written
+    straight into the ``[N, pixels, C]`` layout of the deformable encoder (``src.flatten(2).transpose(1, 2)``),
+    e.g. into the level's rows of the concatenated tensor.  Inference only (no backward).  Returns out_rows."""
+    if not group_norm_rows_supported(x, norm, out_rows):
+        raise RuntimeError("group_norm_rows needs what group_norm needs, channels % 32 == 0 and an fp32 [N, H*W, C] "
+                           "destination view with unit channel stride on the same device")
+    N, C, H, W = x.shape
+    if channel_bias is not None and not (channel_bias.is_cuda and channel_bias.device == x.device
+                                         and channel_bias.dtype == torch.float32 and channel_bias.is_contiguous()
+                                         and channel_bias.shape == (C,)):
+        raise RuntimeError("channel_bias must be a contiguous fp32 [C] tensor on x's device")
+    with torch.cuda.device(x.device):
+        ws = torch.empty(int(_lib.lib.msda_b200_group_norm_workspace_bytes(N, norm.num_groups)), dtype=torch.uint8,
+                         device=x.device)
+        rc = _lib.lib.msda_b200_group_norm_nchw_to_rows_f32(
+            x.data_ptr(), channel_bias.data_ptr() if channel_bias is not None else None, norm.weight.data_ptr(),
+            norm.bias.data_ptr(), out_rows.data_ptr(), out_rows.stride(1), out_rows.stride(0), N, C, H * W,
+            norm.num_groups, float(norm.eps), int(bool(relu)), ws.data_ptr(),
+            torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(rc, "group_norm_rows")
+    return out_rows
+
+
 def channel_bias_supported(x, bias) -> bool:
     return (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
             and x.is_contiguous() and x.numel() > 0 and (x.size(2) * x.size(3)) % 4 == 0 and x.data_ptr() % 16 == 0

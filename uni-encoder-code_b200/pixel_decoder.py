@@ -153,7 +153,15 @@ class MSDeformAttnPixelDecoder(nn.Module):
         with torch.autocast(device_type=next(iter(features.values())).device.type, enabled=False):
             srcs, pos = [], []
             fused_norm = self.linear == "tf32x3"        # the inference kernels of SURVEY 8f.3 / 8f.4
-            for idx, name in enumerate(self.transformer_in_features[::-1]):
+            names = self.transformer_in_features[::-1]
+            levels = [(int(features[k].shape[2]), int(features[k].shape[3])) for k in names]
+            # inference kernels: every input projection's GroupNorm writes its rows of the concatenated
+            # [N, S, C] tensor directly (no transposing `cat` afterwards) when all levels qualify
+            src_flat, starts = None, [0]
+            for h, w in levels:
+                starts.append(starts[-1] + h * w)
+            rows_ok = fused_norm and not torch.is_grad_enabled()
+            for idx, name in enumerate(names):
                 x = features[name].float()
                 proj = self.input_proj[idx]
                 if fused_norm and not torch.is_grad_enabled():
@@ -161,16 +169,28 @@ class MSDeformAttnPixelDecoder(nn.Module):
                     # the GroupNorm kernels add it on the fly
                     y = F.conv2d(x, proj[0].weight, None, proj[0].stride, proj[0].padding, proj[0].dilation,
                                  proj[0].groups)
-                    if ops.group_norm_supported(y, proj[1]):
-                        srcs.append(ops.group_norm(y, proj[1], channel_bias=proj[0].bias))
+                    if rows_ok and src_flat is None:
+                        src_flat = y.new_empty((y.shape[0], starts[-1], y.shape[1]))
+                    rows = src_flat[:, starts[idx]:starts[idx + 1]] if rows_ok else None
+                    if rows_ok and ops.group_norm_rows_supported(y, proj[1], rows):
+                        ops.group_norm_rows(y, proj[1], rows, channel_bias=proj[0].bias)
+                        srcs.append(None)
                     else:
-                        srcs.append(proj[1](y if proj[0].bias is None else y + proj[0].bias.view(1, -1, 1, 1)))
+                        if ops.group_norm_supported(y, proj[1]):
+                            z = ops.group_norm(y, proj[1], channel_bias=proj[0].bias)
+                        else:
+                            z = proj[1](y if proj[0].bias is None else y + proj[0].bias.view(1, -1, 1, 1))
+                        srcs.append(z)
+                        if rows_ok:                                   # keep the rows complete: this level through torch
+                            rows.copy_(z.flatten(2).transpose(1, 2))
                 else:
                     srcs.append(proj[1](proj[0](x)))
                 pos.append(self.pe_layer(x))
-            memory, _, _, _ = self.transformer(srcs, pos)
+            if rows_ok:
+                memory, _, _, _ = self.transformer(None, pos, src_flat=src_flat, levels=levels)
+            else:
+                memory, _, _, _ = self.transformer(srcs, pos)
             n = memory.shape[0]
-            levels = [(int(s.shape[2]), int(s.shape[3])) for s in srcs]
             out: List[torch.Tensor] = [z.transpose(1, 2).reshape(n, -1, h, w) for z, (h, w) in
                                        zip(memory.split([h * w for h, w in levels], dim=1), levels)]
             for idx, name in enumerate(self.in_features[:self.num_fpn_levels][::-1]):
