@@ -13,7 +13,8 @@ for N, K in ((256, 256),):
     x = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev) / K ** 0.5; b = torch.randn(N, device=dev)
     y = torch.empty(M, N, device=dev); ws = torch.empty(2 * N * K, device=dev)
     st = torch.cuda.current_stream().cuda_stream
-    for knob, what in ((0, "as shipped"), (4, "no output stores"), (2, "no split arithmetic"), (1, "no x_lo MMA"),
+    for knob, what in ((0, "as shipped"), (512, "no tcgen05.st (MMAs read stale A)"), (512 + 1024, "no tcgen05.st, no shared-memory loads in the split warps"),
+                       (512 + 1024 + 2, "split warps: wait and arrive only"), (4, "no output stores"), (2, "no split arithmetic"), (1, "no x_lo MMA"),
                        (8, "no x_hi MMA"), (16, "x_hi MMA single width"), (1 + 16, "one single-width MMA per k-step"),
                        (32, "x_lo MMA into main (no shared accumulator half)"), (1 + 8, "no MMAs"),
                        (1 + 8 + 4, "no MMAs, no stores"), (2 + 4, "no split arithmetic, no stores"),
