@@ -264,10 +264,10 @@ int msda_b200_debug_indices_f32(const int64_t *spatial_shapes, const int64_t *le
  *   "tile_order"   0 = auto (2-D tiles when the queries are laid out like the value pixels),
  *                  1 = groups of consecutive queries
  *   "ctas_per_sm"  0 = occupancy limit, k > 0 caps the persistent grid at k CTAs per SM
- *   "linear_variant"  msda_b200_linear_f32: 0 = auto (128/96-column tiles; A operand in tensor memory
- *                  for in_features < 512, four accumulators in one set with both operands in shared
- *                  memory from 512 on), 2 = four accumulators in one set, 3 = two {main, small} sets
- *                  with both operands in shared memory, 4 = A operand in tensor memory always
+ *   "linear_variant"  msda_b200_linear_f32: 0 = auto (128/96-column tiles, A operand in tensor memory,
+ *                  reductions longer than 256 accumulated in chunks of 256 that are added in registers),
+ *                  2 = both operands in shared memory with four accumulators in one set, 3 = the same with
+ *                  two {main, small} sets, 4 = same as 0
  *   "wgrad_chunk"  msda_b200_linear_wgrad_f32: 32-row blocks per work item (0 = 16, i.e. 512 rows)
  * Only in the profiling build (`make -C uni-encoder-code_b200/csrc profile`, -DMSDA_PROFILE_KNOBS; the
  * shipped library rejects the names): "whatif_drop_reds" and "whatif_linear" make kernels SKIP work on
