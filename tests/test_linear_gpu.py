@@ -194,6 +194,53 @@ def test_linear_autograd_function_matches_torch(pkg):
         assert (mine.grad.double() - ref.grad.double()).abs().max().item() <= 1e-5 * max(1.0, ref.grad.abs().max().item())
 
 
+def test_linear_autograd_function_with_relu_in_the_epilogue(pkg):
+    """apply(x, w, b, True) == F.relu(F.linear(x, w, b)) forward and backward (the mask comes from the saved output)."""
+    x, w, b = case(700, 1024, 256, seed=13)
+    x1, w1, b1 = (t.clone().requires_grad_(True) for t in (x, w, b))
+    x2, w2, b2 = (t.clone().requires_grad_(True) for t in (x, w, b))
+    cot = torch.randn(700, 1024, device=DEV)
+    n0 = pkg.launch_count()
+    y1 = pkg.LinearTF32x3Function.apply(x1, w1, b1, True)
+    assert pkg.launch_count() - n0 == 2 and float(y1.min()) == 0.0
+    (y1 * cot).sum().backward()
+    y2 = F.relu(F.linear(x2.double(), w2.double(), b2.double()))
+    # the sign of an output within rounding of zero may differ between the two GEMMs: mask the cotangent there
+    near_zero = (F.linear(x.double(), w.double(), b.double()).abs() < 1e-5)
+    assert (y1.double() - y2).abs().max().item() <= 1e-5
+    (y2 * cot.double().masked_fill(near_zero, 0.0)).sum().backward()
+    x3, w3, b3 = (t.clone().requires_grad_(True) for t in (x, w, b))
+    (pkg.LinearTF32x3Function.apply(x3, w3, b3, True) * cot.masked_fill(near_zero, 0.0)).sum().backward()
+    for mine, ref in ((x3, x2), (w3, w2), (b3, b2)):
+        assert (mine.grad.double() - ref.grad.double()).abs().max().item() <= 2e-5 * max(1.0, ref.grad.abs().max().item())
+
+
+def test_linear_autograd_function_with_relu_and_dropout(pkg):
+    """apply(x, w, b, True, p) == F.dropout(F.relu(F.linear(x, w, b)), p, True) with the same generator state: the
+    same mask (torch's own dropout kernel draws it), the same outputs and gradients."""
+    x, w, b = case(600, 1024, 256, seed=14)
+    p = 0.1
+    cot = torch.randn(600, 1024, device=DEV)
+    near_zero = (F.linear(x.double(), w.double(), b.double()).abs() < 1e-5)
+    cot = cot.masked_fill(near_zero, 0.0)
+    x1, w1, b1 = (t.clone().requires_grad_(True) for t in (x, w, b))
+    x2, w2, b2 = (t.clone().requires_grad_(True) for t in (x, w, b))
+    torch.manual_seed(99)
+    y1 = pkg.LinearTF32x3Function.apply(x1, w1, b1, True, p)
+    (y1 * cot).sum().backward()
+    torch.manual_seed(99)
+    y2 = F.dropout(F.relu(F.linear(x2.double(), w2.double(), b2.double())).float(), p, True)
+    dropped = (y2 == 0) & (F.linear(x.double(), w.double(), b.double()) > 1e-5)
+    assert 0.05 < dropped.float().mean().item() / max((F.linear(x.double(), w.double(), b.double()) > 1e-5).float().mean().item(), 1e-9) < 0.15
+    assert torch.equal((y1 == 0) | near_zero, (y2 == 0) | near_zero)          # the same mask
+    assert (y1.double() - y2.double()).abs().max().item() <= 2e-5
+    (y2.double() * cot.double()).sum().backward()
+    for mine, ref in ((x1, x2), (w1, w2), (b1, b2)):
+        assert (mine.grad.double() - ref.grad.double()).abs().max().item() <= 2e-5 * max(1.0, ref.grad.abs().max().item())
+    with pytest.raises(ValueError, match="dropout_p needs"):
+        pkg.LinearTF32x3Function.apply(x1, w1, b1, False, p)
+
+
 @pytest.mark.parametrize("rows,out_f,in_f", [(4096, 256, 256), (8192, 96, 256), (2080, 1024, 256), (6400, 256, 1024),
                                             (64, 128, 64)])
 def test_linear_weight_gradient_gemm_split_k_in_kernel_split(pkg, rows, out_f, in_f):

@@ -8,6 +8,7 @@ without the reference checkout (the GPU box, bench.py) has the same entry point.
 """
 from __future__ import annotations
 
+import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
@@ -64,7 +65,14 @@ class LinearTF32x3Function(Function):
     input gradient (``grad_y @ weight``) through ops.linear_tf32x3, weight and bias gradient
     (``grad_y^T @ x``, column sums of ``grad_y``) through ops.linear_wgrad, which reduces over the rows
     without transposing the operands in memory (0.15 ms against 0.53 + 0.12 ms for torch's fp32 GEMM and
-    column sum at 172 032 x 256 x 256).  Needs in_features and out_features divisible by 32."""
+    column sum at 172 032 x 256 x 256).  Needs in_features and out_features divisible by 32.
+    ``apply(x, weight, bias, True)`` = ``F.relu(F.linear(...))`` with the ReLU in the GEMM's epilogue (no separate
+    pass over the output); its backward masks ``grad_y`` where the saved output is zero, as ``F.relu`` does.
+    ``apply(x, weight, bias, True, p)`` = ``F.dropout(F.relu(F.linear(...)), p, training=True)`` (the FFN's hidden
+    activation, msdeformattn.py:126-130): the mask is drawn by torch's own dropout kernel (same generator stream
+    as ``F.dropout``); a kept element is positive exactly where the ReLU was active, so the backward needs ONE pass
+    over the hidden gradient (``threshold_backward`` against the saved output) instead of two, and the 1/(1-p)
+    scale moves onto the small tensors (the transposed weight, grad_weight, grad_bias)."""
 
     @staticmethod
     def supported(x, weight) -> bool:
@@ -72,19 +80,38 @@ class LinearTF32x3Function(Function):
                 and weight.size(0) % 32 == 0 and weight.size(1) % 32 == 0)
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
-        ctx.save_for_backward(x, weight)
+    def forward(ctx, x, weight, bias, relu=False, dropout_p=0.0):
+        if dropout_p and not (relu and 0.0 < dropout_p < 1.0):
+            raise ValueError("dropout_p needs relu=True and 0 < p < 1")
+        y = ops.linear_tf32x3(x, weight.contiguous(), bias, relu=relu)
         ctx.has_bias = bias is not None
-        return ops.linear_tf32x3(x, weight.contiguous(), bias)
+        ctx.relu = bool(relu)
+        ctx.scale = 1.0
+        if dropout_p:
+            y, _ = torch.native_dropout(y, float(dropout_p), True)       # y * mask / (1 - p)
+            ctx.scale = 1.0 / (1.0 - float(dropout_p))
+        if relu:
+            ctx.save_for_backward(x, weight, y)
+        else:
+            ctx.save_for_backward(x, weight)
+        return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_y):
-        x, weight = ctx.saved_tensors
+        if ctx.relu:
+            x, weight, y = ctx.saved_tensors
+            # F.relu's backward; with dropout, y > 0 exactly where the element was kept AND the ReLU was active,
+            # and the scale 1/(1-p) is applied to the results below instead of to this (large) tensor
+            grad_y = torch.ops.aten.threshold_backward(grad_y, y, 0)
+        else:
+            x, weight = ctx.saved_tensors
         grad_y = grad_y.contiguous()
+        scale = ctx.scale
         grad_x = grad_w = grad_b = None
         if ctx.needs_input_grad[0]:
-            grad_x = ops.linear_tf32x3(grad_y, weight.t().contiguous(), None)
+            wt = weight.t().contiguous() if scale == 1.0 else (weight.t() * scale).contiguous()
+            grad_x = ops.linear_tf32x3(grad_y, wt, None)
         g2 = grad_y.reshape(-1, grad_y.size(-1))
         want_b = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
@@ -95,7 +122,10 @@ class LinearTF32x3Function(Function):
                 grad_w = g2.t() @ x2
         if want_b and grad_b is None:
             grad_b = g2.sum(0)
-        return grad_x, grad_w, grad_b
+        if scale != 1.0:
+            grad_w = grad_w * scale if grad_w is not None else None
+            grad_b = grad_b * scale if grad_b is not None else None
+        return grad_x, grad_w, grad_b, None, None
 
 
 class AddLayerNormFunction(Function):

@@ -84,8 +84,8 @@ def _linear(layer: nn.Linear, x, impl: str, relu: bool = False):
             and ops.linear_tf32x3_supported(x, layer.weight):
         return ops.linear_tf32x3(x, layer.weight, layer.bias, relu=relu)
     if impl == "tf32x3" and torch.is_grad_enabled() and LinearTF32x3Function.supported(x, layer.weight):
-        y = LinearTF32x3Function.apply(x, layer.weight, layer.bias)      # forward and grad_x on the tensor cores
-        return F.relu(y) if relu else y
+        # all three GEMMs on the tensor cores; the ReLU rides in the forward GEMM's epilogue
+        return LinearTF32x3Function.apply(x, layer.weight, layer.bias, relu)
     if impl not in ("torch", "tf32x3"):
         raise ValueError(f"unknown linear implementation {impl!r}")
     y = layer(x)
@@ -274,12 +274,18 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
         self.norm2 = nn.LayerNorm(d_model)
 
     def forward_ffn(self, src):
-        if self.activation is F.relu:              # ReLU rides in the GEMM epilogue of the tf32x3 kernel
-            hidden = _linear(self.linear1, src, self.linear, relu=True)
+        p = self.dropout2.p if self.dropout2.training else 0.0
+        if (self.activation is F.relu and self.linear == "tf32x3" and torch.is_grad_enabled() and 0.0 < p < 1.0
+                and LinearTF32x3Function.supported(src, self.linear1.weight)):
+            # training: linear1 + ReLU + dropout2 as one autograd node (one pass over the hidden gradient)
+            hidden = LinearTF32x3Function.apply(src, self.linear1.weight, self.linear1.bias, True, p)
         else:
-            hidden = self.activation(_linear(self.linear1, src, self.linear))
-        return _add_norm(self.norm2, src, self.dropout3(_linear(self.linear2, self.dropout2(hidden), self.linear)),
-                         self.linear)
+            if self.activation is F.relu:          # ReLU rides in the GEMM epilogue of the tf32x3 kernel
+                hidden = _linear(self.linear1, src, self.linear, relu=True)
+            else:
+                hidden = self.activation(_linear(self.linear1, src, self.linear))
+            hidden = self.dropout2(hidden)
+        return _add_norm(self.norm2, src, self.dropout3(_linear(self.linear2, hidden, self.linear)), self.linear)
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
         if self.self_attn.can_fold_pos(src, pos, reference_points, padding_mask):
