@@ -104,3 +104,62 @@ def test_forward_features_is_cuda_graph_capturable(pkg, fused, linear):
     assert torch.equal(out[0], eager[0]) and torch.equal(out[1], eager[1])
     for a, b in zip(out[2], eager[2]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_inference_kernels_under_inference_mode_and_repeated_calls(pkg):
+    """The inference path (fused kernels, cached tables) gives the same bits under torch.inference_mode() as under
+    no_grad, call after call (the caches are keyed on tensor versions, which inference tensors do not have)."""
+    m, feats, g = build(pkg, device="cuda:0", fused=True, linear="tf32x3")
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False          # the golden is true fp32 (cuDNN convolutions default to TF32)
+    try:
+        with torch.no_grad():
+            a = m.forward_features(feats)
+        with torch.inference_mode():
+            b = m.forward_features(feats)
+            c = m.forward_features({k: v.clone() for k, v in feats.items()})
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    for x, y, z in zip([a[0], a[1], *a[2]], [b[0], b[1], *b[2]], [c[0], c[1], *c[2]]):
+        assert torch.equal(x, y) and torch.equal(x, z)
+    check(b, g, 5e-4)
+
+
+@pytest.mark.gpu
+def test_full_width_decoder_with_every_inference_kernel_matches_the_torch_path(pkg):
+    """conv_dim 256 / 8 heads (32 channels per head, the shape the fused kernels cover): GroupNorm written as
+    rows of the concatenated tensor, `src + pos` folded into the per-query table, stacked query GEMM read in
+    place, channel bias, transposes -- all on, against the same weights on torch's fp32 kernels."""
+    torch.manual_seed(5)
+    kw = dict(transformer_dropout=0.0, transformer_nheads=8, transformer_dim_feedforward=1024,
+              transformer_enc_layers=2, conv_dim=256, mask_dim=256, norm="GN",
+              transformer_in_features=["res3", "res4", "res5"], common_stride=4)
+    shapes = {"res2": (96, 4), "res3": (192, 8), "res4": (384, 16), "res5": (768, 32)}
+    ref = pkg.pixel_decoder.MSDeformAttnPixelDecoder(shapes, **kw).cuda().eval()
+    fast = pkg.pixel_decoder.MSDeformAttnPixelDecoder(shapes, fused=True, linear="tf32x3", **kw).cuda().eval()
+    for m in ref.modules():                                    # away from the zero-initialised producers
+        if isinstance(m, pkg.modules.MSDeformAttn):
+            torch.nn.init.normal_(m.sampling_offsets.weight, std=0.02)
+            torch.nn.init.normal_(m.attention_weights.weight, std=0.05)
+    fast.load_state_dict(ref.state_dict())
+    feats = {k: torch.randn(2, c, 128 // s, 256 // s, device="cuda:0") for k, (c, s) in shapes.items()}
+    tf32_conv, tf32_mm = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            want = ref.forward_features(feats)
+            n0 = pkg.launch_count()
+            got = fast.forward_features(feats)
+            first = pkg.launch_count() - n0
+            n0 = pkg.launch_count()
+            again = fast.forward_features(feats)
+            steady = pkg.launch_count() - n0
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32_conv, tf32_mm
+    # per layer: fused forward + 5 x (weight split + GEMM) + 2 x add-LayerNorm; 5 GroupNorms x 2; 2 transposes; bias;
+    # the first call also builds the two layers' query tables (weight split + GEMM each)
+    assert steady == 2 * (1 + 5 * 2 + 2) + 5 * 2 + 2 + 1 and first == steady + 2 * 2
+    for a, b, c in zip([want[0], want[1], *want[2]], [got[0], got[1], *got[2]], [again[0], again[1], *again[2]]):
+        assert torch.equal(b, c)
+        assert (a - b).abs().max().item() <= 2e-4 * max(1.0, a.abs().max().item()), (a - b).abs().max().item()
