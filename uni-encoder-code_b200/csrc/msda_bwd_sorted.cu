@@ -25,15 +25,16 @@
 //            rank); corners outside every window are appended behind the sorted ones -- they
 //            are processed by the same loop as runs of length one, so correctness never
 //            depends on the windows, only the amount of merging does;
-//   merge    the record array is cut into equal slices, one per 8-lane group (lane = 16 bytes
-//            of a 128-byte row).  A group walks its slice: at the first record of a pixel it
-//            loads that pixel's value row ONCE (one LDG.128 per lane), then per record reads the
-//            query's grad_output row from shared memory, accumulates weight * grad_output in
-//            registers and forms its part of the dot product D = <value row, grad_output row>;
-//            when the pixel changes the accumulator leaves as ONE red.global.add.v4.f32 per
-//            lane.  A run cut by a slice boundary is simply flushed by both groups.  Eight
-//            records' partial dot products are summed over the 8 lanes with a 7-shuffle
-//            reduce-scatter and land in D[query][point][corner] in shared memory;
+//   merge    the record array is cut into equal slices, one per GW-lane group (GW = 4 shipped: a lane owns
+//            two 16-byte chunks of a 128-byte row; GW = 8: one), slices interleaved over the warps.  A
+//            group walks its slice: at the first record of a pixel it loads that pixel's value row ONCE,
+//            then per record reads the query's grad_output row from shared memory, accumulates
+//            weight * grad_output in registers (packed fma.rn.f32x2) and forms its part of the dot
+//            product D = <value row, grad_output row>; when the pixel changes the accumulator leaves as
+//            ONE red.global.add.v4.f32 per lane and chunk.  A run cut by a slice boundary is simply
+//            flushed by both groups.  The partial dot products of a body of records are summed over the
+//            group's lanes with a shuffle reduce-scatter and land in D[query][point][corner] in shared
+//            memory;
 //   epilogue one sampling point per thread again: grad_attn_weight and grad_sampling_loc are the
 //            reference's linear combinations of the point's four D (cuh:128-163), written with
 //            coalesced stores.  Both are deterministic and need no zero fill.
