@@ -326,13 +326,15 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 }
 
 // ---------------------------------------------------------------------------
-// Kernel with the A operand in tensor memory (the default for in_features < 512; linear_variant 4 forces it).  With both operands in shared memory a
+// Kernel with the A operand in tensor memory (the default).  With both operands in shared memory a
 // 128 x 128 x 8 tf32 MMA reads 8 KB for 64 cycles of math and the shared-memory data pipe is the limit
 // (profiles/r1_linear.md).  Here the split warps write x_hi (the raw words) and x_lo of their 32 rows into a
 // 4-slot ring in TMEM with tcgen05.st (lane = row, 32 columns = the 32 k of a k-block) and the MMAs take A
 // from there ([tmem] operand form): operand reads from shared memory are halved and x_lo is never stored
-// to shared memory.  TMEM: {main, small} accumulators (2 * BN columns, one set: the epilogue is not
-// overlapped with the next tile's MMAs) + 4 x 64 columns of A.
+// to shared memory.  TMEM: {main, small} accumulators (2 * BN columns, one set: the epilogue warps drain it
+// into registers at once and hand it back, their transposes and stores overlap the next tile's MMAs) +
+// 4 x 64 columns of A.  Epilogue buffer: 32 x 32 floats per warp, XOR-swizzled 16-byte chunks (kEpiBytes
+// keeps round 1's padded size).
 // ---------------------------------------------------------------------------
 template <int BN>
 struct LinCfgT {
