@@ -168,6 +168,17 @@ int msda_b200_linear_f32(const float *x, const float *weight, const float *bias,
                          void *stream);
 
 /*
+ * The same GEMM for a weight that does not change between calls (inference): msda_b200_split_weight_f32 writes
+ * the split weight (tf32(W) followed by tf32(W - tf32(W)), 2 * out_features * in_features floats) once,
+ * msda_b200_linear_presplit_f32 then runs the GEMM alone -- one launch per Linear instead of two, bit-identical
+ * results.  Same shape / alignment requirements; MSDA_ERR_UNSUPPORTED otherwise.
+ */
+int msda_b200_split_weight_f32(const float *weight, float *split_weight, int out_features, int in_features,
+                               void *stream);
+int msda_b200_linear_presplit_f32(const float *x, const float *split_weight, const float *bias, float *y,
+                                  int rows, int out_features, int in_features, int relu, void *stream);
+
+/*
  * y[rows, cols] = LayerNorm(x + residual) * gamma + beta over the last dimension (eps inside the square
  * root, biased variance: torch.nn.functional.layer_norm semantics) -- the `norm(src + sublayer(src))`
  * steps of the encoder layer (msdeformattn.py:134-141) in one pass.  residual may be NULL.

@@ -210,11 +210,11 @@ def test_encoder_with_shared_position_embedding_folds_src_plus_pos_into_the_quer
             n3 = pkg.launch_count()
     finally:
         torch.backends.cuda.matmul.allow_tf32 = old
-    per_layer_unfolded = 1 + 6 * 2 + 2          # MSDA forward, 6 x (weight split + GEMM), 2 x add + LayerNorm
-    per_layer_folded = 1 + 5 * 2 + 2            # offsets and logits are ONE GEMM
+    per_layer_unfolded = 1 + 6 * 2 + 2          # MSDA forward, 6 x (weight split + GEMM) on first use, 2 x add + LayerNorm
+    per_layer_folded = 1 + 5 + 2                # offsets and logits are ONE GEMM; split weights are cached per layer
     assert n1 - n0 == 2 * per_layer_unfolded
-    assert n2 - n1 == 2 * (per_layer_folded + 2)            # first call: + the pos W^T + b table (split + GEMM)
-    assert n3 - n2 == 2 * per_layer_folded                  # afterwards the table is cached
+    assert n2 - n1 == 2 * (per_layer_folded + 2)            # first call: + split of the stacked weight + the table GEMM
+    assert n3 - n2 == 2 * per_layer_folded                  # afterwards table and split weights are cached
     assert torch.equal(folded, again)
     assert (folded - unfolded).abs().max().item() <= 2e-5, (folded - unfolded).abs().max().item()
     assert (folded - want).abs().max().item() <= 5e-5, (folded - want).abs().max().item()

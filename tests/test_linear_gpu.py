@@ -517,3 +517,32 @@ def test_group_norm_rows_needs_32_channel_blocks(pkg):
     norm = torch.nn.GroupNorm(4, 16).to(DEV)
     x = torch.randn(1, 16, 4, 4, device=DEV)
     assert not pkg.ops.group_norm_rows_supported(x, norm, torch.empty(1, 16, 16, device=DEV))
+
+
+def test_presplit_weight_gives_the_same_bits_with_one_launch(pkg):
+    x, w, b = case(900, 256, 256, seed=21)
+    want = pkg.linear_tf32x3(x, w, b, relu=True)
+    n0 = pkg.launch_count()
+    split = pkg.ops.split_weight(w)
+    assert pkg.launch_count() - n0 == 1 and split.numel() == 2 * w.numel()
+    n0 = pkg.launch_count()
+    got = pkg.linear_tf32x3(x, w, b, relu=True, presplit=split)
+    assert pkg.launch_count() - n0 == 1
+    assert torch.equal(got, want)
+    xl, wl, bl = case(130, 256, 1024, seed=22)                         # long reduction (chunked accumulation)
+    assert torch.equal(pkg.linear_tf32x3(xl, wl, bl, presplit=pkg.ops.split_weight(wl)), pkg.linear_tf32x3(xl, wl, bl))
+    with pytest.raises(RuntimeError, match="presplit must be"):
+        pkg.linear_tf32x3(x, w, b, presplit=split[:-4])
+    # the mirror caches the split per weight version
+    lin = torch.nn.Linear(256, 256).to(DEV)
+    with torch.no_grad():
+        n0 = pkg.launch_count()
+        y1 = pkg.modules._linear(lin, x, "tf32x3")
+        n1 = pkg.launch_count()
+        y2 = pkg.modules._linear(lin, x, "tf32x3")
+        n2 = pkg.launch_count()
+        lin.weight.mul_(2.0)                                            # in-place update: the split is rebuilt
+        y3 = pkg.modules._linear(lin, x, "tf32x3")
+        n3 = pkg.launch_count()
+    assert (n1 - n0, n2 - n1, n3 - n2) == (2, 1, 2) and torch.equal(y1, y2)
+    assert (y3 - (2.0 * (y1 - lin.bias) + lin.bias)).abs().max().item() <= 1e-4

@@ -75,8 +75,11 @@ def test_mirror_plus_cuda_op_matches_reference_pixel_decoder_golden(pkg, fused, 
     # + statistics and apply kernel of the fused GroupNorm for the four maps whose plane is a multiple
     # of 4 here: the stride-8 and stride-16 input projections, the lateral and the output convolution at stride 4;
     # + one transpose per image for the NCHW copy of the finest encoder level + the mask_features bias)
+    # with fused=True (2 heads of 32 channels: the fused kernels apply) the two query projections are ONE stacked
+    # GEMM on `src` (its weight split once, + the table GEMM on the first call): 5 + 6 instead of 6 x 2 per layer
     n_img = next(iter(feats.values())).shape[0]
-    assert pkg.launch_count() - n0 == (2 if linear == "torch" else 2 + 2 * 6 * 2 + 4 * 2 + n_img + 1)
+    per_layer = 1 + (5 + 6 if fused else 6 * 2)
+    assert pkg.launch_count() - n0 == (2 if linear == "torch" else 2 * per_layer + 4 * 2 + n_img + 1)
     check(outs, g, 5e-4)
 
 
@@ -157,9 +160,9 @@ def test_full_width_decoder_with_every_inference_kernel_matches_the_torch_path(p
             steady = pkg.launch_count() - n0
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32_conv, tf32_mm
-    # per layer: fused forward + 5 x (weight split + GEMM) + 2 x add-LayerNorm; 5 GroupNorms x 2; 2 transposes; bias;
-    # the first call also builds the two layers' query tables (weight split + GEMM each)
-    assert steady == 2 * (1 + 5 * 2 + 2) + 5 * 2 + 2 + 1 and first == steady + 2 * 2
+    # per layer: fused forward + 5 GEMMs + 2 x add-LayerNorm; 5 GroupNorms x 2; 2 transposes; bias; the first call
+    # also splits the weights (4 Linears + the stacked query weight per layer) and builds the query tables (a GEMM each)
+    assert steady == 2 * (1 + 5 + 2) + 5 * 2 + 2 + 1 and first == steady + 2 * (5 + 1)
     for a, b, c in zip([want[0], want[1], *want[2]], [got[0], got[1], *got[2]], [again[0], again[1], *again[2]]):
         assert torch.equal(b, c)
         assert (a - b).abs().max().item() <= 2e-4 * max(1.0, a.abs().max().item()), (a - b).abs().max().item()

@@ -691,10 +691,12 @@ cudaError_t launch_linear_atmem(const float *x, const float *w, const float *bia
     CUtensorMap mx, mwh, mwl;
     if (!make_map(&mx, x, M, K, kBM) || !make_map(&mwh, whi, N, K, BN) || !make_map(&mwl, wlo, N, K, BN))
         return cudaErrorInvalidValue;
-    const long long n4 = (long long)N * K / 4;
-    split_weight_kernel<<<(unsigned)((n4 + 255) / 256 < 592 ? (n4 + 255) / 256 : 592), 256, 0, stream>>>(
-        reinterpret_cast<const float4 *>(w), reinterpret_cast<float4 *>(whi), reinterpret_cast<float4 *>(wlo), n4);
-    note_launch();
+    if (w != nullptr) {              // nullptr: the workspace already holds the split weight (launch_split_weight)
+        const long long n4 = (long long)N * K / 4;
+        split_weight_kernel<<<(unsigned)((n4 + 255) / 256 < 592 ? (n4 + 255) / 256 : 592), 256, 0, stream>>>(
+            reinterpret_cast<const float4 *>(w), reinterpret_cast<float4 *>(whi), reinterpret_cast<float4 *>(wlo), n4);
+        note_launch();
+    }
     const long long tiles = (long long)((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
     const long long grid = tiles < sm_count() ? tiles : sm_count();
     // accumulation chunks of 8 k-blocks (256 of the reduction) -- see the epilogue
@@ -704,7 +706,26 @@ cudaError_t launch_linear_atmem(const float *x, const float *w, const float *bia
     return cudaGetLastError();
 }
 
+// tile width: 128 columns, or 96 when that wastes fewer (N = 96, 192, 288 ...)
+bool narrow_tile(int N) { return (N + 95) / 96 * 96 - N < (N + 127) / 128 * 128 - N; }
+
 }  // namespace
+
+// split[0 .. N*K) = tf32(w), split[N*K .. 2*N*K) = tf32(w - tf32(w)): what launch_linear_tf32x3 does per call when
+// it is given the weight; done once by callers whose weight does not change between calls (inference)
+cudaError_t launch_split_weight(const float *w, float *split, int N, int K, cudaStream_t stream, bool *handled) {
+    *handled = false;
+    if (N <= 0 || K <= 0 || ((long long)N * K) % 4 != 0 ||
+        (reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(split)) % 16 != 0)
+        return cudaSuccess;
+    *handled = true;
+    const long long n4 = (long long)N * K / 4;
+    split_weight_kernel<<<(unsigned)((n4 + 255) / 256 < 592 ? (n4 + 255) / 256 : 592), 256, 0, stream>>>(
+        reinterpret_cast<const float4 *>(w), reinterpret_cast<float4 *>(split),
+        reinterpret_cast<float4 *>(split + (size_t)N * K), n4);
+    note_launch();
+    return cudaGetLastError();
+}
 
 // y[M, N] = x[M, K] * w[N, K]^T + bias[N]; K % 32 == 0, 16-byte aligned rows; workspace: 2*N*K floats
 cudaError_t launch_linear_tf32x3(const float *x, const float *w, const float *bias, float *y, int M, int N, int K,
@@ -713,13 +734,15 @@ cudaError_t launch_linear_tf32x3(const float *x, const float *w, const float *bi
     if (M <= 0 || N <= 0 || K <= 0 || K % kBK != 0 || N % 4 != 0 ||
         (reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(workspace) |
          reinterpret_cast<uintptr_t>(y)) % 16 != 0 ||
-        ((long long)K * 4) % 16 != 0) {
+        ((long long)K * 4) % 16 != 0 || (w == nullptr && workspace == nullptr)) {
         *handled = false;
         return cudaSuccess;
     }
-    // tile width: 128 columns, or 96 when that wastes fewer (N = 96, 192, 288 ...)
-    const int waste128 = (N + 127) / 128 * 128 - N, waste96 = (N + 95) / 96 * 96 - N;
-    const bool narrow = waste96 < waste128;
+    if (w == nullptr) {             // pre-split weight in the workspace: the A-in-tensor-memory kernel only
+        if (narrow_tile(N)) return launch_linear_atmem<96>(x, nullptr, bias, y, M, N, K, relu, workspace, stream);
+        return launch_linear_atmem<128>(x, nullptr, bias, y, M, N, K, relu, workspace, stream);
+    }
+    const bool narrow = narrow_tile(N);
     const int variant = option_value(OPT_LINEAR_VARIANT);
     if (workspace == nullptr) {
         // one-shot weight: split inside the kernel; long reductions (the use case) -> four accumulators

@@ -41,6 +41,7 @@ cudaError_t launch_bwd_generic(const T *, const T *, const int64_t *, const int6
                                const T *, const Dims &, T *, T *, T *, cudaStream_t);
 cudaError_t launch_linear_tf32x3(const float *, const float *, const float *, float *, int, int, int, int,
                                  float *, cudaStream_t, bool *handled);
+cudaError_t launch_split_weight(const float *, float *, int, int, cudaStream_t, bool *handled);
 cudaError_t launch_add_layernorm(const float *, const float *, const float *, const float *, float *, long long,
                                  int, float, cudaStream_t, bool *handled);
 cudaError_t launch_add_layernorm_bwd(const float *, const float *, const float *, const float *, float *, float *,
@@ -327,6 +328,28 @@ int msda_b200_linear_f32(const float *x, const float *weight, const float *bias,
     bool handled = false;
     cudaError_t e = launch_linear_tf32x3(x, weight, bias, y, rows, out_features, in_features, relu,
                                          workspace, (cudaStream_t)stream, &handled);
+    if (e == cudaSuccess && !handled) return MSDA_ERR_UNSUPPORTED;
+    return (int)e;
+}
+
+int msda_b200_split_weight_f32(const float *weight, float *split_weight, int out_features, int in_features,
+                               void *stream) {
+    if (!weight || !split_weight) return MSDA_ERR_NULL_POINTER;
+    if (out_features <= 0 || in_features <= 0) return MSDA_ERR_BAD_SHAPE;
+    bool handled = false;
+    cudaError_t e = launch_split_weight(weight, split_weight, out_features, in_features, (cudaStream_t)stream, &handled);
+    if (e == cudaSuccess && !handled) return MSDA_ERR_UNSUPPORTED;
+    return (int)e;
+}
+
+int msda_b200_linear_presplit_f32(const float *x, const float *split_weight, const float *bias, float *y, int rows,
+                                  int out_features, int in_features, int relu, void *stream) {
+    if (!x || !split_weight || !y) return MSDA_ERR_NULL_POINTER;
+    if (rows <= 0 || out_features <= 0 || in_features <= 0) return MSDA_ERR_BAD_SHAPE;
+    bool handled = false;
+    // the kernel only reads the split weight
+    cudaError_t e = launch_linear_tf32x3(x, nullptr, bias, y, rows, out_features, in_features, relu,
+                                         const_cast<float *>(split_weight), (cudaStream_t)stream, &handled);
     if (e == cudaSuccess && !handled) return MSDA_ERR_UNSUPPORTED;
     return (int)e;
 }

@@ -74,6 +74,18 @@ def _version_of(t: torch.Tensor) -> int:
     return -1 if t.is_inference() else t._version
 
 
+def _presplit_of(layer: nn.Linear):
+    """The split form of `layer.weight` for the inference GEMM, computed once per weight version (the weight does
+    not change between inference calls; an in-place update or a new tensor rebuilds it)."""
+    w = layer.weight
+    key = (w.data_ptr(), _version_of(w), tuple(w.shape), str(w.device))
+    hit = layer.__dict__.get("_tf32x3_presplit")
+    if hit is None or hit[0] != key:
+        hit = (key, ops.split_weight(w))
+        layer.__dict__["_tf32x3_presplit"] = hit
+    return hit[1]
+
+
 def _linear(layer: nn.Linear, x, impl: str, relu: bool = False):
     """``layer(x)`` (+ ReLU).  impl == "tf32x3" selects the inference kernels of SURVEY 8f.3 (this GEMM and the
     fused residual + LayerNorm of `_add_norm`): in inference (autograd off) the fp32 GEMM runs on the
@@ -82,7 +94,7 @@ def _linear(layer: nn.Linear, x, impl: str, relu: bool = False):
     torch GEMM); for any shape the kernel does not cover torch's own fp32 GEMM is used as in the reference."""
     if impl == "tf32x3" and not torch.is_grad_enabled() and x.is_contiguous() \
             and ops.linear_tf32x3_supported(x, layer.weight):
-        return ops.linear_tf32x3(x, layer.weight, layer.bias, relu=relu)
+        return ops.linear_tf32x3(x, layer.weight, layer.bias, relu=relu, presplit=_presplit_of(layer))
     if impl == "tf32x3" and torch.is_grad_enabled() and LinearTF32x3Function.supported(x, layer.weight):
         # all three GEMMs on the tensor cores; the ReLU rides in the forward GEMM's epilogue
         return LinearTF32x3Function.apply(x, layer.weight, layer.bias, relu)
@@ -217,17 +229,19 @@ class MSDeformAttn(nn.Module):
 
     def _query_projection(self, pos_rows):
         """(stacked weight [3*M*L*P, C] of sampling_offsets and attention_weights, table [S, 3*M*L*P] =
-        pos_rows @ weight^T + stacked bias), rebuilt when a parameter or the embedding changes."""
+        pos_rows @ weight^T + stacked bias, the stacked weight in split form), rebuilt when a parameter or the
+        embedding changes."""
         params = (self.sampling_offsets.weight, self.sampling_offsets.bias,
                   self.attention_weights.weight, self.attention_weights.bias)
         key = tuple((t.data_ptr(), _version_of(t)) for t in params + (pos_rows,)) + (tuple(pos_rows.shape),)
         if getattr(self, "_qproj_key", None) != key:
             weight = torch.cat((params[0], params[2]), 0).contiguous()
             bias = torch.cat((params[1], params[3]), 0).contiguous()
+            split = ops.split_weight(weight)
             # the table keeps `pos_rows` referenced so that its memory cannot be handed to other data
-            self._qproj = (weight, ops.linear_tf32x3(pos_rows, weight, bias), pos_rows)
+            self._qproj = (weight, ops.linear_tf32x3(pos_rows, weight, bias, presplit=split), pos_rows, split)
             self._qproj_key = key
-        return self._qproj[0], self._qproj[1]
+        return self._qproj[0], self._qproj[1], self._qproj[3]
 
     def forward_shared_pos(self, src, pos, reference_points, input_spatial_shapes, input_level_start_index,
                            value=None):
@@ -239,8 +253,8 @@ class MSDeformAttn(nn.Module):
         ranks are still in flight while the query GEMM runs); default: `project_value(src)`."""
         if value is None:
             value = self.project_value(src)
-        weight, table = self._query_projection(pos[0])
-        proj = ops.linear_tf32x3(src, weight, None)
+        weight, table, split = self._query_projection(pos[0])
+        proj = ops.linear_tf32x3(src, weight, None, presplit=split)
         if callable(value):
             value = value()
         ref = reference_points

@@ -298,8 +298,24 @@ def linear_tf32x3_supported(x, weight) -> bool:
             and weight.size(1) % 32 == 0 and weight.size(0) % 4 == 0 and x.numel() > 0)
 
 
-def linear_tf32x3(x, weight, bias=None, relu=False, split_weight_in_kernel=False):
+def split_weight(weight):
+    """The split form of a Linear weight that ``linear_tf32x3(..., presplit=...)`` consumes: ``tf32(W)`` followed by
+    ``tf32(W - tf32(W))`` as one flat fp32 tensor of 2 * out * in elements (msda_b200_split_weight_f32).  For weights
+    that do not change between calls (inference): one launch per Linear instead of two."""
+    if not (isinstance(weight, torch.Tensor) and weight.is_cuda and weight.dtype == torch.float32 and weight.dim() == 2
+            and weight.is_contiguous() and weight.numel() % 4 == 0 and weight.numel() > 0):
+        raise RuntimeError("split_weight needs a contiguous 2-d fp32 CUDA weight")
+    out = torch.empty(2 * weight.numel(), dtype=torch.float32, device=weight.device)
+    with torch.cuda.device(weight.device):
+        rc = _lib.lib.msda_b200_split_weight_f32(weight.data_ptr(), out.data_ptr(), weight.size(0), weight.size(1),
+                                                 torch.cuda.current_stream(weight.device).cuda_stream)
+    _lib.check(rc, "split_weight")
+    return out
+
+
+def linear_tf32x3(x, weight, bias=None, relu=False, split_weight_in_kernel=False, presplit=None):
     """``F.linear(x, weight, bias)`` (then ``relu`` if set) for fp32 CUDA tensors; ``x`` [..., in],
+    ``presplit``: ``split_weight(weight)`` computed earlier -- the GEMM then runs alone (same bits);
     ``weight`` [out, in] with in % 32 == 0 and out % 4 == 0.  Non-finite inputs give non-finite outputs in
     the affected rows, but an infinite input may come out as NaN where F.linear returns +-inf (the
     error-compensated split forms inf - inf and inf * w_lo of either sign).  ``split_weight_in_kernel``: no pre-pass over
@@ -318,6 +334,17 @@ def linear_tf32x3(x, weight, bias=None, relu=False, split_weight_in_kernel=False
     out_f, in_f = weight.shape
     rows = x.numel() // in_f
     y = torch.empty(x.shape[:-1] + (out_f,), dtype=x.dtype, device=x.device)
+    if presplit is not None:
+        if not (presplit.is_cuda and presplit.device == x.device and presplit.dtype == torch.float32
+                and presplit.is_contiguous() and presplit.numel() == 2 * out_f * in_f):
+            raise RuntimeError("presplit must be split_weight(weight) on x's device")
+        with torch.cuda.device(x.device):
+            rc = _lib.lib.msda_b200_linear_presplit_f32(x.data_ptr(), presplit.data_ptr(),
+                                                        bias.data_ptr() if bias is not None else None, y.data_ptr(),
+                                                        rows, out_f, in_f, 1 if relu else 0,
+                                                        torch.cuda.current_stream(x.device).cuda_stream)
+        _lib.check(rc, "linear_tf32x3")
+        return y
     workspace = None if split_weight_in_kernel else \
         torch.empty(2 * out_f * in_f, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
