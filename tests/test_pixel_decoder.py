@@ -166,3 +166,27 @@ def test_full_width_decoder_with_every_inference_kernel_matches_the_torch_path(p
     for a, b, c in zip([want[0], want[1], *want[2]], [got[0], got[1], *got[2]], [again[0], again[1], *again[2]]):
         assert torch.equal(b, c)
         assert (a - b).abs().max().item() <= 2e-4 * max(1.0, a.abs().max().item()), (a - b).abs().max().item()
+
+
+@pytest.mark.gpu
+def test_caches_are_not_filled_during_graph_capture(pkg):
+    """A graph captured on a model whose per-module caches (split weights, query tables, position rows, sine
+    embedding) are still cold must not leave un-materialised tensors in them: an eager call after the capture, and
+    the replay, both give the result of a normally warmed model."""
+    warm, feats, g = build(pkg, device="cuda:0", fused=True, linear="tf32x3")
+    cold, _, _ = build(pkg, device="cuda:0", fused=True, linear="tf32x3")
+    with torch.no_grad():
+        want = warm.forward_features(feats)            # also fills the module-global shape caches (host -> device copies)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            torch.zeros(1, device="cuda:0")            # the side stream exists and is idle
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = cold.forward_features(feats)
+        eager = cold.forward_features(feats)           # right after the capture, before any replay
+        graph.replay()
+        torch.cuda.synchronize()
+    for a, b, c in zip([want[0], want[1], *want[2]], [eager[0], eager[1], *eager[2]], [out[0], out[1], *out[2]]):
+        assert torch.equal(a, b) and torch.equal(a, c)

@@ -74,6 +74,12 @@ def _version_of(t: torch.Tensor) -> int:
     return -1 if t.is_inference() else t._version
 
 
+def _capturing(t: torch.Tensor) -> bool:
+    """True while a CUDA graph is being captured on the current stream: results computed now are not materialised
+    until the graph is replayed, so nothing computed during capture may be kept in a cache that eager calls read."""
+    return t.is_cuda and torch.cuda.is_current_stream_capturing()
+
+
 def _presplit_of(layer: nn.Linear):
     """The split form of `layer.weight` for the inference GEMM, computed once per weight version (the weight does
     not change between inference calls; an in-place update or a new tensor rebuilds it)."""
@@ -82,7 +88,8 @@ def _presplit_of(layer: nn.Linear):
     hit = layer.__dict__.get("_tf32x3_presplit")
     if hit is None or hit[0] != key:
         hit = (key, ops.split_weight(w))
-        layer.__dict__["_tf32x3_presplit"] = hit
+        if not _capturing(w):
+            layer.__dict__["_tf32x3_presplit"] = hit
     return hit[1]
 
 
@@ -239,8 +246,10 @@ class MSDeformAttn(nn.Module):
             bias = torch.cat((params[1], params[3]), 0).contiguous()
             split = ops.split_weight(weight)
             # the table keeps `pos_rows` referenced so that its memory cannot be handed to other data
-            self._qproj = (weight, ops.linear_tf32x3(pos_rows, weight, bias, presplit=split), pos_rows, split)
-            self._qproj_key = key
+            built = (weight, ops.linear_tf32x3(pos_rows, weight, bias, presplit=split), pos_rows, split)
+            if _capturing(pos_rows):
+                return built[0], built[1], built[3]
+            self._qproj, self._qproj_key = built, key
         return self._qproj[0], self._qproj[1], self._qproj[3]
 
     def forward_shared_pos(self, src, pos, reference_points, input_spatial_shapes, input_level_start_index,
@@ -435,10 +444,14 @@ class MSDeformAttnTransformerEncoderOnly(nn.Module):
             key = (tuple((p.data_ptr(), _version_of(p), tuple(p.shape), tuple(p.stride())) for p in pos_embeds),
                    self.level_embed.data_ptr(), _version_of(self.level_embed))
             if getattr(self, "_pos_cache_key", None) != key:
-                # the position tensors are kept referenced so their memory cannot be handed to other data
-                self._pos_cache_key, self._pos_cache_src = key, list(pos_embeds)
-                self._pos_cache = self._level_pos(pos_embeds)
-            pos = self._pos_cache
+                if _capturing(pos_embeds[0]):
+                    pos = self._level_pos(pos_embeds)          # not kept: see _capturing
+                else:
+                    # the position tensors are kept referenced so their memory cannot be handed to other data
+                    self._pos_cache_key, self._pos_cache_src = key, list(pos_embeds)
+                    self._pos_cache = pos = self._level_pos(pos_embeds)
+            else:
+                pos = self._pos_cache
         shapes, lsi = level_tensors_for(levels, src.device)
         return src, pos, shapes, lsi, levels
 

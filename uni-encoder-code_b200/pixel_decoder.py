@@ -24,7 +24,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
-from .modules import CoreFn, MSDeformAttnTransformerEncoderOnly, ShapeCache
+from .modules import CoreFn, MSDeformAttnTransformerEncoderOnly, ShapeCache, _capturing
 
 
 class PositionEmbeddingSine(nn.Module):
@@ -58,7 +58,9 @@ class PositionEmbeddingSine(nn.Module):
         key = (x.shape[2], x.shape[3], str(x.device))
         pos = self._cache.get(key)
         if pos is None:
-            pos = self._cache.put(key, self._build(x.shape[2], x.shape[3], x.device))
+            pos = self._build(x.shape[2], x.shape[3], x.device)
+            if not _capturing(x):                      # built during a graph capture: not materialised yet, not kept
+                self._cache.put(key, pos)
         return pos.expand(x.shape[0], -1, -1, -1)
 
 
