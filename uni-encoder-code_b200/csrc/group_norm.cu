@@ -261,6 +261,9 @@ cudaError_t launch_group_norm_rows(const float *x, const float *cbias, const flo
     const int cpg = C / groups;
     const long long chunk = (long long)cpg * hw;
     if (cbias != nullptr && chunk > 0x7fffffffLL) return cudaSuccess;
+    const long long per_cta = 32LL * kRowsWarps * kRowsTilesPerWarp;
+    const long long parts = (hw + per_cta - 1) / per_cta;
+    if (parts > 65535) return cudaSuccess;
     *handled = true;
     const dim3 sgrid((unsigned)(N * groups), kGnSplit);
     if (cbias != nullptr)
@@ -270,9 +273,6 @@ cudaError_t launch_group_norm_rows(const float *x, const float *cbias, const flo
     note_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    const long long per_cta = 32LL * kRowsWarps * kRowsTilesPerWarp;
-    const long long parts = (hw + per_cta - 1) / per_cta;
-    if (parts > 65535) { *handled = false; return cudaSuccess; }
     group_apply_rows_kernel<<<dim3((unsigned)(N * (C / 32)), (unsigned)parts), kRowsWarps * 32, 0, stream>>>(
         x, workspace, gamma, beta, y, C, hw, cpg, eps, cbias, row_stride, image_stride, relu);
     note_launch();
