@@ -15,7 +15,7 @@
 // One work item = (image n, head m, tile of 128 queries = 8 x 16 pixels of one level).  Per item:
 //   pass A   one sampling point per thread: decompose() (the same single home of the integer
 //            work as every other kernel), and for each contributing corner whose pixel lies in
-//            the item's per-level WINDOW (tile footprint +- 9 px, clipped to the level) the
+//            the item's per-level WINDOW (tile footprint +- 7 px, clipped to the level) the
 //            counter of that pixel is incremented (integer shared-memory atomics: 0.84 cycles
 //            per warp instruction measured; fp32 ones are CAS loops).  The point's window slots,
 //            first pixel, fractions and weight stay in registers for pass B;
@@ -51,7 +51,7 @@
 namespace msda {
 
 constexpr int kSortTileMax = 256;        // queries per item: 7 or 8 bits of the record word
-constexpr int kSortMargin = 9;           // window = tile footprint +- this many pixels
+constexpr int kSortMargin = 7;           // window = tile footprint +- this many pixels (5..7 measured equal, 9: +0.8 %, 4: +2 %)
 constexpr uint32_t kNoKey = 0x3ffffu;    // pixel field of an absent record (7-bit query slot); S < kNoKey (host check)
 constexpr uint32_t kSlotNone = 0xffffu;  // pass A -> pass B: corner does not contribute
 constexpr uint32_t kSlotTail = 0xfffeu;  //                   corner outside every window
