@@ -468,7 +468,7 @@ __device__ __forceinline__ void phase1_records(const LevelTable &lt, uint2 *rec,
 // query.  The verdict is therefore identical everywhere; the kernel it goes against returns at once.
 // Must be called by all threads of the CTA, after fill_level_table() + __syncthreads().
 // ---------------------------------------------------------------------------
-constexpr int kProbeSamples = 1024;
+constexpr int kProbeSamples = 512;      // one per thread of a 16-warp CTA: one round of loads (1024: + 2 us per backward)
 constexpr float kProbeMarginPx = 8.f;     // kSortMargin - 1 (msda_bwd_sorted.cu)
 enum { GATE_NONE = 0, GATE_RUN_IF_LOCAL = 1, GATE_RUN_IF_SPREAD = 2 };
 
