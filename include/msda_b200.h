@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define MSDA_B200_ABI_VERSION 1
+#define MSDA_B200_ABI_VERSION 2
 
 enum {
     MSDA_OK = 0,

@@ -32,7 +32,7 @@ def test_header_symbols_all_exported(pkg):
 
 def test_abi_version_and_error_strings(pkg):
     lib = pkg._lib.lib
-    assert lib.msda_b200_abi_version() == 1
+    assert lib.msda_b200_abi_version() == 2          # round 2: new entry points, group_norm gained channel_bias
     assert lib.msda_b200_error_string(0) == b"success"
     for code in (-1, -2, -3, -4):
         assert b"msda_b200" in lib.msda_b200_error_string(code)

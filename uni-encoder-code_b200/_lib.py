@@ -12,7 +12,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 # MSDA_B200_LIB selects another build of the same ABI (the bounds-checked one of `make checked`)
 LIB_PATH = os.environ.get("MSDA_B200_LIB") or os.path.join(_PKG, "lib", "libmsda_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # name -> (restype, argtypes); must list every symbol of include/msda_b200.h
 _P = ctypes.c_void_p
