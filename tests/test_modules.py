@@ -219,3 +219,31 @@ def test_shape_keyed_caches_are_bounded(pkg):
     assert len(pe._cache) <= pe._cache.maxsize <= 16
     a = pe(torch.zeros(1, 1, 5, 4))
     assert torch.equal(a, pe(torch.zeros(2, 1, 5, 4))[:1])                 # hit == rebuilt
+
+
+def test_batch_shared_position_embedding_and_preflattened_input_on_cpu(pkg, oracle):
+    """Host logic of the round-2 inference path, without a GPU: a position embedding shared by the batch
+    (stride 0) stays ONE copy of the rows broadcast over the batch; the folded-projection path and the split-weight
+    cache never engage on the CPU; pre-flattened rows give the same result as the per-level maps."""
+    m, g = build_small(pkg, core=oracle_core(oracle), dtype=torch.float32)
+    srcs = [torch.from_numpy(g[f"src{i}"]).float() for i in range(3)]
+    one = [torch.from_numpy(g[f"pos{i}"]).float()[:1] for i in range(3)]
+    n = srcs[0].shape[0]
+    shared = [p.expand(n, -1, -1, -1) for p in one]
+    copies = [p.expand(n, -1, -1, -1).contiguous() for p in one]
+    with torch.no_grad():
+        src, pos, shapes, lsi, levels = m.flatten_inputs(srcs, shared)
+        assert pos.shape[0] == n and pos.stride(0) == 0 and pos[0].is_contiguous()
+        src2, pos2, _, _, _ = m.flatten_inputs(srcs, copies)
+        assert pos2.stride(0) != 0 and torch.equal(pos.contiguous(), pos2)
+        layer = m.encoder.layers[0]
+        ref = pkg.modules.reference_points_for(levels, "cpu").expand(n, -1, -1, -1)
+        assert not layer.self_attn.can_fold_pos(src, pos, ref)          # CPU tensors, linear="torch"
+        a = m(srcs, shared)[0]
+        b = m(srcs, copies)[0]
+        c = m(None, shared, src_flat=src.clone(), levels=levels)[0]
+    assert torch.equal(a, b) and torch.equal(a, c)
+    # with autograd on, the embedding is materialised per image as the reference does
+    src3, pos3, _, _, _ = m.flatten_inputs(srcs, shared)
+    assert pos3.stride(0) != 0
+    assert "_tf32x3_presplit" not in layer.linear1.__dict__
